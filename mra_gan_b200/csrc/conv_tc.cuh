@@ -1,0 +1,621 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution kernels for sm_100a (bf16 operands, fp32 accumulate).
+//
+// Two kernels serve every eligible conv-family op (see conv_plan.h for the lowering):
+//
+//  gather_tc_kernel : D[128 positions][n_tile channels] = sum_{tap, kchunk} A_tap[128][64] * B_tap[n_tile][64]^T
+//     A tile  = one 5-D TMA box (64 ch, bw, bh, bd, 1) of the channels-last activation tensor per filter
+//               tap (zero fill out of bounds gives the implicit zero padding; element strides give
+//               stride-2), landing in shared memory as 128 rows x 128 B, SWIZZLE_128B  -> K-major A.
+//     B tile  = 2-D TMA box (64, n_tile) of the packed weights [tap*Cn + cn][ck]        -> K-major B.
+//     MMA     = tcgen05.mma.cta_group::1.kind::f16, M=128, N=n_tile, K=16, 4 per 64-channel chunk,
+//               issued by one elected thread; accumulator lives in TMEM (n_tile fp32 columns).
+//     Epilogue= 4 warps, one TMEM lane quadrant each: tcgen05.ld 32x32b.x32 -> bias/activation,
+//               optional per-(n,channel) sum / sum-of-squares for the following InstanceNorm
+//               (warp transpose-reduce, fp64 atomics), convert, 64 B vector stores.
+//
+//  wgrad_tc_kernel  : dW[tap][128 cm][n_tile cn] += sum_{positions} Mop[pos][cm] * Nop[pos'][cn]
+//     both operands are position-major in memory, i.e. MN-major for the MMA: each 64-channel chunk of
+//     a 64-position K-block is one TMA box landing as 64 rows x 128 B (SWIZZLE_128B); descriptors use
+//     the MN-major canonical layout (LBO = chunk stride 8 KiB, SBO = 1 KiB).  Split-K over position
+//     blocks, fp32 red.global.add epilogue.
+//
+// Pipeline: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue,
+// ring of STAGES shared-memory stages guarded by full/empty mbarriers; every wait is bounded and
+// reports through an error flag instead of hanging the GPU.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "conv_plan.h"
+
+namespace mra {
+namespace tc {
+
+constexpr int kThreads = 192;
+constexpr int kMaxTaps = 64;
+constexpr uint32_t kABytes = 128 * 128;          // 128 rows x 64 bf16
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: returns false (and raises the error flag) instead of hanging
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
+  for (uint32_t it = 0; it < (1u << 24); ++it)
+    if (mbar_try_wait(bar, parity)) return true;
+  if (err) atomicExch(err, code);
+  return false;
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptors (cute::UMMA::SmemDescriptor bit layout, version 1 = Blackwell)
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version | [61,64) layout (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t desc_kmajor_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint64_t desc_mnmajor_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32, a=b=BF16, M=128, N=n
+__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// Sum over the 32 lanes of each of 32 per-lane values; lane j ends up with column j's total.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float send = hi ? v[i] : v[i + n];
+      const float keep = hi ? v[i + n] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+// ------------------------------------------------------------------ gather (fprop / dgrad) kernel
+struct GatherP {
+  int tilesW, tilesH, tilesD;
+  int bw, bh, bd;
+  int Dl, Hl, Wl;
+  int astep;
+  int Cn, n_tile, kchunks, ntaps;
+  int ostep, od0, oh0, ow0;
+  long long osn, osd, osh, osw;     // output strides in elements
+  void* out;
+  int out_bf16;
+  const float* bias;
+  int act;
+  float slope;
+  double* stats;                    // [N][Cn][2] or null
+  int* err;
+  int stages;
+  uint32_t tmem_cols;
+  int8_t tdd[kMaxTaps], tdh[kMaxTaps], tdw[kMaxTaps];
+  int16_t twi[kMaxTaps];
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ GatherP P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t b_bytes = (uint32_t)P.n_tile * 128u;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + P.stages;
+  uint64_t* accum_bar = empty_bar + P.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile decode
+  int tile = blockIdx.x;
+  const int tw = tile % P.tilesW; tile /= P.tilesW;
+  const int th = tile % P.tilesH; tile /= P.tilesH;
+  const int td = tile % P.tilesD;
+  const int n = tile / P.tilesD;
+  const int lw0 = tw * P.bw, lh0 = th * P.bh, ld0 = td * P.bd;
+  const int n0 = blockIdx.y * P.n_tile;
+  const int iters = P.ntaps * P.kchunks;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % P.stages;
+        const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
+        if (!mbar_wait(&empty_bar[s], ph ^ 1u, P.err, 1)) break;
+        const int tap = it / P.kchunks, kc = it - tap * P.kchunks;
+        uint8_t* sa = smem + (size_t)s * stage_bytes;
+        mbar_expect_tx(&full_bar[s], stage_bytes);
+        tma_load_5d(sa, &tmA, &full_bar[s], kc * 64, lw0 * P.astep + P.tdw[tap], lh0 * P.astep + P.tdh[tap],
+                    ld0 * P.astep + P.tdd[tap], n);
+        tma_load_2d(sa + kABytes, &tmB, &full_bar[s], kc * 64, (int)P.twi[tap] * P.Cn + n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(P.n_tile, 0, 0);
+      bool ok = true;
+      for (int it = 0; it < iters && ok; ++it) {
+        const int s = it % P.stages;
+        const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
+        ok = mbar_wait(&full_bar[s], ph, P.err, 2);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t sb = sa + kABytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem_base, desc_kmajor_sw128(sa + k * 32), desc_kmajor_sw128(sb + k * 32), idesc,
+                   (uint32_t)((it | k) != 0));
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(accum_bar);
+    }
+  } else {
+    // epilogue warps 2..5 -> TMEM lane quadrant (warp % 4)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int lw = lw0 + row % P.bw, lh = lh0 + (row / P.bw) % P.bh, ld = ld0 + row / (P.bw * P.bh);
+    const bool valid = lw < P.Wl && lh < P.Hl && ld < P.Dl;
+    const long long obase = (long long)n * P.osn + (long long)(ld * P.ostep + P.od0) * P.osd +
+                            (long long)(lh * P.ostep + P.oh0) * P.osh + (long long)(lw * P.ostep + P.ow0) * P.osw + n0;
+    const bool ok = mbar_wait(accum_bar, 0, P.err, 3);
+    tc_fence_after();
+    if (ok) {
+      for (int c0 = 0; c0 < P.n_tile; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tmem_wait_ld();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (P.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __ldg(P.bias + n0 + c0 + j);
+        }
+        if (P.stats) {
+          float s1[32], s2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { s1[j] = valid ? v[j] : 0.f; s2[j] = s1[j] * s1[j]; }
+          const float a = warp_colsum32(s1, lane);
+          const float b = warp_colsum32(s2, lane);
+          double* st = P.stats + ((long long)n * P.Cn + n0 + c0 + lane) * 2;
+          atomicAdd(st, (double)a);
+          atomicAdd(st + 1, (double)b);
+        }
+        if (P.act != MRA_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], P.act, P.slope);
+        }
+        if (valid) {
+          if (P.out_bf16) {
+            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(P.out) + obase + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              o[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+          } else {
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + obase + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, P.tmem_cols);
+}
+
+// ------------------------------------------------------------------ wgrad kernel
+struct WgradP {
+  int tilesW, tilesH, tilesD;       // K-block boxes per dim of the dense position space
+  int bw, bh, bd;                   // box (product 64)
+  int N;
+  int sstep;
+  int m_is_shifted;
+  int Cm, Cn, n_tile;
+  int m_tiles, n_tiles, ntaps;
+  int splits;
+  float* dw;                        // [taps][Cm][Cn]
+  int* err;
+  int stages;
+  uint32_t tmem_cols;
+  int8_t tdd[kMaxTaps], tdh[kMaxTaps], tdw[kMaxTaps];
+  int16_t twi[kMaxTaps];
+};
+
+constexpr uint32_t kChunkBytes = 64 * 128;       // 64 positions x 64 bf16
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmN,
+                const __grid_constant__ WgradP P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int n_chunks = P.n_tile / 64;
+  const uint32_t stage_bytes = (2 + n_chunks) * kChunkBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + P.stages;
+  uint64_t* accum_bar = empty_bar + P.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int w = blockIdx.x;
+  const int nt = w % P.n_tiles; w /= P.n_tiles;
+  const int mt = w % P.m_tiles;
+  const int tap = w / P.m_tiles;
+  const int m0 = mt * 128, n0 = nt * P.n_tile;
+  const long long boxes_per_sample = (long long)P.tilesW * P.tilesH * P.tilesD;
+  const long long total_boxes = boxes_per_sample * P.N;
+  const long long per_split = (total_boxes + P.splits - 1) / P.splits;
+  const long long b0 = (long long)blockIdx.y * per_split;
+  long long b1 = b0 + per_split;
+  if (b1 > total_boxes) b1 = total_boxes;
+  const int iters = b1 > b0 ? (int)(b1 - b0) : 0;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmM);
+    prefetch_tmap(&tmN);
+    for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int dd = P.tdd[tap], dh = P.tdh[tap], dw_ = P.tdw[tap];
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % P.stages;
+        const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
+        if (!mbar_wait(&empty_bar[s], ph ^ 1u, P.err, 11)) break;
+        long long b = b0 + it;
+        const int n = (int)(b / boxes_per_sample);
+        int r = (int)(b - (long long)n * boxes_per_sample);
+        const int qw = (r % P.tilesW) * P.bw; r /= P.tilesW;
+        const int qh = (r % P.tilesH) * P.bh;
+        const int qd = (r / P.tilesH) * P.bd;
+        // dense coords (qw,qh,qd); shifted coords q*sstep + tap offset
+        const int sw_ = qw * P.sstep + dw_, sh_ = qh * P.sstep + dh, sd_ = qd * P.sstep + dd;
+        const int mw = P.m_is_shifted ? sw_ : qw, mh = P.m_is_shifted ? sh_ : qh, md = P.m_is_shifted ? sd_ : qd;
+        const int nw = P.m_is_shifted ? qw : sw_, nh = P.m_is_shifted ? qh : sh_, nd = P.m_is_shifted ? qd : sd_;
+        uint8_t* sa = smem + (size_t)s * stage_bytes;
+        mbar_expect_tx(&full_bar[s], stage_bytes);
+        tma_load_5d(sa, &tmM, &full_bar[s], m0, mw, mh, md, n);
+        tma_load_5d(sa + kChunkBytes, &tmM, &full_bar[s], m0 + 64, mw, mh, md, n);
+        for (int j = 0; j < n_chunks; ++j)
+          tma_load_5d(sa + (2 + j) * kChunkBytes, &tmN, &full_bar[s], n0 + 64 * j, nw, nh, nd, n);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && iters > 0) {
+      const uint32_t idesc = make_idesc(P.n_tile, 1, 1);
+      bool ok = true;
+      for (int it = 0; it < iters && ok; ++it) {
+        const int s = it % P.stages;
+        const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
+        ok = mbar_wait(&full_bar[s], ph, P.err, 12);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t sb = sa + 2 * kChunkBytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)      // 16 positions (rows of 128 B) per MMA
+          umma_f16(tmem_base, desc_mnmajor_sw128(sa + k * 2048, kChunkBytes),
+                   desc_mnmajor_sw128(sb + k * 2048, kChunkBytes), idesc, (uint32_t)((it | k) != 0));
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(accum_bar);
+    }
+  } else if (iters > 0) {
+    const int q = warp & 3;
+    const int cm = m0 + q * 32 + lane;
+    const bool valid = cm < P.Cm;
+    const bool ok = mbar_wait(accum_bar, 0, P.err, 13);
+    tc_fence_after();
+    if (ok) {
+      float* orow = P.dw + ((long long)P.twi[tap] * P.Cm + cm) * P.Cn + n0;
+      for (int c0 = 0; c0 < P.n_tile; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tmem_wait_ld();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + c0 + j),
+                         "f"(__uint_as_float(r[j])), "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])),
+                         "f"(__uint_as_float(r[j + 3]))
+                         : "memory");
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, P.tmem_cols);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// channels-last bf16 activation [N][D][H][W][C] -> 5-D map (C, W, H, D, N), box (64, bw*s, bh*s, bd*s, 1)
+inline int make_act_map(CUtensorMap* tm, const void* base, int N, int D, int H, int W, int C, int bw, int bh, int bd,
+                        int step) {
+  EncodeTiledFn fn = get_encode_fn();
+  MRA_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
+                           (cuuint64_t)D * H * W * C * 2};
+  cuuint32_t box[5] = {64, (cuuint32_t)(bw * step), (cuuint32_t)(bh * step), (cuuint32_t)(bd * step), 1};
+  cuuint32_t es[5] = {1, (cuuint32_t)step, (cuuint32_t)step, (cuuint32_t)step, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MRA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed: %d (dims %d %d %d %d %d box %d %d %d step %d)",
+              (int)r, C, W, H, D, N, bw, bh, bd, step);
+  return 0;
+}
+// packed weights [rows][Ck] bf16 -> 2-D map, box (64, box_rows)
+inline int make_weight_map(CUtensorMap* tm, const void* base, long long rows, int Ck, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  MRA_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)Ck, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Ck * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MRA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+  return 0;
+}
+
+inline uint32_t pow2_cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
+constexpr size_t kSmemLimit = 227 * 1024;
+
+// device-side error flag shared by all TC launches (checked lazily by mra_tc_error_check)
+inline int* tc_err_flag() {
+  static int* flag = nullptr;
+  if (!flag) {
+    if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(flag, 0, sizeof(int));
+  }
+  return flag;
+}
+
+inline int pick_n_tile(int cn) {
+  if (cn % 256 == 0) return 256;
+  if (cn % 128 == 0) return 128;
+  if (cn % 64 == 0) return 64;
+  return 0;
+}
+
+inline bool gather_eligible(const mra_conv_desc& d, int which) {
+  if (d.dtype != MRA_BF16 || (d.flags & MRA_CONV_FORCE_NAIVE)) return false;
+  const int ck = which == 0 ? d.cin : d.cout, cn = which == 0 ? d.cout : d.cin;
+  if (ck % 64 != 0 || pick_n_tile(cn) == 0) return false;
+  if (d.k * d.k * d.k > kMaxTaps) return false;
+  if (d.stride != 1 && d.stride != 2) return false;
+  return true;
+}
+inline bool wgrad_eligible(const mra_conv_desc& d) {
+  if (d.dtype != MRA_BF16 || (d.flags & MRA_CONV_FORCE_NAIVE)) return false;
+  if (d.cout % 64 != 0 || d.cin % 64 != 0) return false;
+  if (d.k * d.k * d.k > kMaxTaps) return false;
+  if (d.stride != 1 && d.stride != 2) return false;
+  return true;
+}
+
+// Run every launch of a gather plan on the tensor cores.
+inline int run_gather_tc(const mra_conv_desc& d, int which, const void* a, const void* b, const float* bias, void* out,
+                         double* stats, cudaStream_t st) {
+  GatherPlan plan;
+  MRA_REQUIRE(build_gather_plan(d, which, plan), "unsupported conv geometry");
+  int* err = tc_err_flag();
+  const int n_tile = pick_n_tile(plan.cn);
+  const long long rows = (long long)d.k * d.k * d.k * plan.cn;
+  CUtensorMap tmB;
+  if (int rc = make_weight_map(&tmB, b, rows, plan.ck, n_tile)) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    attr_set = true;
+  }
+  for (const GatherLaunch& L : plan.launches) {
+    MRA_REQUIRE((int)L.taps.size() <= kMaxTaps, "too many taps for the tensor-core path");
+    GatherP P;
+    memset(&P, 0, sizeof(P));
+    P.bd = L.box[0]; P.bh = L.box[1]; P.bw = L.box[2];
+    P.Dl = L.dims[0]; P.Hl = L.dims[1]; P.Wl = L.dims[2];
+    P.tilesD = (P.Dl + P.bd - 1) / P.bd; P.tilesH = (P.Hl + P.bh - 1) / P.bh; P.tilesW = (P.Wl + P.bw - 1) / P.bw;
+    P.astep = L.astep;
+    P.Cn = plan.cn; P.n_tile = n_tile; P.kchunks = plan.ck / 64; P.ntaps = (int)L.taps.size();
+    P.ostep = L.ostep; P.od0 = L.o0[0]; P.oh0 = L.o0[1]; P.ow0 = L.o0[2];
+    P.osw = plan.cn;
+    P.osh = (long long)plan.odims[2] * P.osw;
+    P.osd = (long long)plan.odims[1] * P.osh;
+    P.osn = (long long)plan.odims[0] * P.osd;
+    P.out = out; P.out_bf16 = 1;
+    P.bias = bias; P.act = which == 0 ? d.act : MRA_ACT_NONE; P.slope = d.slope;
+    P.stats = stats; P.err = err;
+    for (int i = 0; i < P.ntaps; ++i) {
+      P.tdd[i] = (int8_t)L.taps[i].dd; P.tdh[i] = (int8_t)L.taps[i].dh; P.tdw[i] = (int8_t)L.taps[i].dw;
+      P.twi[i] = (int16_t)L.taps[i].widx;
+    }
+    const size_t stage_bytes = kABytes + (size_t)n_tile * 128;
+    int stages = (int)((kSmemLimit - 2048) / stage_bytes);
+    if (stages > 6) stages = 6;
+    P.stages = stages;
+    P.tmem_cols = pow2_cols(n_tile);
+    const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+    CUtensorMap tmA;
+    if (int rc = make_act_map(&tmA, a, plan.n, plan.adims[0], plan.adims[1], plan.adims[2], plan.ck, P.bw, P.bh, P.bd,
+                              P.astep))
+      return rc;
+    dim3 grid((unsigned)((long long)plan.n * P.tilesD * P.tilesH * P.tilesW), (unsigned)(plan.cn / n_tile));
+    gather_tc_kernel<<<grid, kThreads, smem, st>>>(tmA, tmB, P);
+    MRA_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+inline int run_wgrad_tc(const mra_conv_desc& d, const void* x, const void* dy, float* dw, cudaStream_t st) {
+  WgradPlan plan;
+  MRA_REQUIRE(build_wgrad_plan(d, plan), "unsupported conv geometry");
+  int* err = tc_err_flag();
+  static bool attr_set = false;
+  if (!attr_set) {
+    MRA_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    attr_set = true;
+  }
+  WgradP P;
+  memset(&P, 0, sizeof(P));
+  P.bd = plan.box[0]; P.bh = plan.box[1]; P.bw = plan.box[2];
+  P.tilesD = (plan.qdims[0] + P.bd - 1) / P.bd; P.tilesH = (plan.qdims[1] + P.bh - 1) / P.bh;
+  P.tilesW = (plan.qdims[2] + P.bw - 1) / P.bw;
+  P.N = plan.n; P.sstep = plan.sstep; P.m_is_shifted = plan.m_is_shifted;
+  P.Cm = plan.cm; P.Cn = plan.cn;
+  P.n_tile = pick_n_tile(plan.cn);
+  P.m_tiles = (plan.cm + 127) / 128; P.n_tiles = plan.cn / P.n_tile; P.ntaps = (int)plan.taps.size();
+  P.dw = dw; P.err = err;
+  for (int i = 0; i < P.ntaps; ++i) {
+    P.tdd[i] = (int8_t)plan.taps[i].dd; P.tdh[i] = (int8_t)plan.taps[i].dh; P.tdw[i] = (int8_t)plan.taps[i].dw;
+    P.twi[i] = (int16_t)plan.taps[i].widx;
+  }
+  const size_t stage_bytes = (size_t)(2 + P.n_tile / 64) * kChunkBytes;
+  int stages = (int)((kSmemLimit - 2048) / stage_bytes);
+  if (stages > 6) stages = 6;
+  P.stages = stages;
+  P.tmem_cols = pow2_cols(P.n_tile);
+  const long long work = (long long)P.ntaps * P.m_tiles * P.n_tiles;
+  const long long total_boxes = (long long)P.tilesW * P.tilesH * P.tilesD * plan.n;
+  long long splits = ((long long)num_sms() * 3 + work - 1) / work;
+  if (splits > total_boxes) splits = total_boxes;
+  if (splits < 1) splits = 1;
+  P.splits = (int)splits;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  // M operand = dy, N operand = x; the shifted one carries the element stride
+  const int mstep = plan.m_is_shifted ? plan.sstep : 1, nstep = plan.m_is_shifted ? 1 : plan.sstep;
+  CUtensorMap tmM, tmN;
+  if (int rc = make_act_map(&tmM, dy, plan.n, plan.mdims[0], plan.mdims[1], plan.mdims[2], plan.cm, P.bw, P.bh, P.bd, mstep))
+    return rc;
+  if (int rc = make_act_map(&tmN, x, plan.n, plan.ndims[0], plan.ndims[1], plan.ndims[2], plan.cn, P.bw, P.bh, P.bd, nstep))
+    return rc;
+  dim3 grid((unsigned)work, (unsigned)splits);
+  wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(tmM, tmN, P);
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace mra

@@ -1,0 +1,347 @@
+// extern "C" entry points of libmra_b200.so (see include/mra_gan_b200.h for the contract).
+#include <stdarg.h>
+
+#include "common.cuh"
+#include "conv_naive.cuh"
+#include "conv_plan.h"
+#include "conv_tc.cuh"
+#include "misc.cuh"
+#include "norm.cuh"
+
+namespace mra {
+thread_local std::string g_last_error;
+}
+using namespace mra;
+
+#define DISPATCH_DTYPE(dt, ...)                                  \
+  do {                                                           \
+    if ((dt) == MRA_F32) { typedef float T; __VA_ARGS__; }       \
+    else if ((dt) == MRA_BF16) { typedef bf16 T; __VA_ARGS__; }  \
+    else return fail(-1, "unknown dtype %d", (int)(dt));         \
+  } while (0)
+
+static int check_conv(const mra_conv_desc* d) {
+  MRA_REQUIRE(d != nullptr, "null conv descriptor");
+  MRA_REQUIRE(d->n > 0 && d->cin > 0 && d->cout > 0 && d->k > 0, "bad conv sizes");
+  MRA_REQUIRE(d->stride == 1 || d->stride == 2, "stride must be 1 or 2 (got %d)", d->stride);
+  const int in[3] = {d->din, d->hin, d->win}, out[3] = {d->dout, d->hout, d->wout};
+  for (int i = 0; i < 3; ++i) {
+    MRA_REQUIRE(in[i] > 0 && out[i] > 0, "bad conv spatial dims");
+    if (!d->transposed) {
+      const int e = (in[i] + 2 * d->pad - d->k) / d->stride + 1;
+      MRA_REQUIRE(e == out[i], "conv output dim %d: expected %d got %d", i, e, out[i]);
+    } else {
+      const int lo = (in[i] - 1) * d->stride - 2 * d->pad + d->k;   // output_padding in [0, stride)
+      MRA_REQUIRE(out[i] >= lo && out[i] < lo + d->stride, "convT output dim %d: %d not in [%d,%d)", i, out[i], lo,
+                  lo + d->stride);
+    }
+  }
+  return 0;
+}
+
+static NaiveGatherP naive_params(const mra_conv_desc& d, int which, const void* a, const void* b, const float* bias,
+                                 void* out) {
+  NaiveGatherP P;
+  const bool fprop = which == 0;
+  P.a = a; P.b = b; P.bias = bias; P.out = out;
+  P.N = d.n; P.Ck = fprop ? d.cin : d.cout; P.Cn = fprop ? d.cout : d.cin;
+  if (fprop) { P.Ad = d.din; P.Ah = d.hin; P.Aw = d.win; P.Od = d.dout; P.Oh = d.hout; P.Ow = d.wout; }
+  else       { P.Ad = d.dout; P.Ah = d.hout; P.Aw = d.wout; P.Od = d.din; P.Oh = d.hin; P.Ow = d.win; }
+  P.k = d.k; P.s = d.stride; P.p = d.pad;
+  const bool direct = (fprop && !d.transposed) || (!fprop && d.transposed);
+  P.transposed_mode = direct ? 0 : 1;
+  P.act = fprop ? d.act : MRA_ACT_NONE; P.slope = d.slope;
+  return P;
+}
+
+extern "C" {
+
+int mra_version(void) { return 100; }
+const char* mra_last_error(void) { return g_last_error.c_str(); }
+
+int mra_conv3d_uses_tensor_cores(const mra_conv_desc* d, int which) {
+  if (!d) return 0;
+  if (which == 2) return tc::wgrad_eligible(*d) ? 1 : 0;
+  return tc::gather_eligible(*d, which) ? 1 : 0;
+}
+
+int mra_conv3d_fprop(const mra_conv_desc* d, const void* x, const void* w, const float* bias, void* y, double* stats,
+                     mra_stream_t stream) {
+  if (int rc = check_conv(d)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (stats) MRA_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * d->n * d->cout, st));
+  if (tc::gather_eligible(*d, 0)) return tc::run_gather_tc(*d, 0, x, w, bias, y, stats, st);
+  NaiveGatherP P = naive_params(*d, 0, x, w, bias, y);
+  DISPATCH_DTYPE(d->dtype, { if (int rc = launch_naive_gather<T>(P, st)) return rc; });
+  if (stats) {
+    MRA_REQUIRE(d->act == MRA_ACT_NONE, "stats are defined on the pre-activation output only");
+    mra_norm_desc nd;
+    memset(&nd, 0, sizeof(nd));
+    nd.n = d->n; nd.c = d->cout; nd.d = d->dout; nd.h = d->hout; nd.w = d->wout; nd.res_pad = -1; nd.dtype = d->dtype;
+    return mra_inorm_stats(&nd, y, stats, stream);
+  }
+  return 0;
+}
+
+int mra_conv3d_dgrad(const mra_conv_desc* d, const void* dy, const void* wT, void* dx, mra_stream_t stream) {
+  if (int rc = check_conv(d)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (tc::gather_eligible(*d, 1)) return tc::run_gather_tc(*d, 1, dy, wT, nullptr, dx, nullptr, st);
+  NaiveGatherP P = naive_params(*d, 1, dy, wT, nullptr, dx);
+  DISPATCH_DTYPE(d->dtype, { if (int rc = launch_naive_gather<T>(P, st)) return rc; });
+  return 0;
+}
+
+int mra_conv3d_wgrad(const mra_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias,
+                     mra_stream_t stream) {
+  if (int rc = check_conv(d)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t wn = (size_t)d->k * d->k * d->k * d->cout * d->cin;
+  if (!(d->flags & MRA_CONV_ACCUMULATE)) {
+    if (dw) MRA_CHECK_CUDA(cudaMemsetAsync(dw, 0, wn * sizeof(float), st));
+    if (dbias) MRA_CHECK_CUDA(cudaMemsetAsync(dbias, 0, (size_t)d->cout * sizeof(float), st));
+  }
+  if (dw) {
+    if (tc::wgrad_eligible(*d)) {
+      if (int rc = tc::run_wgrad_tc(*d, x, dy, dw, st)) return rc;
+    } else {
+      NaiveWgradP P;
+      P.x = x; P.dy = dy; P.dw = dw; P.N = d->n; P.Cin = d->cin; P.Cout = d->cout;
+      P.Xd = d->din; P.Xh = d->hin; P.Xw = d->win; P.Yd = d->dout; P.Yh = d->hout; P.Yw = d->wout;
+      P.k = d->k; P.s = d->stride; P.p = d->pad; P.transposed = d->transposed; P.chunks = 1;
+      DISPATCH_DTYPE(d->dtype, { if (int rc = launch_naive_wgrad<T>(P, st)) return rc; });
+    }
+  }
+  if (dbias) {
+    const long long rows = (long long)d->n * d->dout * d->hout * d->wout;
+    DISPATCH_DTYPE(d->dtype, { if (int rc = launch_colsum<T>(dy, rows, d->cout, dbias, st)) return rc; });
+  }
+  return 0;
+}
+
+int mra_pack_weight_t(const void* w, int src_dtype, void* wT, int dst_dtype, int taps, int cout, int cin,
+                      mra_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MRA_REQUIRE(taps > 0 && cout > 0 && cin > 0 && taps <= 65535, "bad pack sizes");
+  dim3 grid((cin + 31) / 32, (cout + 31) / 32, taps), block(32, 8);
+  if (src_dtype == MRA_F32 && dst_dtype == MRA_F32)
+    pack_weight_t_kernel<float, float><<<grid, block, 0, st>>>((const float*)w, (float*)wT, cout, cin);
+  else if (src_dtype == MRA_F32 && dst_dtype == MRA_BF16)
+    pack_weight_t_kernel<float, bf16><<<grid, block, 0, st>>>((const float*)w, (bf16*)wT, cout, cin);
+  else if (src_dtype == MRA_BF16 && dst_dtype == MRA_BF16)
+    pack_weight_t_kernel<bf16, bf16><<<grid, block, 0, st>>>((const bf16*)w, (bf16*)wT, cout, cin);
+  else return fail(-1, "unsupported pack dtype combination %d -> %d", src_dtype, dst_dtype);
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+
+int mra_convert(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t numel, mra_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (numel <= 0) return 0;
+  const unsigned g = ew_grid(numel);
+  if (src_dtype == MRA_F32 && dst_dtype == MRA_BF16)
+    convert_kernel<float, bf16><<<g, 256, 0, st>>>((const float*)src, (bf16*)dst, numel);
+  else if (src_dtype == MRA_BF16 && dst_dtype == MRA_F32)
+    convert_kernel<bf16, float><<<g, 256, 0, st>>>((const bf16*)src, (float*)dst, numel);
+  else if (src_dtype == MRA_F32 && dst_dtype == MRA_F32)
+    convert_kernel<float, float><<<g, 256, 0, st>>>((const float*)src, (float*)dst, numel);
+  else if (src_dtype == MRA_BF16 && dst_dtype == MRA_BF16)
+    convert_kernel<bf16, bf16><<<g, 256, 0, st>>>((const bf16*)src, (bf16*)dst, numel);
+  else return fail(-1, "unsupported convert %d -> %d", src_dtype, dst_dtype);
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------ norm family
+static int check_norm(const mra_norm_desc* d) {
+  MRA_REQUIRE(d != nullptr, "null norm descriptor");
+  MRA_REQUIRE(d->n > 0 && d->c > 0 && d->d > 0 && d->h > 0 && d->w > 0, "bad norm sizes");
+  MRA_REQUIRE(d->c <= 2048, "channel count %d too large", d->c);
+  MRA_REQUIRE(d->pad >= 0 && d->res_pad >= -1, "bad pad");
+  return 0;
+}
+#define DISPATCH_NORM(d, ...)                                                       \
+  do {                                                                              \
+    const bool vec8 = ((d)->c % 8) == 0;                                            \
+    if ((d)->dtype == MRA_F32) { typedef float T; if (vec8) { constexpr int VEC = 8; __VA_ARGS__; } else { constexpr int VEC = 1; __VA_ARGS__; } } \
+    else if ((d)->dtype == MRA_BF16) { typedef bf16 T; if (vec8) { constexpr int VEC = 8; __VA_ARGS__; } else { constexpr int VEC = 1; __VA_ARGS__; } } \
+    else return fail(-1, "unknown dtype %d", (int)(d)->dtype);                      \
+  } while (0)
+
+int mra_inorm_stats(const mra_norm_desc* d, const void* x, double* stats, mra_stream_t stream) {
+  if (int rc = check_norm(d)) return rc;
+  DISPATCH_NORM(d, return (norm_stats_launch<T, VEC>(*d, x, stats, (cudaStream_t)stream)));
+  return 0;
+}
+
+int mra_inorm_act_pad_fwd(const mra_norm_desc* d, const void* x, const double* stats, const void* residual, void* y,
+                          float* mean, float* rstd, float* running_mean, float* running_var, mra_stream_t stream) {
+  if (int rc = check_norm(d)) return rc;
+  MRA_REQUIRE(d->use_running || (long long)d->d * d->h * d->w > 1,
+              "InstanceNorm needs more than 1 spatial element per channel in training mode");
+  MRA_REQUIRE((d->res_pad >= 0) == (residual != nullptr), "residual pointer / res_pad mismatch");
+  MRA_REQUIRE(!d->use_running || (running_mean && running_var), "eval-mode norm needs running stats");
+  DISPATCH_NORM(d, return (norm_fwd_launch<T, VEC>(*d, x, stats, residual, y, mean, rstd, running_mean, running_var,
+                                                   (cudaStream_t)stream)));
+  return 0;
+}
+
+int mra_inorm_act_pad_bwd(const mra_norm_desc* d, const void* gy, const void* x, const float* mean, const float* rstd,
+                          void* dx, void* dres, double* sums, mra_stream_t stream) {
+  if (int rc = check_norm(d)) return rc;
+  MRA_REQUIRE(!dres || d->res_pad >= 0, "dres requested without a residual");
+  DISPATCH_NORM(d, return (norm_bwd_launch<T, VEC>(*d, gy, x, mean, rstd, dx, dres, sums, (cudaStream_t)stream)));
+  return 0;
+}
+
+int mra_act_fwd(const void* x, void* y, int64_t numel, int act, float slope, int dtype, mra_stream_t stream) {
+  if (numel <= 0) return 0;
+  DISPATCH_DTYPE(dtype, (act_fwd_kernel<T><<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, numel, act, slope)));
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+int mra_act_bwd(const void* dy, const void* y, void* dx, int64_t numel, int act, float slope, int dtype,
+                mra_stream_t stream) {
+  if (numel <= 0) return 0;
+  DISPATCH_DTYPE(dtype, (act_bwd_kernel<T><<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>((const T*)dy, (const T*)y, (T*)dx, numel, act, slope)));
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+
+static mra_norm_desc pad_desc(int n, int d, int h, int w, int c, int pad, int dtype) {
+  mra_norm_desc nd;
+  memset(&nd, 0, sizeof(nd));
+  nd.n = n; nd.c = c; nd.d = d; nd.h = h; nd.w = w; nd.pad = pad; nd.res_pad = -1; nd.dtype = dtype;
+  return nd;
+}
+int mra_reppad_fwd(const void* x, void* y, int n, int d, int h, int w, int c, int pad, int dtype, mra_stream_t stream) {
+  mra_norm_desc nd = pad_desc(n, d, h, w, c, pad, dtype);
+  if (int rc = check_norm(&nd)) return rc;
+  const mra_norm_desc* dp = &nd;
+  DISPATCH_NORM(dp, {
+    NormP P = make_norm_params(nd, VEC);
+    const long long items = (long long)(d + 2 * pad) * (h + 2 * pad) * (w + 2 * pad) * P.G;
+    dim3 grid(grid_for(items, 1024, (16 + n - 1) / n), n);
+    reppad_fwd_kernel<T, VEC><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, P);
+  });
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+int mra_reppad_bwd(const void* gy, void* dx, int n, int d, int h, int w, int c, int pad, int dtype, mra_stream_t stream) {
+  mra_norm_desc nd = pad_desc(n, d, h, w, c, pad, dtype);
+  if (int rc = check_norm(&nd)) return rc;
+  const mra_norm_desc* dp = &nd;
+  DISPATCH_NORM(dp, {
+    NormP P = make_norm_params(nd, VEC);
+    dim3 grid(grid_for(P.V * P.G, 1024, (16 + n - 1) / n), n);
+    reppad_bwd_kernel<T, VEC><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)gy, (T*)dx, P);
+  });
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------ losses / optimiser
+int mra_loss_fwd(int kind, const void* a, const void* b, float target, int64_t numel, int dtype, double* acc,
+                 mra_stream_t stream) {
+  MRA_REQUIRE(kind >= 0 && kind <= 2, "unknown loss kind %d", kind);
+  MRA_REQUIRE(kind != MRA_LOSS_L1 || b != nullptr, "L1 needs two operands");
+  if (numel <= 0) return 0;
+  unsigned g = ew_grid(numel, 16);
+  DISPATCH_DTYPE(dtype, (loss_fwd_kernel<T><<<g, 256, 0, (cudaStream_t)stream>>>(kind, (const T*)a, (const T*)b, target, numel, acc)));
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+int mra_loss_bwd(int kind, const void* a, const void* b, float target, int64_t numel, int dtype, const float* gout,
+                 float scale, void* da, mra_stream_t stream) {
+  MRA_REQUIRE(kind >= 0 && kind <= 2, "unknown loss kind %d", kind);
+  if (numel <= 0) return 0;
+  DISPATCH_DTYPE(dtype, (loss_bwd_kernel<T><<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(kind, (const T*)a, (const T*)b, target, numel, gout, scale, (T*)da)));
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+int mra_corr_sums(const void* x, const void* y, int64_t numel, int dtype, double* acc, mra_stream_t stream) {
+  if (numel <= 0) return 0;
+  DISPATCH_DTYPE(dtype, (corr_sums_kernel<T><<<ew_grid(numel, 16), 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)y, numel, acc)));
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+
+int mra_adam_multi(const mra_adam_tensor* tensors, int count, float lr, float beta1, float beta2, float eps, int step,
+                   mra_stream_t stream) {
+  MRA_REQUIRE(count >= 0 && step >= 1, "bad adam arguments");
+  const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+  int i = 0;
+  while (i < count) {
+    AdamBatch B;
+    memset(&B, 0, sizeof(B));
+    B.lr = lr; B.b1 = beta1; B.b2 = beta2; B.eps = eps;
+    B.step_size = (float)((double)lr / bc1);
+    B.bc2_sqrt = (float)sqrt(bc2);
+    long long blocks = 0;
+    int c = 0;
+    for (; c < MRA_ADAM_MAX_TENSORS && i < count; ++i) {
+      const mra_adam_tensor& t = tensors[i];
+      if (t.numel <= 0) continue;
+      B.p[c] = t.p; B.g[c] = t.g; B.m[c] = t.m; B.v[c] = t.v; B.shadow[c] = (bf16*)t.shadow; B.numel[c] = t.numel;
+      B.block_start[c] = blocks;
+      blocks += (t.numel + MRA_ADAM_ELEMS_PER_BLOCK - 1) / MRA_ADAM_ELEMS_PER_BLOCK;
+      ++c;
+    }
+    B.block_start[c] = blocks;
+    B.count = c;
+    if (c == 0) continue;
+    adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(B);
+    MRA_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ sliding window helpers
+int mra_window_extract(const float* vol, int X, int Y, int Z, int i0, int j0, int k0, int px, int py, int pz,
+                       void* patch, int dtype, mra_stream_t stream) {
+  MRA_REQUIRE(i0 >= 0 && j0 >= 0 && k0 >= 0 && i0 + px <= X && j0 + py <= Y && k0 + pz <= Z, "window out of range");
+  const long long n = (long long)px * py * pz;
+  DISPATCH_DTYPE(dtype, (window_extract_kernel<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(vol, Y, Z, i0, j0, k0, px, py, pz, (T*)patch)));
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+int mra_window_accumulate(const void* pred, int dtype, float* label, float* weight, int X, int Y, int Z, int i0, int j0,
+                          int k0, int px, int py, int pz, mra_stream_t stream) {
+  MRA_REQUIRE(i0 >= 0 && j0 >= 0 && k0 >= 0 && i0 + px <= X && j0 + py <= Y && k0 + pz <= Z, "window out of range");
+  const long long n = (long long)px * py * pz;
+  DISPATCH_DTYPE(dtype, (window_accumulate_kernel<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const T*)pred, label, weight, Y, Z, i0, j0, k0, px, py, pz)));
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+int mra_window_finalize(float* label, const float* weight, int64_t numel, mra_stream_t stream) {
+  if (numel <= 0) return 0;
+  window_finalize_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(label, weight, numel);
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------ introspection
+int mra_conv_plan_describe(const mra_conv_desc* d, int which, int32_t* out, int cap) {
+  if (int rc = check_conv(d)) return rc;
+  if (which == 2) {
+    WgradPlan P;
+    MRA_REQUIRE(build_wgrad_plan(*d, P), "unsupported geometry");
+    return describe(P, out, cap);
+  }
+  GatherPlan P;
+  MRA_REQUIRE(build_gather_plan(*d, which, P), "unsupported geometry");
+  return describe(P, out, cap);
+}
+
+// Reads (and optionally clears) the tensor-core kernels' device error flag.  Synchronises the
+// device: debugging / test use only.  0 = no error, else the code of the first timed-out wait.
+int mra_debug_tc_error(int reset) {
+  int* flag = tc::tc_err_flag();
+  if (!flag) return -1;
+  int v = 0;
+  if (cudaMemcpy(&v, flag, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+  if (reset && v) cudaMemset(flag, 0, sizeof(int));
+  return v;
+}
+
+}  // extern "C"

@@ -1,0 +1,247 @@
+"""GPU parity of every C-ABI op against the op-level oracle (oracle/ops_ref.py, torch CPU).
+Tolerances (BASELINE.json north_star): rel-L2 <= 1e-4 on the fp32 path, <= 1e-2 on the bf16 path."""
+import pytest
+import torch
+
+from mra_gan_b200 import ops
+from mra_gan_b200.ops import ConvGeom
+from oracle import ops_ref as R
+from oracle.functional import rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = {torch.float32: 1e-4, torch.bfloat16: 1e-2}
+
+CONVS = [
+    # (geom, in_dims, N)
+    (ConvGeom(1, 8, 7, 1, 0), (14, 14, 14), 2),            # stem-like (Cin=1)
+    (ConvGeom(8, 1, 7, 1, 0), (14, 14, 14), 2),            # head-like (Cout=1)
+    (ConvGeom(8, 16, 3, 2, 1), (12, 12, 12), 2),
+    (ConvGeom(16, 16, 3, 1, 0), (10, 10, 10), 1),
+    (ConvGeom(1, 8, 4, 2, 1), (12, 12, 12), 2),
+    (ConvGeom(16, 24, 4, 1, 1), (7, 7, 7), 2),
+    (ConvGeom(16, 8, 3, 2, 1, True, 1), (5, 6, 7), 2),
+    (ConvGeom(16, 8, 4, 2, 1, True, 0), (4, 5, 3), 2),
+]
+TC_CONVS = [
+    (ConvGeom(256, 256, 3, 1, 0), (10, 10, 10), 2),        # G.rb
+    (ConvGeom(64, 128, 3, 2, 1), (16, 16, 16), 1),         # G.d1
+    (ConvGeom(64, 128, 4, 2, 1), (16, 16, 16), 2),         # D.2
+    (ConvGeom(128, 512, 4, 1, 1), (10, 10, 10), 1),        # D.4-like, ragged 9^3 output
+    (ConvGeom(256, 128, 3, 2, 1, True, 1), (6, 6, 6), 2),  # G.u1
+    (ConvGeom(128, 64, 4, 2, 1, True, 0), (5, 5, 5), 1),   # UNet up
+    (ConvGeom(64, 64, 3, 1, 1), (9, 7, 5), 1),             # zero-padded, odd dims
+]
+
+
+def gid(v):
+    g, dims, n = v
+    return "c%d-%d_k%d_s%d_p%d_%s_%s" % (g.cin, g.cout, g.k, g.stride, g.pad, "T" if g.transposed else "C",
+                                         "x".join(map(str, dims)))
+
+
+def _conv_case(g, dims, n, dtype, seed=0):
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randn((n,) + dims + (g.cin,), generator=gen).to(dtype)
+    w = (torch.randn((g.taps, g.cout, g.cin), generator=gen) / (g.taps * g.cin) ** 0.5).to(dtype)
+    b = torch.randn((g.cout,), generator=gen)
+    dy = torch.randn((n,) + g.out_dims(dims) + (g.cout,), generator=gen).to(dtype)
+    return x, w, b, dy
+
+
+def _check_conv(g, dims, n, dtype, expect_tc):
+    I = ops.impl()
+    ref = R.RefImpl(torch.float64)
+    x, w, b, dy = _conv_case(g, dims, n, dtype)
+    dev = "cuda"
+    xd, wd, bd, dyd = x.to(dev), w.to(dev), b.to(dev), dy.to(dev)
+    for which in range(3):
+        assert I.conv_uses_tensor_cores(g, n, dims, dtype, which) == expect_tc
+    tol = TOL[dtype]
+    # fprop (+bias, + epilogue statistics)
+    y, st = I.conv_fprop(xd, wd, bd, g, want_stats=True)
+    y_ref, st_ref = ref.conv_fprop(x.double(), w.double(), b.double(), g, want_stats=True)
+    assert I.tc_error() == 0
+    assert rel_l2(y.cpu(), y_ref) < tol, "fprop"
+    assert rel_l2(st.cpu(), st_ref) < 10 * tol, "epilogue stats"
+    y2, _ = I.conv_fprop(xd, wd, None, g, act=ops.ACT_LRELU, slope=0.2)
+    y2_ref, _ = ref.conv_fprop(x.double(), w.double(), None, g, act=R.ACT_LRELU, slope=0.2)
+    assert rel_l2(y2.cpu(), y2_ref) < tol, "fprop+lrelu"
+    # dgrad
+    wT = I.pack_weight_t(wd, dtype)
+    assert torch.equal(wT.cpu(), w.transpose(1, 2).contiguous())
+    dx = I.conv_dgrad(dyd, wT, g, dims)
+    dx_ref = ref.conv_dgrad(dy.double(), w.double().transpose(1, 2).contiguous(), g, dims)
+    assert I.tc_error() == 0
+    assert rel_l2(dx.cpu(), dx_ref) < tol, "dgrad"
+    # wgrad (+dbias)
+    dw, db = I.conv_wgrad(xd, dyd, g, want_bias=True)
+    dw_ref, db_ref = ref.conv_wgrad(x.double(), dy.double(), g, want_bias=True)
+    assert I.tc_error() == 0
+    assert rel_l2(dw.cpu(), dw_ref) < tol, "wgrad"
+    assert rel_l2(db.cpu(), db_ref) < tol, "dbias"
+
+
+@pytest.mark.parametrize("case", CONVS, ids=gid)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_conv_cuda_core_path(case, dtype):
+    _check_conv(*case, dtype, expect_tc=False)
+
+
+@pytest.mark.parametrize("case", TC_CONVS, ids=gid)
+def test_conv_tcgen05_path(case):
+    _check_conv(*case, torch.bfloat16, expect_tc=True)
+
+
+@pytest.mark.parametrize("case", TC_CONVS[:3], ids=gid)
+def test_conv_same_shape_fp32_path(case):
+    _check_conv(*case, torch.float32, expect_tc=False)
+
+
+NORMS = [
+    # (N, D, H, W, C, pad, act, residual_pad)
+    (2, 6, 5, 7, 16, 1, R.ACT_RELU, -1),
+    (1, 8, 8, 8, 64, 3, R.ACT_RELU, -1),
+    (2, 4, 6, 5, 32, 1, R.ACT_NONE, 1),
+    (2, 5, 5, 5, 24, 0, R.ACT_LRELU, -1),
+    (1, 3, 4, 5, 4, 1, R.ACT_RELU, -1),        # scalar (C % 8 != 0) path
+    (1, 2, 2, 2, 512, 0, R.ACT_LRELU, -1),     # tiny reduction, many channels
+    (2, 4, 4, 4, 8, 0, R.ACT_NONE, 0),
+]
+
+
+@pytest.mark.parametrize("case", NORMS, ids=lambda c: "x".join(map(str, c)))
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_inorm_act_pad(case, dtype):
+    n, d, h, w, c, pad, act, rp = case
+    I, ref = ops.impl(), R.RefImpl(torch.float64)
+    gen = torch.Generator().manual_seed(1)
+    x = (torch.randn((n, d, h, w, c), generator=gen) * 1.5 + 0.3).to(dtype)
+    res = torch.randn((n, d + 2 * rp, h + 2 * rp, w + 2 * rp, c), generator=gen).to(dtype) if rp >= 0 else None
+    gy = torch.randn((n, d + 2 * pad, h + 2 * pad, w + 2 * pad, c), generator=gen).to(dtype)
+    rm, rv = torch.randn(c, generator=gen) * 0.1, 1 + 0.1 * torch.rand(c, generator=gen)
+    tol = TOL[dtype]
+    xd = x.cuda()
+    st = I.inorm_stats(xd)
+    st_ref = ref.inorm_stats(x)
+    assert rel_l2(st.cpu(), st_ref) < 1e-5
+    rmd, rvd = rm.cuda(), rv.cuda()
+    y, mean, rstd = I.inorm_fwd(xd, st, res.cuda() if res is not None else None, pad, act, 0.2, rp,
+                                running_mean=rmd, running_var=rvd)
+    rm_r, rv_r = rm.clone().double(), rv.clone().double()
+    y_ref, mean_ref, rstd_ref = ref.inorm_fwd(x.double(), st_ref, res.double() if res is not None else None, pad, act,
+                                              0.2, rp, running_mean=rm_r, running_var=rv_r)
+    assert rel_l2(y.cpu(), y_ref) < tol
+    assert rel_l2(mean.cpu(), mean_ref) < 1e-5 and rel_l2(rstd.cpu(), rstd_ref) < 1e-5
+    assert rel_l2(rmd.cpu(), rm_r) < 1e-5 and rel_l2(rvd.cpu(), rv_r) < 1e-5
+    dx, dres = I.inorm_bwd(gy.cuda(), xd, mean, rstd, pad, act, 0.2, rp)
+    dx_ref, dres_ref = ref.inorm_bwd(gy.double(), x.double(), mean_ref, rstd_ref, pad, act, 0.2, rp)
+    assert rel_l2(dx.cpu(), dx_ref) < tol
+    if rp >= 0:
+        assert rel_l2(dres.cpu(), dres_ref) < tol
+    # eval mode (running statistics)
+    y2, m2, r2 = I.inorm_fwd(xd, st, None, pad, act, 0.2, -1, running_mean=rmd, running_var=rvd, use_running=True)
+    y2_ref, _, _ = ref.inorm_fwd(x.double(), st_ref, None, pad, act, 0.2, -1, running_mean=rm_r, running_var=rv_r,
+                                 use_running=True)
+    assert rel_l2(y2.cpu(), y2_ref) < tol
+
+
+def test_norm_matches_torch_instance_norm_module():
+    """End-to-end against the reference's own layer composition (networks3D.py:232-243):
+    ReplicationPad3d(1) o ReLU o InstanceNorm3d, forward and backward through autograd."""
+    import torch.nn.functional as F
+    I = ops.impl()
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn((2, 16, 6, 6, 6), generator=gen, dtype=torch.float64, requires_grad=True)
+    rm, rv = torch.zeros(16, dtype=torch.float64), torch.ones(16, dtype=torch.float64)
+    y = F.pad(F.relu(F.instance_norm(x, rm, rv, use_input_stats=True, momentum=0.1, eps=1e-5)), (1,) * 6, mode="replicate")
+    gy = torch.randn(y.shape, generator=gen, dtype=torch.float64)
+    y.backward(gy)
+    xl = x.detach().permute(0, 2, 3, 4, 1).contiguous().float().cuda()
+    rmd, rvd = torch.zeros(16).cuda(), torch.ones(16).cuda()
+    st = I.inorm_stats(xl)
+    yl, mean, rstd = I.inorm_fwd(xl, st, None, 1, ops.ACT_RELU, running_mean=rmd, running_var=rvd)
+    assert rel_l2(yl.cpu().permute(0, 4, 1, 2, 3), y.detach()) < 1e-5
+    assert rel_l2(rmd.cpu(), rm) < 1e-5 and rel_l2(rvd.cpu(), rv) < 1e-5
+    dx, _ = I.inorm_bwd(gy.permute(0, 2, 3, 4, 1).contiguous().float().cuda(), xl, mean, rstd, 1, ops.ACT_RELU)
+    assert rel_l2(dx.cpu().permute(0, 4, 1, 2, 3), x.grad) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_pad_act_standalone(dtype):
+    I, ref = ops.impl(), R.RefImpl(torch.float64)
+    gen = torch.Generator().manual_seed(2)
+    for c in (1, 8):
+        x = torch.randn((2, 5, 4, 6, c), generator=gen).to(dtype)
+        y = I.reppad_fwd(x.cuda(), 3)
+        assert torch.equal(y.cpu(), ref.reppad_fwd(x, 3))
+        gy = torch.randn(y.shape, generator=gen).to(dtype)
+        assert rel_l2(I.reppad_bwd(gy.cuda(), 3).cpu(), ref.reppad_bwd(gy.double(), 3)) < TOL[dtype]
+    x = torch.randn((3, 4, 5, 6, 7), generator=gen).to(dtype)
+    for act in (R.ACT_RELU, R.ACT_LRELU, R.ACT_TANH, R.ACT_SIGMOID):
+        y = I.act_fwd(x.cuda(), act, 0.2)
+        assert rel_l2(y.cpu(), ref.act_fwd(x.double(), act, 0.2)) < TOL[dtype]
+        dx = I.act_bwd(x.cuda(), y, act, 0.2)
+        assert rel_l2(dx.cpu(), ref.act_bwd(x.double(), y.cpu().double(), act, 0.2)) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_losses(dtype):
+    I, ref = ops.impl(), R.RefImpl(torch.float64)
+    gen = torch.Generator().manual_seed(4)
+    a = torch.randn((2, 14, 14, 14, 1), generator=gen).to(dtype)
+    b = torch.randn((2, 14, 14, 14, 1), generator=gen).to(dtype)
+    p = torch.rand((2, 6, 6, 6, 1), generator=gen).clamp(1e-3, 1 - 1e-3).to(dtype)
+    gout = torch.tensor(0.7)
+    for kind, aa, bb, tgt in ((R.LOSS_L1, a, b, 0.0), (R.LOSS_MSE_CONST, a, None, 1.0), (R.LOSS_MSE_CONST, a, None, 0.0),
+                              (R.LOSS_BCE_CONST, p, None, 1.0), (R.LOSS_BCE_CONST, p, None, 0.0)):
+        got = I.loss_fwd(kind, aa.cuda(), bb.cuda() if bb is not None else None, tgt)
+        want = ref.loss_fwd(kind, aa.double(), bb.double() if bb is not None else None, tgt)
+        assert float(got) == pytest.approx(float(want), rel=1e-5)
+        da = I.loss_bwd(kind, aa.cuda(), bb.cuda() if bb is not None else None, tgt, gout.cuda(), 3.0 / aa.numel())
+        da_ref = ref.loss_bwd(kind, aa.double(), bb.double() if bb is not None else None, tgt, gout.double(), 3.0 / aa.numel())
+        assert rel_l2(da.cpu(), da_ref) < TOL[dtype]
+    s = I.corr_sums(a.cuda(), b.cuda())
+    assert rel_l2(s.cpu(), ref.corr_sums(a, b)) < 1e-9
+
+
+def test_adam_matches_torch_optim():
+    I = ops.impl()
+    gen = torch.Generator().manual_seed(5)
+    shapes = [(27, 16, 16), (16,), (343, 8, 1), (5000,), (1,)] * 12          # > 48 tensors: several launches
+    ps = [torch.randn(s, generator=gen) for s in shapes]
+    ref_p = [p.clone().requires_grad_(True) for p in ps]
+    opt = torch.optim.Adam(ref_p, lr=2e-4, betas=(0.5, 0.999))
+    dp = [p.cuda() for p in ps]
+    m = [torch.zeros_like(p) for p in dp]
+    v = [torch.zeros_like(p) for p in dp]
+    sh = [torch.empty_like(p, dtype=torch.bfloat16) if i % 2 == 0 else None for i, p in enumerate(dp)]
+    for step in range(1, 4):
+        gs = [torch.randn(s, generator=gen) * (0.1 if step < 3 else 1e-6) for s in shapes]
+        for p, g in zip(ref_p, gs):
+            p.grad = g.clone()
+        opt.step()
+        I.adam_step(dp, [g.cuda() for g in gs], m, v, sh, 2e-4, 0.5, 0.999, 1e-8, step)
+        for a, b in zip(dp, ref_p):
+            assert float((a.cpu() - b.detach()).abs().max()) < 2e-7
+    for a, s in zip(dp, sh):
+        if s is not None:
+            assert torch.equal(s.cpu(), a.cpu().to(torch.bfloat16))
+
+
+def test_sliding_window_helpers():
+    I, ref = ops.impl(), R.RefImpl()
+    gen = torch.Generator().manual_seed(6)
+    vol = torch.rand((20, 18, 11), generator=gen) * 255
+    lab, wt = torch.zeros_like(vol), torch.zeros_like(vol)
+    labd, wtd, vold = lab.cuda(), wt.cuda(), vol.cuda()
+    for (i0, j0, k0) in ((0, 0, 0), (12, 10, 3), (4, 2, 1)):
+        pr = ref.window_extract(vol, i0, j0, k0, (8, 8, 8), torch.float32)
+        pd = I.window_extract(vold, i0, j0, k0, (8, 8, 8), torch.float32)
+        assert torch.equal(pd.cpu(), pr)
+        ref.window_accumulate(pr * 0.5, lab, wt, i0, j0, k0)
+        I.window_accumulate(pd * 0.5, labd, wtd, i0, j0, k0)
+    assert torch.allclose(labd.cpu(), lab, atol=1e-4) and torch.equal(wtd.cpu(), wt)
+    lab += 1; wt += 1; labd += 1; wtd += 1
+    ref.window_finalize(lab, wt)
+    I.window_finalize(labd, wtd)
+    assert torch.allclose(labd.cpu(), lab, atol=1e-4)
