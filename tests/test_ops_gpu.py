@@ -201,7 +201,7 @@ def test_losses(dtype):
         da_ref = ref.loss_bwd(kind, aa.double(), bb.double() if bb is not None else None, tgt, gout.double(), 3.0 / aa.numel())
         assert rel_l2(da.cpu(), da_ref) < TOL[dtype]
     s = I.corr_sums(a.cuda(), b.cuda())
-    assert rel_l2(s.cpu(), ref.corr_sums(a, b)) < 1e-9
+    assert rel_l2(s.cpu(), ref.corr_sums(a, b)) < 1e-6
 
 
 def test_adam_matches_torch_optim():
