@@ -1,0 +1,184 @@
+"""Autograd wiring of the fused ops.
+
+Each ``torch.autograd.Function`` below is one unit of the fused execution plan; forward and backward
+both call only ``ops.impl()`` (the C-ABI kernels).  Activations inside a network are channels-last
+(N, D, H, W, C) tensors in the network's compute dtype; network inputs / outputs are converted from
+/ to the reference's (N, C, D, H, W) fp32 convention at the boundary (torch view/cast plumbing).
+"""
+import torch
+
+from . import ops
+from .ops import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, LOSS_BCE_CONST, LOSS_L1, LOSS_MSE_CONST
+
+
+def weight_grad_view(dw_packed, k, transposed):
+    """[taps][Cout][Cin] fp32 -> the parameter's logical shape with the packed memory layout
+    (so autograd's AccumulateGrad can adopt it without a copy)."""
+    t, co, ci = dw_packed.shape
+    v = dw_packed.view(k, k, k, co, ci)
+    return v.permute(4, 3, 0, 1, 2) if transposed else v.permute(3, 4, 0, 1, 2)
+
+
+class ConvFn(torch.autograd.Function):
+    """nn.Conv3d / nn.ConvTranspose3d (+bias, + epilogue activation, + InstanceNorm statistics)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, mod, act, slope, want_stats, bias_grad):
+        I = ops.impl()
+        g = mod.geom
+        wc = mod.packed_weight(x.dtype)
+        y, stats = I.conv_fprop(x, wc, bias.detach() if bias is not None else None, g, act, slope, want_stats)
+        ctx.mod, ctx.act, ctx.slope, ctx.bias_grad = mod, act, slope, bias_grad
+        ctx.in_dims = tuple(x.shape[1:4])
+        ctx.save_for_backward(x, y if act != ACT_NONE else None)
+        if stats is not None:
+            ctx.mark_non_differentiable(stats)
+            return y, stats
+        return y, None
+
+    @staticmethod
+    def backward(ctx, gy, _gstats):
+        I = ops.impl()
+        x, y = ctx.saved_tensors
+        mod, g = ctx.mod, ctx.mod.geom
+        gy = gy.contiguous()
+        if ctx.act != ACT_NONE:
+            gy = I.act_bwd(gy, y, ctx.act, ctx.slope)
+        dx = dw = db = None
+        has_bias = mod.bias is not None
+        if ctx.needs_input_grad[1]:
+            dwp, dbv = I.conv_wgrad(x, gy, g, want_bias=has_bias and ctx.bias_grad)
+            dw = weight_grad_view(dwp, g.k, g.transposed)
+            if has_bias and ctx.needs_input_grad[2]:
+                db = dbv if dbv is not None else torch.zeros_like(mod.bias)
+        if ctx.needs_input_grad[0]:
+            dx = I.conv_dgrad(gy, mod.packed_weight_t(gy.dtype), g, ctx.in_dims)
+        return dx, dw, db, None, None, None, None, None
+
+
+class NormActPadFn(torch.autograd.Function):
+    """InstanceNorm3d -> ReLU/LeakyReLU -> (+ residual) -> ReplicationPad3d, one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, x, stats, residual, mod, act, slope, pad, res_pad):
+        I = ops.impl()
+        use_running = not mod.training and mod.track_running_stats
+        if stats is None and not use_running:
+            stats = I.inorm_stats(x)
+        update = mod.training and mod.track_running_stats
+        y, mean, rstd = I.inorm_fwd(x, stats, residual, pad, act, slope, res_pad if residual is not None else -1,
+                                    mod.eps, mod.momentum,
+                                    mod.running_mean if (update or use_running) else None,
+                                    mod.running_var if (update or use_running) else None, use_running)
+        ctx.cfg = (act, slope, pad, res_pad if residual is not None else -1, use_running)
+        ctx.save_for_backward(x, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        I = ops.impl()
+        x, mean, rstd = ctx.saved_tensors
+        act, slope, pad, res_pad, use_running = ctx.cfg
+        want_res = res_pad >= 0 and ctx.needs_input_grad[2]
+        dx, dres = I.inorm_bwd(gy.contiguous(), x, mean, rstd, pad, act, slope, res_pad if want_res else -1, use_running)
+        return dx, None, dres, None, None, None, None, None
+
+
+class ActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act, slope):
+        y = ops.impl().act_fwd(x.contiguous(), act, slope)
+        ctx.cfg = (act, slope)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        return ops.impl().act_bwd(gy.contiguous(), y, *ctx.cfg), None, None
+
+
+class RepPadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pad):
+        ctx.pad = pad
+        return ops.impl().reppad_fwd(x.contiguous(), pad)
+
+    @staticmethod
+    def backward(ctx, gy):
+        return ops.impl().reppad_bwd(gy.contiguous(), ctx.pad), None
+
+
+class PairLossFn(torch.autograd.Function):
+    """mean |a - b| (torch.nn.L1Loss).  ``b`` is treated as a constant (it is always a real image)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = a.contiguous(), b.contiguous()
+        ctx.save_for_backward(a, b)
+        return ops.impl().loss_fwd(LOSS_L1, a, b)
+
+    @staticmethod
+    def backward(ctx, gout):
+        a, b = ctx.saved_tensors
+        return ops.impl().loss_bwd(LOSS_L1, a, b, 0.0, gout.float().reshape(1).contiguous(), 1.0 / a.numel()), None
+
+
+class ConstLossFn(torch.autograd.Function):
+    """MSELoss / BCELoss against a constant label expanded to the input's shape (GANLoss)."""
+
+    @staticmethod
+    def forward(ctx, a, kind, target):
+        a = a.contiguous()
+        ctx.kind, ctx.target = kind, target
+        ctx.save_for_backward(a)
+        return ops.impl().loss_fwd(kind, a, None, target)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (a,) = ctx.saved_tensors
+        return ops.impl().loss_bwd(ctx.kind, a, None, ctx.target, gout.float().reshape(1).contiguous(),
+                                   1.0 / a.numel()), None, None
+
+
+def l1_loss(a, b):
+    return PairLossFn.apply(a, b.detach())
+
+
+def mse_const_loss(a, target):
+    return ConstLossFn.apply(a, LOSS_MSE_CONST, float(target))
+
+
+def bce_const_loss(a, target):
+    return ConstLossFn.apply(a, LOSS_BCE_CONST, float(target))
+
+
+def cor_coe_loss(y_pred, y_target):
+    """Cor_CoeLoss = 1 - r^2 from one fused pass over both volumes (5 sums); value only -- the
+    reference computes it every step but never adds it to loss_G (cycle_gan_model.py:217-223)."""
+    s = ops.impl().corr_sums(y_pred.detach().contiguous(), y_target.detach().contiguous())
+    n = y_pred.numel()
+    sx, sy, sxy, sxx, syy = s[0], s[1], s[2], s[3], s[4]
+    num = sxy - sx * sy / n
+    den = torch.sqrt(sxx - sx * sx / n) * torch.sqrt(syy - sy * sy / n)
+    r = num / den
+    return (1 - r * r).float()
+
+
+# -- boundary layout helpers (views / casts only) ---------------------------------------------
+def to_channels_last(x, dtype):
+    """(N, C, D, H, W) any float dtype -> (N, D, H, W, C) contiguous ``dtype``."""
+    if x.shape[1] == 1:
+        y = x.reshape(x.shape[0], x.shape[2], x.shape[3], x.shape[4], 1)
+    else:
+        y = x.permute(0, 2, 3, 4, 1)
+    return y.to(dtype).contiguous()
+
+
+def to_channels_first(y, dtype=torch.float32):
+    """(N, D, H, W, C) -> (N, C, D, H, W) contiguous ``dtype``."""
+    if y.shape[4] == 1:
+        x = y.reshape(y.shape[0], 1, y.shape[1], y.shape[2], y.shape[3])
+    else:
+        x = y.permute(0, 4, 1, 2, 3)
+    return x.to(dtype).contiguous()

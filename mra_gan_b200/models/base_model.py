@@ -1,0 +1,121 @@
+"""BaseModel: the orchestration surface train.py / test.py use (reference models/base_model.py:7-171).
+
+Method names, attribute names and the on-disk checkpoint format
+(``<checkpoints_dir>/<name>/<epoch>_net_<X>.pth`` holding ``net.state_dict()`` with the reference key
+layout, tensors on CPU in torch's standard layout) are kept.
+"""
+import os
+from collections import OrderedDict
+
+import torch
+
+from .. import networks3D
+
+device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+
+
+class BaseModel:
+    @staticmethod
+    def modify_commandline_options(parser, is_train):
+        return parser
+
+    def name(self):
+        return "BaseModel"
+
+    def initialize(self, opt):
+        self.opt = opt
+        self.gpu_ids = opt.gpu_ids
+        self.isTrain = opt.isTrain
+        # the reference resolves opt.gpu_ids=0 to CPU and then sprinkles .to(cuda) everywhere
+        # (base_model.py:22, cycle_gan_model.py:131-135); here the model simply lives on the GPU.
+        self.device = device
+        self.save_dir = os.path.join(opt.checkpoints_dir, opt.name)
+        self.loss_names, self.model_names, self.visual_names, self.image_paths = [], [], [], []
+
+    def set_input(self, input):
+        self.input = input
+
+    def forward(self):
+        pass
+
+    def optimize_parameters(self):
+        pass
+
+    def _nets(self):
+        return [(n, getattr(self, "net" + n)) for n in self.model_names if isinstance(n, str)]
+
+    def setup(self, opt, parser=None):
+        if self.isTrain:
+            self.schedulers = [networks3D.get_scheduler(o, opt) for o in self.optimizers]
+        if not self.isTrain or opt.continue_train:
+            self.load_networks(opt.which_epoch)
+        self.print_networks(opt.verbose)
+
+    def eval(self):
+        for _, net in self._nets():
+            net.eval()
+
+    def test(self):
+        with torch.no_grad():
+            self.forward()
+
+    def get_image_paths(self):
+        return self.image_paths
+
+    def update_learning_rate(self):
+        for s in self.schedulers:
+            s.step()
+        print("learning rate = %.7f" % self.optimizers[0].param_groups[0]["lr"])
+
+    def get_current_visuals(self):
+        return OrderedDict((n, getattr(self, n)) for n in self.visual_names if isinstance(n, str))
+
+    def get_current_losses(self):
+        out = OrderedDict()
+        for n in self.loss_names:
+            if isinstance(n, str):
+                v = getattr(self, "loss_" + n)
+                out[n] = float(v.detach()) if torch.is_tensor(v) else float(v)   # host sync, print time only
+        return out
+
+    # -- checkpoints ---------------------------------------------------------------------------
+    def save_networks(self, which_epoch):
+        os.makedirs(self.save_dir, exist_ok=True)
+        for n, net in self._nets():
+            path = os.path.join(self.save_dir, "%s_net_%s.pth" % (which_epoch, n))
+            sd = OrderedDict((k, v.detach().to("cpu").contiguous()) for k, v in net.state_dict().items())
+            torch.save(sd, path)
+
+    def load_networks(self, which_epoch):
+        for n, net in self._nets():
+            path = os.path.join(self.save_dir, "%s_net_%s.pth" % (which_epoch, n))
+            print("loading the model from %s" % path)
+            sd = torch.load(path, map_location="cpu")
+            if hasattr(sd, "_metadata"):
+                del sd._metadata
+            own = net.state_dict()
+            for k in list(sd.keys()):
+                # pre-0.4 InstanceNorm checkpoints / DataParallel prefixes (base_model.py:114-148, utils.py:24-32)
+                if k.startswith("module."):
+                    sd[k[7:]] = sd.pop(k)
+            for k in list(sd.keys()):
+                if k.endswith("num_batches_tracked") and k not in own:
+                    sd.pop(k)
+            missing = [k for k in own if k not in sd and k.endswith("num_batches_tracked")]
+            for k in missing:
+                sd[k] = own[k].detach().cpu().clone()
+            net.load_state_dict(sd)
+
+    def print_networks(self, verbose):
+        print("---------- Networks initialized -------------")
+        for n, net in self._nets():
+            if verbose:
+                print(net)
+            print("[Network %s] Total number of parameters : %.3f M" % (n, sum(p.numel() for p in net.parameters()) / 1e6))
+        print("-----------------------------------------------")
+
+    def set_requires_grad(self, nets, requires_grad=False):
+        for net in nets if isinstance(nets, list) else [nets]:
+            if net is not None:
+                for p in net.parameters():
+                    p.requires_grad = requires_grad

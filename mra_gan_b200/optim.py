@@ -1,0 +1,70 @@
+"""Fused multi-tensor Adam with torch.optim.Adam semantics (the reference builds
+torch.optim.Adam(lr, betas=(beta1, 0.999)) for G and D: models/cycle_gan_model.py:107-110).
+
+It is a regular ``torch.optim.Optimizer`` (param_groups / state_dict / LR schedulers work), but
+``step()`` is one kernel sweep (``mra_adam_multi``) over every parameter that also refreshes the
+bf16 shadow copies the tensor-core convolutions read.
+"""
+import torch
+
+from . import ops
+from .networks3D import _WeightsEpoch
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False):
+        if weight_decay != 0 or amsgrad:
+            raise NotImplementedError("the reference uses plain Adam (no weight decay, no amsgrad)")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        I = ops.impl()
+        new_epoch = _WeightsEpoch.value + 1
+        for group in self.param_groups:
+            ps, gs, ms, vs, shs = [], [], [], [], []
+            step_no = None
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["step"] += 1
+                if step_no is None:
+                    step_no = st["step"]
+                elif step_no != st["step"]:
+                    # parameters that joined late get their own sweep below
+                    I.adam_step([p], [self._grad(p)], [st["exp_avg"]], [st["exp_avg_sq"]], [self._shadow(p)],
+                                group["lr"], group["betas"][0], group["betas"][1], group["eps"], st["step"])
+                    self._mark(p, new_epoch)
+                    continue
+                ps.append(p); gs.append(self._grad(p)); ms.append(st["exp_avg"]); vs.append(st["exp_avg_sq"])
+                shs.append(self._shadow(p))
+            if ps:
+                I.adam_step(ps, gs, ms, vs, shs, group["lr"], group["betas"][0], group["betas"][1], group["eps"],
+                            step_no)
+                for p in ps:
+                    self._mark(p, new_epoch)
+        _WeightsEpoch.value = new_epoch
+        return loss
+
+    @staticmethod
+    def _grad(p):
+        g = p.grad
+        if g.stride() != p.stride():
+            g = torch.empty_like(p, memory_format=torch.preserve_format).copy_(g)
+        return g
+
+    @staticmethod
+    def _shadow(p):
+        return getattr(p, "_mra_shadow", None)
+
+    @staticmethod
+    def _mark(p, epoch):
+        if getattr(p, "_mra_shadow", None) is not None:
+            # tag = (version, epoch, data_ptr) as computed by _ConvNd._tag() after this step
+            p._mra_shadow_tag = (p._version, epoch, p.data_ptr())

@@ -103,15 +103,17 @@ class RefImpl:
 
     def conv_dgrad(self, dy, wT, g, in_dims):
         wp = self._c(wT).transpose(1, 2).contiguous()
-        x = torch.zeros((dy.shape[0], g.cin) + tuple(in_dims), dtype=self.cd, requires_grad=True)
-        y = self._conv(x, wp, None, g)
-        (dx,) = torch.autograd.grad(y, x, to_ncdhw(self._c(dy)))
+        with torch.enable_grad():       # may be called from inside an autograd backward
+            x = torch.zeros((dy.shape[0], g.cin) + tuple(in_dims), dtype=self.cd, requires_grad=True)
+            y = self._conv(x, wp, None, g)
+            (dx,) = torch.autograd.grad(y, x, to_ncdhw(self._c(dy)))
         return to_ndhwc(dx).to(dy.dtype)
 
     def conv_wgrad(self, x, dy, g, want_bias=False):
-        wp = torch.zeros((g.taps, g.cout, g.cin), dtype=self.cd, requires_grad=True)
-        y = self._conv(to_ncdhw(self._c(x)), wp, None, g)
-        (dw,) = torch.autograd.grad(y, wp, to_ncdhw(self._c(dy)))
+        with torch.enable_grad():
+            wp = torch.zeros((g.taps, g.cout, g.cin), dtype=self.cd, requires_grad=True)
+            y = self._conv(to_ncdhw(self._c(x)).detach(), wp, None, g)
+            (dw,) = torch.autograd.grad(y, wp, to_ncdhw(self._c(dy)))
         db = self._c(dy).sum((0, 1, 2, 3)).float() if want_bias else None
         return dw.float(), db
 
