@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""Benchmark of the CycleGAN training hot path (BASELINE.json metric: train voxels/sec at 128^3).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this framework on N B200s
+    python bench.py --impl reference [...]                         # the reference's CPU path (oracle port)
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL).  A "step" is one
+``CycleGANModel.optimize_parameters()`` on a synthetic U(-1,1) 128^3 batch; rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PATCH = 128
+FLOP_PER_SAMPLE_STEP = 48.540e12        # conv MACs x2, fwd+dgrad+wgrad, 128^3
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p, "measured"
+    except Exception:  # noqa: BLE001
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:  # noqa: BLE001
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for nm, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        # samples taken while the GPU was busy = upper half of the distribution
+        busy = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_opt(**kw):
+    ns = argparse.Namespace(
+        gpu_ids=0, isTrain=True, checkpoints_dir="/tmp/mra_bench_ckpt", name="bench", input_nc=1, output_nc=1,
+        ngf=64, ndf=64, netG="resnet_9blocks", netD="n_layers", n_layers_D=3, norm="instance", no_dropout=True,
+        init_type="normal", init_gain=0.02, no_lsgan=False, pool_size=50, lr=2e-4, beta1=0.5, lambda_A=10.0,
+        lambda_B=10.0, lambda_identity=0.5, lambda_co_A=2, lambda_co_B=2, which_direction="AtoB",
+        lr_policy="lambda", epoch_count=1, niter=500, niter_decay=100, lr_decay_iters=50, continue_train=False,
+        which_epoch="latest", verbose=False, model="cycle_gan", model_suffix="", batch_size=1)
+    for k, v in kw.items():
+        setattr(ns, k, v)
+    return ns
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the reference's algorithm (oracle port) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_step_seconds(size, steps, warmup, ngf=64):
+    import random
+
+    import torch
+
+    from oracle import functional as OF
+    random.seed(1234)
+    sds = OF.build_cyclegan_weights(ngf, ngf, seed=1234)
+    m = OF.CycleGANOracle(*sds, netG="resnet_9blocks", no_lsgan=False)
+    times = []
+    for s in range(warmup + steps):
+        A, B = OF.synthetic_patches(1, size, seed=1234 + s)
+        t0 = time.perf_counter()
+        m.optimize_parameters(A, B)
+        float(m.losses["G"].detach())
+        if s >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), torch.get_num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is
+    pure Python on torch CPU and cannot be pip-installed: no setup.py), bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    # calibrate on a tiny patch, then pick the largest patch that keeps the run within ~3 minutes
+    t_small, threads = cpu_step_seconds(32, 1, 0)
+    budget = 170.0
+    size = 32
+    for cand in (64, 48):
+        est = t_small * (cand / 32.0) ** 3 * (args.steps + args.warmup)
+        if est < budget:
+            size = cand
+            break
+    sec, threads = cpu_step_seconds(size, args.steps, args.warmup)
+    vox = size ** 3 / sec
+    line = {
+        "impl": "reference", "metric": "cyclegan_train_voxels_per_sec", "value": vox, "unit": "voxels/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "resnet_9blocks G + 3-layer PatchGAN D, ngf=ndf=64, LSGAN, one optimize_parameters()",
+                   "patch": size, "batch": 1, "note": "CPU sample of the 128^3 workload (same model, smaller patch)"},
+        "cpu_baseline": {"value": vox, "unit": "voxels/s", "cores": threads, "kind": "port",
+                         "sample": "%d^3 patch, batch 1, fp32, %d timed step(s), torch CPU %s" % (size, args.steps, torch.__version__)},
+        "e2e": {"value": vox, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def time_dominant_kernel(torch, I, batch, reps=20):
+    """The dominant kernel: the 256->256 k3 conv on the padded 34^3 tensor (G.rb fprop = gather_tc_kernel,
+    79.7 % of generator FLOPs).  Timed alone with CUDA events on the launching stream."""
+    from mra_gan_b200.ops import ConvGeom
+    g = ConvGeom(256, 256, 3, 1, 0)
+    x = torch.randn((batch, 34, 34, 34, 256), device="cuda").to(torch.bfloat16)
+    w = (torch.randn((27, 256, 256), device="cuda") * 0.02).to(torch.bfloat16)
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        I.conv_fprop(x, w, None, g, want_stats=True)
+    total = 0.0
+    for _ in range(reps):
+        flush.zero_()                                  # evict the operands from L2 between launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        I.conv_fprop(x, w, None, g, want_stats=True)
+        e1.record()
+        e1.synchronize()
+        total += e0.elapsed_time(e1)
+    ms = total / reps
+    flops = 2.0 * batch * 32 ** 3 * 256 * 256 * 27
+    return ms, flops
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from mra_gan_b200 import networks3D as N3
+    from mra_gan_b200 import ops, parallel
+    from mra_gan_b200.models import create_model
+
+    rank, world = parallel.init_distributed()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if args.gpus != world and rank == 0:
+        print("warning: --gpus %d but WORLD_SIZE=%d (launch with torchrun for N>1)" % (args.gpus, world), file=sys.stderr)
+    per_gpu_batch = args.batch if args.batch else (2 if world == 1 else 4)
+    N3.set_default_compute_dtype(torch.bfloat16)
+    torch.manual_seed(1234)
+    import random
+    random.seed(1234 + rank)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = create_model(make_opt())
+        model.setup(make_opt())
+    I = ops.impl()
+    if world > 1:
+        parallel.attach(model)
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    shape = (per_gpu_batch, 1, PATCH, PATCH, PATCH)
+    host_A = (torch.rand(shape, generator=g) * 2 - 1).pin_memory()
+    host_B = (torch.rand(shape, generator=g) * 2 - 1).pin_memory()
+    dev_A, dev_B = host_A.cuda(), host_B.cuda()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    def step_resident():
+        model.set_input([dev_A, dev_B])
+        model.optimize_parameters()
+
+    last_losses = {}
+
+    def step_e2e():
+        model.set_input([host_A, host_B])           # pinned host -> device inside the timed region
+        model.optimize_parameters()
+        last_losses.update(model.get_current_losses())   # device -> host read of the 8 losses
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = I.launch_count()
+    ms_step = timed(step_resident, args.steps)
+    launches = (I.launch_count() - launches0) // args.steps
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if sampler else None
+    err = I.tc_error()
+
+    global_batch = per_gpu_batch * world
+    vox = global_batch * PATCH ** 3 / (ms_step * 1e-3)
+    vox_e2e = global_batch * PATCH ** 3 / (ms_e2e * 1e-3)
+    if rank != 0:
+        return 0
+
+    peaks, peak_src = load_peaks()
+    k_ms, k_flops = time_dominant_kernel(torch, I, per_gpu_batch)
+    achieved = k_flops / (k_ms * 1e-3) / 1e12
+    peak = float(peaks.get("bf16_tflops", 1590.0))
+    line = {
+        "metric": "cyclegan_train_voxels_per_sec", "value": vox, "unit": "voxels/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "resnet_9blocks G + 3-layer PatchGAN D, ngf=ndf=64, LSGAN, one CycleGAN "
+                               "optimize_parameters() on synthetic 128^3 patches",
+                   "patch": PATCH, "per_gpu_batch": per_gpu_batch, "global_batch": global_batch,
+                   "parallelism": "dp%d" % world, "l2": "per-step working set (tens of GB) >> 126 MB L2",
+                   "model_tflop_per_sample_step": FLOP_PER_SAMPLE_STEP / 1e12},
+        "e2e": {"value": vox_e2e, "unit": "voxels/s", "h2d_bytes_per_step": int(host_A.numel() * 4 * 2),
+                "d2h_bytes_per_step": 8 * 4, "ms_per_step": ms_e2e},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "model_tflops": global_batch * FLOP_PER_SAMPLE_STEP / (ms_step * 1e-3) / 1e12,
+        "roofline": {"bound": "tensor", "kernel": "gather_tc_kernel (Conv3d 256->256 k3, 34^3->32^3, batch %d)" % per_gpu_batch,
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "peak_source": peak_src + " bf16_tflops (burst: kernel timed alone)", "ms_per_launch": k_ms,
+                     "traffic": None},
+        "tc_error_flag": err,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        sec, threads = cpu_step_seconds(64, 1, 0)
+        line["cpu_baseline"] = {"value": 64 ** 3 / sec, "unit": "voxels/s", "cores": threads, "kind": "port",
+                                "sample": "BASELINE config 1: 64^3 patch, batch 1, fp32, first optimize_parameters() "
+                                          "(%.1f s) of the oracle port on the host cores" % sec}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 2 on 1 GPU, 4 per GPU on N>1)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -155,6 +155,9 @@ int mra_conv_plan_describe(const mra_conv_desc* d, int which, int32_t* out, int 
  * bounded mbarrier wait expires.  Synchronises the device; for tests / debugging only. */
 int mra_debug_tc_error(int reset);
 
+/* Number of kernels this library has launched in this process (host-side counter). */
+long long mra_debug_launch_count(void);
+
 const char* mra_last_error(void);
 int mra_version(void);
 

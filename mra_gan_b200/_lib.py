@@ -38,6 +38,7 @@ _SIGNATURES = {
     "mra_version": ([], C.c_int),
     "mra_last_error": ([], C.c_char_p),
     "mra_debug_tc_error": ([_I], C.c_int),
+    "mra_debug_launch_count": ([], C.c_longlong),
     "mra_conv3d_fprop": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P], C.c_int),
     "mra_conv3d_dgrad": ([C.POINTER(ConvDesc), _P, _P, _P, _P], C.c_int),
     "mra_conv3d_wgrad": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P], C.c_int),

@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <atomic>
 #include <string>
 
 #include "../../include/mra_gan_b200.h"
@@ -36,7 +37,13 @@ inline int fail(int code, const char* fmt, ...) {
   do {                                                                                    \
     if (!(cond)) return ::mra::fail(-1, __VA_ARGS__);                                     \
   } while (0)
-#define MRA_LAUNCH_CHECK() MRA_CHECK_CUDA(cudaGetLastError())
+// every kernel launch site is followed by exactly one MRA_LAUNCH_CHECK(): it doubles as the launch counter
+extern std::atomic<long long> g_launch_count;
+#define MRA_LAUNCH_CHECK()                                                                \
+  do {                                                                                    \
+    ::mra::g_launch_count.fetch_add(1, std::memory_order_relaxed);                        \
+    MRA_CHECK_CUDA(cudaGetLastError());                                                   \
+  } while (0)
 
 inline int num_sms() {
   static int n = 0;

@@ -10,6 +10,7 @@
 
 namespace mra {
 thread_local std::string g_last_error;
+std::atomic<long long> g_launch_count{0};
 }
 using namespace mra;
 
@@ -57,6 +58,7 @@ static NaiveGatherP naive_params(const mra_conv_desc& d, int which, const void* 
 extern "C" {
 
 int mra_version(void) { return 100; }
+long long mra_debug_launch_count(void) { return g_launch_count.load(); }
 const char* mra_last_error(void) { return g_last_error.c_str(); }
 
 int mra_conv3d_uses_tensor_cores(const mra_conv_desc* d, int which) {

@@ -285,6 +285,9 @@ class CudaImpl:
     def tc_error(self, reset=True):
         return int(self.L.mra_debug_tc_error(int(reset)))
 
+    def launch_count(self):
+        return int(self.L.mra_debug_launch_count())
+
 
 _impl = None
 
