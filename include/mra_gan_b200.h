@@ -57,13 +57,17 @@ typedef struct mra_conv_desc {
  * output accumulated into `stats` ([n][cout][2] doubles, zeroed by the call) for the InstanceNorm
  * that follows (models/networks3D.py:188,196,209,242,257,404,413). */
 int mra_conv3d_fprop(const mra_conv_desc* d, const void* x, const void* w, const float* bias,
-                     void* y, double* stats, mra_stream_t stream);
+                     void* y, double* stats, void* workspace, size_t workspace_bytes,
+                     mra_stream_t stream);
 /* dx = conv^T(dy, w): gradient wrt the op's input (ATen convolution_backward, input part). */
 int mra_conv3d_dgrad(const mra_conv_desc* d, const void* dy, const void* wT, void* dx,
-                     mra_stream_t stream);
+                     void* workspace, size_t workspace_bytes, mra_stream_t stream);
 /* dw[taps][cout][cin] (fp32) and optional dbias[cout] (fp32) (convolution_backward, weight/bias part). */
 int mra_conv3d_wgrad(const mra_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias,
-                     mra_stream_t stream);
+                     void* workspace, size_t workspace_bytes, mra_stream_t stream);
+/* Bytes of caller-provided scratch the op needs (which: 0 fprop, 1 dgrad, 2 wgrad); 0 for most
+ * layers -- only the channel-expanded stem (Cin = 1) / head (Cout = 1) lowerings use any. */
+size_t mra_conv3d_workspace_size(const mra_conv_desc* d, int which);
 /* 1 if the tcgen05 tensor-core path serves this descriptor's fprop(0)/dgrad(1)/wgrad(2). */
 int mra_conv3d_uses_tensor_cores(const mra_conv_desc* d, int which);
 

@@ -39,9 +39,10 @@ _SIGNATURES = {
     "mra_last_error": ([], C.c_char_p),
     "mra_debug_tc_error": ([_I], C.c_int),
     "mra_debug_launch_count": ([], C.c_longlong),
-    "mra_conv3d_fprop": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P], C.c_int),
-    "mra_conv3d_dgrad": ([C.POINTER(ConvDesc), _P, _P, _P, _P], C.c_int),
-    "mra_conv3d_wgrad": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P], C.c_int),
+    "mra_conv3d_fprop": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, C.c_size_t, _P], C.c_int),
+    "mra_conv3d_dgrad": ([C.POINTER(ConvDesc), _P, _P, _P, _P, C.c_size_t, _P], C.c_int),
+    "mra_conv3d_wgrad": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, C.c_size_t, _P], C.c_int),
+    "mra_conv3d_workspace_size": ([C.POINTER(ConvDesc), _I], C.c_size_t),
     "mra_conv3d_uses_tensor_cores": ([C.POINTER(ConvDesc), _I], C.c_int),
     "mra_pack_weight_t": ([_P, _I, _P, _I, _I, _I, _I, _P], C.c_int),
     "mra_convert": ([_P, _I, _P, _I, _L, _P], C.c_int),

@@ -78,37 +78,52 @@ inline void choose_box(const int dims[3], int total, int maxw, int box[3]) {
   box[0] = bb[0]; box[1] = bb[1]; box[2] = bb[2];
 }
 
-inline bool build_gather_plan(const mra_conv_desc& d, int which, GatherPlan& P) {
+// Extended geometry: per-axis kernel extent and zero padding (the public descriptor is cubic; the
+// stem / head lowerings in conv_special.cuh use (7,1,1) kernels on channel-expanded tensors).
+struct GeomEx {
+  int n, cin, cout;
+  int in[3], out[3];   // x / y spatial dims (d, h, w)
+  int k[3], pad[3];
+  int stride;
+  int transposed;
+};
+
+inline GeomEx geom_from_desc(const mra_conv_desc& d) {
+  GeomEx g;
+  g.n = d.n; g.cin = d.cin; g.cout = d.cout;
+  g.in[0] = d.din; g.in[1] = d.hin; g.in[2] = d.win;
+  g.out[0] = d.dout; g.out[1] = d.hout; g.out[2] = d.wout;
+  for (int i = 0; i < 3; ++i) { g.k[i] = d.k; g.pad[i] = d.pad; }
+  g.stride = d.stride; g.transposed = d.transposed;
+  return g;
+}
+
+inline bool build_gather_plan(const GeomEx& d, int which, GatherPlan& P) {
   // which: 0 = fprop (A = x, out = y), 1 = dgrad (A = dy, out = dx)
-  const int k = d.k, s = d.stride, p = d.pad;
+  const int s = d.stride;
   if (s != 1 && s != 2) return false;
   const bool fprop = which == 0;
   P.n = d.n;
   P.ck = fprop ? d.cin : d.cout;
   P.cn = fprop ? d.cout : d.cin;
-  const int xin[3] = {d.din, d.hin, d.win}, yout[3] = {d.dout, d.hout, d.wout};
   for (int i = 0; i < 3; ++i) {
-    P.adims[i] = fprop ? xin[i] : yout[i];
-    P.odims[i] = fprop ? yout[i] : xin[i];
+    P.adims[i] = fprop ? d.in[i] : d.out[i];
+    P.odims[i] = fprop ? d.out[i] : d.in[i];
   }
   // direct addressing: A coord = o*s - p + t.  Used by conv fprop and convT dgrad.
   const bool direct = (fprop && !d.transposed) || (!fprop && d.transposed);
+  const int K0 = d.k[0], K1 = d.k[1], K2 = d.k[2];
+  auto widx = [&](int a, int b, int c) { return (a * K1 + b) * K2 + c; };
   P.launches.clear();
-  if (direct) {
+  if (direct || s == 1) {
     GatherLaunch L;
     for (int i = 0; i < 3; ++i) { L.o0[i] = 0; L.dims[i] = P.odims[i]; }
-    L.ostep = 1; L.astep = s;
-    for (int kd = 0; kd < k; ++kd) for (int kh = 0; kh < k; ++kh) for (int kw = 0; kw < k; ++kw)
-      L.taps.push_back(Tap{kd - p, kh - p, kw - p, (kd * k + kh) * k + kw});
-    choose_box(L.dims, 128, 256 / s, L.box);
-    P.launches.push_back(L);
-  } else if (s == 1) {
-    GatherLaunch L;
-    for (int i = 0; i < 3; ++i) { L.o0[i] = 0; L.dims[i] = P.odims[i]; }
-    L.ostep = 1; L.astep = 1;
-    for (int kd = 0; kd < k; ++kd) for (int kh = 0; kh < k; ++kh) for (int kw = 0; kw < k; ++kw)
-      L.taps.push_back(Tap{p - kd, p - kh, p - kw, (kd * k + kh) * k + kw});
-    choose_box(L.dims, 128, 256, L.box);
+    L.ostep = 1; L.astep = direct ? s : 1;
+    for (int kd = 0; kd < K0; ++kd) for (int kh = 0; kh < K1; ++kh) for (int kw = 0; kw < K2; ++kw) {
+      if (direct) L.taps.push_back(Tap{kd - d.pad[0], kh - d.pad[1], kw - d.pad[2], widx(kd, kh, kw)});
+      else        L.taps.push_back(Tap{d.pad[0] - kd, d.pad[1] - kh, d.pad[2] - kw, widx(kd, kh, kw)});
+    }
+    choose_box(L.dims, 128, 256 / L.astep, L.box);
     P.launches.push_back(L);
   } else {
     for (int rd = 0; rd < 2; ++rd) for (int rh = 0; rh < 2; ++rh) for (int rw = 0; rw < 2; ++rw) {
@@ -122,42 +137,46 @@ inline bool build_gather_plan(const mra_conv_desc& d, int which, GatherPlan& P) 
       }
       if (empty) continue;
       L.ostep = 2; L.astep = 1;
-      for (int kd = 0; kd < k; ++kd) {
-        if ((rd + p - kd) & 1) continue;
-        for (int kh = 0; kh < k; ++kh) {
-          if ((rh + p - kh) & 1) continue;
-          for (int kw = 0; kw < k; ++kw) {
-            if ((rw + p - kw) & 1) continue;
-            L.taps.push_back(Tap{(rd + p - kd) / 2, (rh + p - kh) / 2, (rw + p - kw) / 2,
-                                 (kd * k + kh) * k + kw});
+      for (int kd = 0; kd < K0; ++kd) {
+        if ((rd + d.pad[0] - kd) & 1) continue;
+        for (int kh = 0; kh < K1; ++kh) {
+          if ((rh + d.pad[1] - kh) & 1) continue;
+          for (int kw = 0; kw < K2; ++kw) {
+            if ((rw + d.pad[2] - kw) & 1) continue;
+            L.taps.push_back(Tap{(rd + d.pad[0] - kd) / 2, (rh + d.pad[1] - kh) / 2, (rw + d.pad[2] - kw) / 2,
+                                 widx(kd, kh, kw)});
           }
         }
       }
+      if (L.taps.empty()) continue;
       choose_box(L.dims, 128, 256, L.box);
       P.launches.push_back(L);
     }
   }
   return true;
 }
+inline bool build_gather_plan(const mra_conv_desc& d, int which, GatherPlan& P) {
+  return build_gather_plan(geom_from_desc(d), which, P);
+}
 
-inline bool build_wgrad_plan(const mra_conv_desc& d, WgradPlan& P) {
-  const int k = d.k, s = d.stride, p = d.pad;
+inline bool build_wgrad_plan(const GeomEx& d, WgradPlan& P) {
+  const int s = d.stride;
   if (s != 1 && s != 2) return false;
   P.n = d.n; P.cm = d.cout; P.cn = d.cin;
-  const int xin[3] = {d.din, d.hin, d.win}, yout[3] = {d.dout, d.hout, d.wout};
   for (int i = 0; i < 3; ++i) {
-    P.mdims[i] = yout[i];          // M operand = dy
-    P.ndims[i] = xin[i];           // N operand = x
-    P.qdims[i] = d.transposed ? xin[i] : yout[i];
+    P.mdims[i] = d.out[i];         // M operand = dy
+    P.ndims[i] = d.in[i];          // N operand = x
+    P.qdims[i] = d.transposed ? d.in[i] : d.out[i];
   }
   P.sstep = s;
   P.m_is_shifted = d.transposed ? 1 : 0;
   P.taps.clear();
-  for (int kd = 0; kd < k; ++kd) for (int kh = 0; kh < k; ++kh) for (int kw = 0; kw < k; ++kw)
-    P.taps.push_back(Tap{kd - p, kh - p, kw - p, (kd * k + kh) * k + kw});
+  for (int kd = 0; kd < d.k[0]; ++kd) for (int kh = 0; kh < d.k[1]; ++kh) for (int kw = 0; kw < d.k[2]; ++kw)
+    P.taps.push_back(Tap{kd - d.pad[0], kh - d.pad[1], kw - d.pad[2], (kd * d.k[1] + kh) * d.k[2] + kw});
   choose_box(P.qdims, 64, 256 / s, P.box);
   return true;
 }
+inline bool build_wgrad_plan(const mra_conv_desc& d, WgradPlan& P) { return build_wgrad_plan(geom_from_desc(d), P); }
 
 // Serialisation for mra_conv_plan_describe():
 //  gather: [0, n, ck, cn, adims[3], odims[3], nlaunch, then per launch:

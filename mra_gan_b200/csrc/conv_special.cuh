@@ -1,0 +1,420 @@
+// Tensor-core lowering of the two degenerate-channel layers of the generator:
+//
+//   STEM  Conv3d(1 -> Co, k, pad 0) on the replication-padded image   (networks3D.py:185-187)
+//   HEAD  Conv3d(Ci -> 1, k, pad 0) on the replication-padded features (networks3D.py:211-213)
+//
+// A direct implicit GEMM would have K = k^3 with Cin = 1 (stem) or N = 1 (head): hopeless for the MMA.
+// Instead the (kh, kw) taps are folded into a 64-wide channel axis, c = kh*8 + kw (k <= 8):
+//
+//   stem fprop : E[n,d,h,w,c]   = x[n,d,h+kh,w+kw]                       (expand_hw, sgn = +1)
+//                y              = GATHER_{kd}(E, B[kd][co][c])           (Cin=64 conv with a (k,1,1) kernel)
+//   stem wgrad : dWe[kd][co][c] = WGRAD(dy, E)  -> scatter back to dw[(kd,kh,kw)][co]
+//   stem dgrad : Z[n,d',h,w,c]  = GATHER_{kd}(dy, B^T)  ; dx[n,d',h',w'] = sum_c Z[n,d',h'-kh,w'-kw,c]  (shift_sum, sgn = -1)
+//   head fprop : Z[n,d,h',w',c] = GATHER_{kd}(x, B[kd][c][ci]) ; y = act(bias + sum_c Z[n,d,h+kh,w+kw,c]) (shift_sum, sgn = +1)
+//   head dgrad : E'[n,d,h',w',c] = dy[n,d,h'-kh,w'-kw] (expand_hw, sgn = -1) ; dx = GATHER_{kd}(E', B^T)
+//   head wgrad : dWe[kd][c][ci] = WGRAD(E', x)  -> scatter back to dw[(kd,kh,kw)][ci]
+//
+// so all six run on gather_tc_kernel / wgrad_tc_kernel; the helpers here are small HBM-bound kernels.
+// Cost: K efficiency k^2/64 (77 % for k = 7) and one extra 64-channel intermediate (E or Z) per call.
+#pragma once
+#include "common.cuh"
+#include "conv_plan.h"
+#include "conv_tc.cuh"
+
+namespace mra {
+namespace special {
+
+// out[n,d,ho,wo,kh*8+kw] = src[n,d,ho+sgn*kh+off,wo+sgn*kw+off] (0 out of range / kh,kw >= k).  One thread = one kh row (8 ch).
+__global__ void __launch_bounds__(256) expand_hw_kernel(const bf16* __restrict__ src, bf16* __restrict__ out, long long rows /*N*D*/,
+                                                         int Hs, int Ws, int Ho, int Wo, int k, int sgn, int off) {
+  const long long total = rows * Ho * Wo * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int kh = (int)(i & 7);
+    long long p = i >> 3;
+    const int wo = (int)(p % Wo); p /= Wo;
+    const int ho = (int)(p % Ho);
+    const long long r = p / Ho;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    const int hs = ho + sgn * kh + off;
+    if (kh < k && hs >= 0 && hs < Hs) {
+      const bf16* row = src + (r * Hs + hs) * Ws;
+#pragma unroll
+      for (int kw = 0; kw < 8; ++kw) {
+        const int ws = wo + sgn * kw + off;
+        if (kw < k && ws >= 0 && ws < Ws) v[kw] = __bfloat162float(row[ws]);
+      }
+    }
+    Vec8<bf16>::store(out + (i >> 3) * 64 + kh * 8, v);
+  }
+}
+
+// out[n,d,ho,wo] = act(bias + sum_{kh,kw<k} Z[n,d,ho+sgn*kh,wo+sgn*kw,kh*8+kw])
+template <typename TZ, typename TO>
+__global__ void __launch_bounds__(256) shift_sum_kernel(const TZ* __restrict__ Z, TO* __restrict__ out, long long rows, int Hz,
+                                                         int Wz, int Ho, int Wo, int k, int sgn, int off,
+                                                         const float* __restrict__ bias, int act, float slope) {
+  const long long total = rows * Ho * Wo;
+  const float b = bias ? bias[0] : 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int wo = (int)(i % Wo);
+    const int ho = (int)((i / Wo) % Ho);
+    const long long r = i / ((long long)Wo * Ho);
+    float acc = 0.f;
+    for (int kh = 0; kh < k; ++kh) {
+      const int hz = ho + sgn * kh + off;
+      if (hz < 0 || hz >= Hz) continue;
+      for (int kw = 0; kw < k; ++kw) {
+        const int wz = wo + sgn * kw + off;
+        if (wz < 0 || wz >= Wz) continue;
+        acc += to_f(Z[((r * Hz + hz) * Wz + wz) * 64 + kh * 8 + kw]);
+      }
+    }
+    out[i] = from_f<TO>(apply_act(acc + b, act, slope));
+  }
+}
+
+// src [k^3][C] (the packed weight of a layer whose other channel count is 1)
+//   mode 0: dst[kd][ch][c] = src[(kd,kh,kw)][ch]      mode 1: dst[kd][c][ch] = src[(kd,kh,kw)][ch]     (c = kh*8+kw)
+__global__ void wexp_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int k, int C, int mode) {
+  const int total = k * C * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int kd, ch, c;
+    if (mode == 0) { c = i % 64; ch = (i / 64) % C; kd = i / (64 * C); }
+    else           { ch = i % C; c = (i / C) % 64; kd = i / (64 * C); }
+    const int kh = c >> 3, kw = c & 7;
+    bf16 v = __float2bfloat16_rn(0.f);
+    if (kh < k && kw < k) v = src[((long long)(kd * k + kh) * k + kw) * C + ch];
+    dst[i] = v;
+  }
+}
+// dw[(kd,kh,kw)][ch] += dWe (mode 0: dWe[kd][ch][c], mode 1: dWe[kd][c][ch])
+__global__ void wunexp_kernel(const float* __restrict__ dwe, float* __restrict__ dw, int k, int C, int mode) {
+  const int total = k * k * k * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ch = i % C;
+    const int t = i / C;
+    const int kw = t % k, kh = (t / k) % k, kd = t / (k * k);
+    const int c = kh * 8 + kw;
+    const float v = mode == 0 ? dwe[((long long)kd * C + ch) * 64 + c] : dwe[((long long)kd * 64 + c) * C + ch];
+    dw[i] += v;
+  }
+}
+
+// PatchGAN layer 0 (networks3D.py:392): Conv3d(1 -> Co, k4, s2, p1).  With Cin = 1 and k^3 <= 64 the whole
+// receptive field fits one 64-wide channel axis: E[n,o,(kd,kh,kw)] = x[n, o*s - p + k] (im2col), after which
+// the layer is a 1x1x1 convolution (one GEMM tap) on the tensor cores; dgrad is the GEMM followed by col2im.
+__global__ void __launch_bounds__(256) im2col1_kernel(const bf16* __restrict__ x, bf16* __restrict__ E, int N, int Di, int Hi, int Wi,
+                                                       int Do, int Ho, int Wo, int k, int s, int p) {
+  const long long total = (long long)N * Do * Ho * Wo * 8;       // one thread = 8 consecutive channels
+  const int taps = k * k * k;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i & 7) * 8;
+    long long q = i >> 3;
+    const int ow = (int)(q % Wo); q /= Wo;
+    const int oh = (int)(q % Ho); q /= Ho;
+    const int od = (int)(q % Do);
+    const int n = (int)(q / Do);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int t = c0 + j;
+      v[j] = 0.f;
+      if (t < taps) {
+        const int kw = t % k, kh = (t / k) % k, kd = t / (k * k);
+        const int d = od * s - p + kd, h = oh * s - p + kh, w = ow * s - p + kw;
+        if (d >= 0 && d < Di && h >= 0 && h < Hi && w >= 0 && w < Wi)
+          v[j] = __bfloat162float(x[(((long long)n * Di + d) * Hi + h) * Wi + w]);
+      }
+    }
+    Vec8<bf16>::store(E + (i >> 3) * 64 + c0, v);
+  }
+}
+// dx[n,i] = sum over (o, k) with o*s - p + k == i of dE[n,o,(kd,kh,kw)]
+__global__ void __launch_bounds__(256) col2im1_kernel(const bf16* __restrict__ dE, bf16* __restrict__ dx, int N, int Di, int Hi, int Wi,
+                                                       int Do, int Ho, int Wo, int k, int s, int p) {
+  const long long total = (long long)N * Di * Hi * Wi;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long q = i;
+    const int w = (int)(q % Wi); q /= Wi;
+    const int h = (int)(q % Hi); q /= Hi;
+    const int d = (int)(q % Di);
+    const int n = (int)(q / Di);
+    float acc = 0.f;
+    for (int kd = 0; kd < k; ++kd) {
+      const int a = d + p - kd;
+      if (a < 0 || a % s) continue;
+      const int od = a / s;
+      if (od >= Do) continue;
+      for (int kh = 0; kh < k; ++kh) {
+        const int b = h + p - kh;
+        if (b < 0 || b % s) continue;
+        const int oh = b / s;
+        if (oh >= Ho) continue;
+        for (int kw = 0; kw < k; ++kw) {
+          const int c = w + p - kw;
+          if (c < 0 || c % s) continue;
+          const int ow = c / s;
+          if (ow >= Wo) continue;
+          acc += __bfloat162float(dE[((((long long)n * Do + od) * Ho + oh) * Wo + ow) * 64 + (kd * k + kh) * k + kw]);
+        }
+      }
+    }
+    dx[i] = __float2bfloat16_rn(acc);
+  }
+}
+// B[co][c] = w[c][co] (c < taps, else 0)  /  BT[c][co]  /  dw[t][co] += dWe[co][t]
+__global__ void im2col_w_kernel(const bf16* __restrict__ w, bf16* __restrict__ B, int taps, int C, int transpose) {
+  const int total = C * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int ch, c;
+    if (!transpose) { c = i % 64; ch = i / 64; } else { ch = i % C; c = i / C; }
+    B[i] = c < taps ? w[(long long)c * C + ch] : __float2bfloat16_rn(0.f);
+  }
+}
+__global__ void im2col_dw_kernel(const float* __restrict__ dwe, float* __restrict__ dw, int taps, int C) {
+  const int total = taps * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ch = i % C, t = i / C;
+    dw[i] += dwe[(long long)ch * 64 + t];
+  }
+}
+
+struct Workspace {
+  char* base; size_t size, off;
+  void* take(size_t bytes) {
+    off = (off + 255) & ~size_t(255);
+    if (off + bytes > size) return nullptr;
+    void* p = base + off;
+    off += bytes;
+    return p;
+  }
+};
+
+inline bool stem_eligible(const mra_conv_desc& d) {
+  return d.dtype == MRA_BF16 && !(d.flags & MRA_CONV_FORCE_NAIVE) && !d.transposed && d.stride == 1 && d.pad == 0 &&
+         d.cin == 1 && d.k >= 2 && d.k <= 8 && tc::pick_n_tile(d.cout) > 0;
+}
+inline bool head_eligible(const mra_conv_desc& d) {
+  return d.dtype == MRA_BF16 && !(d.flags & MRA_CONV_FORCE_NAIVE) && !d.transposed && d.stride == 1 && d.pad >= 0 &&
+         d.pad < d.k && d.cout == 1 && d.k >= 2 && d.k <= 8 && d.cin % 64 == 0;
+}
+
+inline bool im2col_eligible(const mra_conv_desc& d) {
+  return d.dtype == MRA_BF16 && !(d.flags & MRA_CONV_FORCE_NAIVE) && !d.transposed && d.cin == 1 &&
+         d.k * d.k * d.k <= 64 && tc::pick_n_tile(d.cout) > 0 && !(d.stride == 1 && d.pad == 0 && d.k >= 2);
+}
+inline GeomEx im2col_geom(const mra_conv_desc& d) {    // E [N][Do][Ho][Wo][64] -> y [N][Do][Ho][Wo][Co], 1x1x1
+  GeomEx g;
+  g.n = d.n; g.cin = 64; g.cout = d.cout;
+  for (int i = 0; i < 3; ++i) { g.k[i] = 1; g.pad[i] = 0; }
+  g.in[0] = g.out[0] = d.dout; g.in[1] = g.out[1] = d.hout; g.in[2] = g.out[2] = d.wout;
+  g.stride = 1; g.transposed = 0;
+  return g;
+}
+
+// expanded-geometry helpers
+inline GeomEx stem_geom(const mra_conv_desc& d) {      // x := E [N][Din][Hout][Wout][64] -> y [N][Dout][Hout][Wout][Co]
+  GeomEx g;
+  g.n = d.n; g.cin = 64; g.cout = d.cout;
+  g.in[0] = d.din; g.in[1] = d.hout; g.in[2] = d.wout;
+  g.out[0] = d.dout; g.out[1] = d.hout; g.out[2] = d.wout;
+  g.k[0] = d.k; g.k[1] = 1; g.k[2] = 1;
+  g.pad[0] = g.pad[1] = g.pad[2] = 0;
+  g.stride = 1; g.transposed = 0;
+  return g;
+}
+inline GeomEx head_geom(const mra_conv_desc& d) {      // x [N][Din][Hin][Win][Ci] -> Z [N][Dout][Hin][Win][64]
+  GeomEx g;
+  g.n = d.n; g.cin = d.cin; g.cout = 64;
+  g.in[0] = d.din; g.in[1] = d.hin; g.in[2] = d.win;
+  g.out[0] = d.dout; g.out[1] = d.hin; g.out[2] = d.win;
+  g.k[0] = d.k; g.k[1] = 1; g.k[2] = 1;
+  g.pad[0] = d.pad; g.pad[1] = g.pad[2] = 0;      // (kh, kw) zero padding is applied by shift_sum / expand_hw
+  g.stride = 1; g.transposed = 0;
+  return g;
+}
+
+inline size_t a256(size_t v) { return (v + 255) & ~size_t(255); }
+inline size_t workspace_bytes(const mra_conv_desc& d, int which) {
+  const size_t wexp = a256((size_t)d.k * 64 * (d.cin == 1 ? d.cout : d.cin) * 2);
+  const size_t dwe = a256((size_t)d.k * 64 * (d.cin == 1 ? d.cout : d.cin) * 4);
+  if (im2col_eligible(d)) {
+    const size_t e = a256((size_t)d.n * d.dout * d.hout * d.wout * 64 * 2);
+    return e + a256((size_t)64 * d.cout * 4) + 512;
+  }
+  if (stem_eligible(d)) {
+    const size_t e = (size_t)d.n * d.din * d.hout * d.wout * 64;
+    if (which == 0) return a256(e * 2) + wexp + 512;
+    if (which == 1) return a256(e * 4) + wexp + 512;
+    return a256(e * 2) + dwe + 512;
+  }
+  if (head_eligible(d)) {
+    const size_t z = (size_t)d.n * d.dout * d.hin * d.win * 64;
+    if (which == 0) return a256(z * 4) + wexp + 512;
+    if (which == 1) return a256(z * 2) + wexp + 512;
+    return a256(z * 2) + dwe + 512;
+  }
+  return 0;
+}
+
+inline unsigned sgrid(long long n) {
+  long long b = (n + 255) / 256;
+  const long long cap = (long long)num_sms() * 32;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+#define MRA_WS_TAKE(var, type, bytes)                                                      \
+  type* var = reinterpret_cast<type*>(ws.take(bytes));                                      \
+  MRA_REQUIRE(var != nullptr, "workspace too small (need mra_conv3d_workspace_size bytes)")
+
+inline int im2col_fprop(const mra_conv_desc& d, const void* x, const void* w, const float* bias, void* y, double* stats,
+                        void* wsp, size_t wsb, cudaStream_t st) {
+  Workspace ws{(char*)wsp, wsb, 0};
+  const long long pos = (long long)d.n * d.dout * d.hout * d.wout;
+  MRA_WS_TAKE(E, bf16, (size_t)pos * 64 * 2);
+  MRA_WS_TAKE(B, bf16, (size_t)64 * d.cout * 2);
+  im2col1_kernel<<<sgrid(pos * 8), 256, 0, st>>>((const bf16*)x, E, d.n, d.din, d.hin, d.win, d.dout, d.hout, d.wout, d.k, d.stride, d.pad);
+  MRA_LAUNCH_CHECK();
+  im2col_w_kernel<<<sgrid(64 * d.cout), 256, 0, st>>>((const bf16*)w, B, d.k * d.k * d.k, d.cout, 0);
+  MRA_LAUNCH_CHECK();
+  GatherPlan plan;
+  MRA_REQUIRE(build_gather_plan(im2col_geom(d), 0, plan), "im2col plan");
+  tc::GatherRun R{E, B, 1, bias, y, 1, d.act, d.slope, stats};
+  return tc::run_gather_tc(plan, R, st);
+}
+inline int im2col_wgrad(const mra_conv_desc& d, const void* x, const void* dy, float* dw, void* wsp, size_t wsb, cudaStream_t st) {
+  Workspace ws{(char*)wsp, wsb, 0};
+  const long long pos = (long long)d.n * d.dout * d.hout * d.wout;
+  MRA_WS_TAKE(E, bf16, (size_t)pos * 64 * 2);
+  MRA_WS_TAKE(dWe, float, (size_t)64 * d.cout * 4);
+  im2col1_kernel<<<sgrid(pos * 8), 256, 0, st>>>((const bf16*)x, E, d.n, d.din, d.hin, d.win, d.dout, d.hout, d.wout, d.k, d.stride, d.pad);
+  MRA_LAUNCH_CHECK();
+  MRA_CHECK_CUDA(cudaMemsetAsync(dWe, 0, (size_t)64 * d.cout * 4, st));
+  WgradPlan plan;
+  MRA_REQUIRE(build_wgrad_plan(im2col_geom(d), plan), "im2col wgrad plan");
+  if (int rc = tc::run_wgrad_tc(plan, E, dy, dWe, st)) return rc;           // dWe[co][c]
+  im2col_dw_kernel<<<sgrid((long long)d.k * d.k * d.k * d.cout), 256, 0, st>>>(dWe, dw, d.k * d.k * d.k, d.cout);
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+inline int im2col_dgrad(const mra_conv_desc& d, const void* dy, const void* wT, void* dx, void* wsp, size_t wsb, cudaStream_t st) {
+  Workspace ws{(char*)wsp, wsb, 0};
+  const long long pos = (long long)d.n * d.dout * d.hout * d.wout;
+  MRA_WS_TAKE(dE, bf16, (size_t)pos * 64 * 2);
+  MRA_WS_TAKE(BT, bf16, (size_t)64 * d.cout * 2);
+  im2col_w_kernel<<<sgrid(64 * d.cout), 256, 0, st>>>((const bf16*)wT, BT, d.k * d.k * d.k, d.cout, 1);    // [c][co]
+  MRA_LAUNCH_CHECK();
+  GatherPlan plan;
+  MRA_REQUIRE(build_gather_plan(im2col_geom(d), 1, plan), "im2col dgrad plan");
+  tc::GatherRun R{dy, BT, 1, nullptr, dE, 1, MRA_ACT_NONE, 0.f, nullptr};
+  if (int rc = tc::run_gather_tc(plan, R, st)) return rc;
+  col2im1_kernel<<<sgrid((long long)d.n * d.din * d.hin * d.win), 256, 0, st>>>(dE, (bf16*)dx, d.n, d.din, d.hin, d.win, d.dout, d.hout,
+                                                                                  d.wout, d.k, d.stride, d.pad);
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+
+inline int stem_fprop(const mra_conv_desc& d, const void* x, const void* w, const float* bias, void* y, double* stats,
+                      void* wsp, size_t wsb, cudaStream_t st) {
+  Workspace ws{(char*)wsp, wsb, 0};
+  const long long rows = (long long)d.n * d.din;
+  MRA_WS_TAKE(E, bf16, (size_t)rows * d.hout * d.wout * 64 * 2);
+  MRA_WS_TAKE(B, bf16, (size_t)d.k * d.cout * 64 * 2);
+  expand_hw_kernel<<<sgrid(rows * d.hout * d.wout * 8), 256, 0, st>>>((const bf16*)x, E, rows, d.hin, d.win, d.hout, d.wout, d.k, +1, 0);
+  MRA_LAUNCH_CHECK();
+  wexp_kernel<<<sgrid((long long)d.k * d.cout * 64), 256, 0, st>>>((const bf16*)w, B, d.k, d.cout, 0);
+  MRA_LAUNCH_CHECK();
+  GatherPlan plan;
+  MRA_REQUIRE(build_gather_plan(stem_geom(d), 0, plan), "stem plan");
+  tc::GatherRun R{E, B, d.k, bias, y, 1, d.act, d.slope, stats};
+  return tc::run_gather_tc(plan, R, st);
+}
+
+inline int stem_wgrad(const mra_conv_desc& d, const void* x, const void* dy, float* dw, void* wsp, size_t wsb, cudaStream_t st) {
+  Workspace ws{(char*)wsp, wsb, 0};
+  const long long rows = (long long)d.n * d.din;
+  MRA_WS_TAKE(E, bf16, (size_t)rows * d.hout * d.wout * 64 * 2);
+  MRA_WS_TAKE(dWe, float, (size_t)d.k * d.cout * 64 * 4);
+  expand_hw_kernel<<<sgrid(rows * d.hout * d.wout * 8), 256, 0, st>>>((const bf16*)x, E, rows, d.hin, d.win, d.hout, d.wout, d.k, +1, 0);
+  MRA_LAUNCH_CHECK();
+  MRA_CHECK_CUDA(cudaMemsetAsync(dWe, 0, (size_t)d.k * d.cout * 64 * 4, st));
+  WgradPlan plan;
+  MRA_REQUIRE(build_wgrad_plan(stem_geom(d), plan), "stem wgrad plan");
+  if (int rc = tc::run_wgrad_tc(plan, E, dy, dWe, st)) return rc;
+  wunexp_kernel<<<sgrid((long long)d.k * d.k * d.k * d.cout), 256, 0, st>>>(dWe, dw, d.k, d.cout, 0);
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+
+inline int stem_dgrad(const mra_conv_desc& d, const void* dy, const void* wT, void* dx, void* wsp, size_t wsb, cudaStream_t st) {
+  Workspace ws{(char*)wsp, wsb, 0};
+  const long long rows = (long long)d.n * d.din;
+  MRA_WS_TAKE(Z, float, (size_t)rows * d.hout * d.wout * 64 * 4);
+  MRA_WS_TAKE(BT, bf16, (size_t)d.k * d.cout * 64 * 2);
+  wexp_kernel<<<sgrid((long long)d.k * d.cout * 64), 256, 0, st>>>((const bf16*)wT, BT, d.k, d.cout, 1);   // [kd][c][co]
+  MRA_LAUNCH_CHECK();
+  GatherPlan plan;
+  MRA_REQUIRE(build_gather_plan(stem_geom(d), 1, plan), "stem dgrad plan");
+  tc::GatherRun R{dy, BT, d.k, nullptr, Z, 0, MRA_ACT_NONE, 0.f, nullptr};
+  if (int rc = tc::run_gather_tc(plan, R, st)) return rc;
+  shift_sum_kernel<float, bf16><<<sgrid(rows * d.hin * d.win), 256, 0, st>>>(Z, (bf16*)dx, rows, d.hout, d.wout, d.hin, d.win, d.k, -1, 0,
+                                                                              nullptr, MRA_ACT_NONE, 0.f);
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+
+inline int head_fprop(const mra_conv_desc& d, const void* x, const void* w, const float* bias, void* y, void* wsp, size_t wsb,
+                      cudaStream_t st) {
+  Workspace ws{(char*)wsp, wsb, 0};
+  const long long rows = (long long)d.n * d.dout;
+  MRA_WS_TAKE(Z, float, (size_t)rows * d.hin * d.win * 64 * 4);
+  MRA_WS_TAKE(B, bf16, (size_t)d.k * d.cin * 64 * 2);
+  wexp_kernel<<<sgrid((long long)d.k * d.cin * 64), 256, 0, st>>>((const bf16*)w, B, d.k, d.cin, 1);       // [kd][c][ci]
+  MRA_LAUNCH_CHECK();
+  GatherPlan plan;
+  MRA_REQUIRE(build_gather_plan(head_geom(d), 0, plan), "head plan");
+  tc::GatherRun R{x, B, d.k, nullptr, Z, 0, MRA_ACT_NONE, 0.f, nullptr};
+  if (int rc = tc::run_gather_tc(plan, R, st)) return rc;
+  shift_sum_kernel<float, bf16><<<sgrid(rows * d.hout * d.wout), 256, 0, st>>>(Z, (bf16*)y, rows, d.hin, d.win, d.hout, d.wout, d.k, +1, -d.pad,
+                                                                                bias, d.act, d.slope);
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+
+inline int head_dgrad(const mra_conv_desc& d, const void* dy, const void* wT, void* dx, void* wsp, size_t wsb, cudaStream_t st) {
+  Workspace ws{(char*)wsp, wsb, 0};
+  const long long rows = (long long)d.n * d.dout;
+  MRA_WS_TAKE(E, bf16, (size_t)rows * d.hin * d.win * 64 * 2);
+  MRA_WS_TAKE(BT, bf16, (size_t)d.k * d.cin * 64 * 2);
+  expand_hw_kernel<<<sgrid(rows * d.hin * d.win * 8), 256, 0, st>>>((const bf16*)dy, E, rows, d.hout, d.wout, d.hin, d.win, d.k, -1, d.pad);
+  MRA_LAUNCH_CHECK();
+  wexp_kernel<<<sgrid((long long)d.k * d.cin * 64), 256, 0, st>>>((const bf16*)wT, BT, d.k, d.cin, 0);      // [kd][ci][c]
+  MRA_LAUNCH_CHECK();
+  GatherPlan plan;
+  MRA_REQUIRE(build_gather_plan(head_geom(d), 1, plan), "head dgrad plan");
+  tc::GatherRun R{E, BT, d.k, nullptr, dx, 1, MRA_ACT_NONE, 0.f, nullptr};
+  return tc::run_gather_tc(plan, R, st);
+}
+
+inline int head_wgrad(const mra_conv_desc& d, const void* x, const void* dy, float* dw, void* wsp, size_t wsb, cudaStream_t st) {
+  Workspace ws{(char*)wsp, wsb, 0};
+  const long long rows = (long long)d.n * d.dout;
+  MRA_WS_TAKE(E, bf16, (size_t)rows * d.hin * d.win * 64 * 2);
+  MRA_WS_TAKE(dWe, float, (size_t)d.k * d.cin * 64 * 4);
+  expand_hw_kernel<<<sgrid(rows * d.hin * d.win * 8), 256, 0, st>>>((const bf16*)dy, E, rows, d.hout, d.wout, d.hin, d.win, d.k, -1, d.pad);
+  MRA_LAUNCH_CHECK();
+  MRA_CHECK_CUDA(cudaMemsetAsync(dWe, 0, (size_t)d.k * d.cin * 64 * 4, st));
+  WgradPlan plan;
+  MRA_REQUIRE(build_wgrad_plan(head_geom(d), plan), "head wgrad plan");
+  if (int rc = tc::run_wgrad_tc(plan, x, E, dWe, st)) return rc;      // dWe[kd][c][ci]
+  wunexp_kernel<<<sgrid((long long)d.k * d.k * d.k * d.cin), 256, 0, st>>>(dWe, dw, d.k, d.cin, 1);
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace special
+}  // namespace mra

@@ -516,16 +516,26 @@ inline bool wgrad_eligible(const mra_conv_desc& d) {
   return true;
 }
 
+struct GatherRun {
+  const void* a;        // activations (bf16, channels-last)
+  const void* b;        // packed weights [slabs][cn][ck] (bf16)
+  int slabs;            // number of weight slabs addressed by tap.widx
+  const float* bias;
+  void* out;
+  int out_bf16;         // 1: bf16 output, 0: fp32 output
+  int act;
+  float slope;
+  double* stats;
+};
+
 // Run every launch of a gather plan on the tensor cores.
-inline int run_gather_tc(const mra_conv_desc& d, int which, const void* a, const void* b, const float* bias, void* out,
-                         double* stats, cudaStream_t st) {
-  GatherPlan plan;
-  MRA_REQUIRE(build_gather_plan(d, which, plan), "unsupported conv geometry");
+inline int run_gather_tc(const GatherPlan& plan, const GatherRun& R, cudaStream_t st) {
   int* err = tc_err_flag();
   const int n_tile = pick_n_tile(plan.cn);
-  const long long rows = (long long)d.k * d.k * d.k * plan.cn;
+  MRA_REQUIRE(n_tile > 0 && plan.ck % 64 == 0, "channel counts not eligible for the tensor-core path");
+  const long long rows = (long long)R.slabs * plan.cn;
   CUtensorMap tmB;
-  if (int rc = make_weight_map(&tmB, b, rows, plan.ck, n_tile)) return rc;
+  if (int rc = make_weight_map(&tmB, R.b, rows, plan.ck, n_tile)) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
@@ -545,10 +555,11 @@ inline int run_gather_tc(const mra_conv_desc& d, int which, const void* a, const
     P.osh = (long long)plan.odims[2] * P.osw;
     P.osd = (long long)plan.odims[1] * P.osh;
     P.osn = (long long)plan.odims[0] * P.osd;
-    P.out = out; P.out_bf16 = 1;
-    P.bias = bias; P.act = which == 0 ? d.act : MRA_ACT_NONE; P.slope = d.slope;
-    P.stats = stats; P.err = err;
+    P.out = R.out; P.out_bf16 = R.out_bf16;
+    P.bias = R.bias; P.act = R.act; P.slope = R.slope;
+    P.stats = R.stats; P.err = err;
     for (int i = 0; i < P.ntaps; ++i) {
+      MRA_REQUIRE(L.taps[i].dd >= -128 && L.taps[i].dd < 128 && L.taps[i].widx < R.slabs, "tap out of range");
       P.tdd[i] = (int8_t)L.taps[i].dd; P.tdh[i] = (int8_t)L.taps[i].dh; P.tdw[i] = (int8_t)L.taps[i].dw;
       P.twi[i] = (int16_t)L.taps[i].widx;
     }
@@ -559,7 +570,7 @@ inline int run_gather_tc(const mra_conv_desc& d, int which, const void* a, const
     P.tmem_cols = pow2_cols(n_tile);
     const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
     CUtensorMap tmA;
-    if (int rc = make_act_map(&tmA, a, plan.n, plan.adims[0], plan.adims[1], plan.adims[2], plan.ck, P.bw, P.bh, P.bd,
+    if (int rc = make_act_map(&tmA, R.a, plan.n, plan.adims[0], plan.adims[1], plan.adims[2], plan.ck, P.bw, P.bh, P.bd,
                               P.astep))
       return rc;
     dim3 grid((unsigned)((long long)plan.n * P.tilesD * P.tilesH * P.tilesW), (unsigned)(plan.cn / n_tile));
@@ -569,10 +580,18 @@ inline int run_gather_tc(const mra_conv_desc& d, int which, const void* a, const
   return 0;
 }
 
-inline int run_wgrad_tc(const mra_conv_desc& d, const void* x, const void* dy, float* dw, cudaStream_t st) {
-  WgradPlan plan;
-  MRA_REQUIRE(build_wgrad_plan(d, plan), "unsupported conv geometry");
+inline int run_gather_tc(const mra_conv_desc& d, int which, const void* a, const void* b, const float* bias, void* out,
+                         double* stats, cudaStream_t st) {
+  GatherPlan plan;
+  MRA_REQUIRE(build_gather_plan(d, which, plan), "unsupported conv geometry");
+  GatherRun R{a, b, d.k * d.k * d.k, bias, out, 1, which == 0 ? d.act : MRA_ACT_NONE, d.slope, stats};
+  return run_gather_tc(plan, R, st);
+}
+
+inline int run_wgrad_tc(const WgradPlan& plan, const void* x, const void* dy, float* dw, cudaStream_t st) {
   int* err = tc_err_flag();
+  MRA_REQUIRE(pick_n_tile(plan.cn) > 0 && plan.cm % 64 == 0 && (int)plan.taps.size() <= kMaxTaps,
+              "shape not eligible for the tensor-core wgrad path");
   static bool attr_set = false;
   if (!attr_set) {
     MRA_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
@@ -615,6 +634,11 @@ inline int run_wgrad_tc(const mra_conv_desc& d, const void* x, const void* dy, f
   wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(tmM, tmN, P);
   MRA_LAUNCH_CHECK();
   return 0;
+}
+inline int run_wgrad_tc(const mra_conv_desc& d, const void* x, const void* dy, float* dw, cudaStream_t st) {
+  WgradPlan plan;
+  MRA_REQUIRE(build_wgrad_plan(d, plan), "unsupported conv geometry");
+  return run_wgrad_tc(plan, x, dy, dw, st);
 }
 
 }  // namespace tc

@@ -5,6 +5,7 @@
 #include "conv_naive.cuh"
 #include "conv_plan.h"
 #include "conv_tc.cuh"
+#include "conv_special.cuh"
 #include "misc.cuh"
 #include "norm.cuh"
 
@@ -61,17 +62,25 @@ int mra_version(void) { return 100; }
 long long mra_debug_launch_count(void) { return g_launch_count.load(); }
 const char* mra_last_error(void) { return g_last_error.c_str(); }
 
+size_t mra_conv3d_workspace_size(const mra_conv_desc* d, int which) {
+  return d ? special::workspace_bytes(*d, which) : 0;
+}
+
 int mra_conv3d_uses_tensor_cores(const mra_conv_desc* d, int which) {
   if (!d) return 0;
+  if (special::stem_eligible(*d) || special::head_eligible(*d) || special::im2col_eligible(*d)) return 1;
   if (which == 2) return tc::wgrad_eligible(*d) ? 1 : 0;
   return tc::gather_eligible(*d, which) ? 1 : 0;
 }
 
 int mra_conv3d_fprop(const mra_conv_desc* d, const void* x, const void* w, const float* bias, void* y, double* stats,
-                     mra_stream_t stream) {
+                     void* workspace, size_t workspace_bytes, mra_stream_t stream) {
   if (int rc = check_conv(d)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (stats) MRA_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * d->n * d->cout, st));
+  if (special::im2col_eligible(*d)) return special::im2col_fprop(*d, x, w, bias, y, stats, workspace, workspace_bytes, st);
+  if (special::stem_eligible(*d)) return special::stem_fprop(*d, x, w, bias, y, stats, workspace, workspace_bytes, st);
+  if (special::head_eligible(*d) && !stats) return special::head_fprop(*d, x, w, bias, y, workspace, workspace_bytes, st);
   if (tc::gather_eligible(*d, 0)) return tc::run_gather_tc(*d, 0, x, w, bias, y, stats, st);
   NaiveGatherP P = naive_params(*d, 0, x, w, bias, y);
   DISPATCH_DTYPE(d->dtype, { if (int rc = launch_naive_gather<T>(P, st)) return rc; });
@@ -85,9 +94,13 @@ int mra_conv3d_fprop(const mra_conv_desc* d, const void* x, const void* w, const
   return 0;
 }
 
-int mra_conv3d_dgrad(const mra_conv_desc* d, const void* dy, const void* wT, void* dx, mra_stream_t stream) {
+int mra_conv3d_dgrad(const mra_conv_desc* d, const void* dy, const void* wT, void* dx, void* workspace,
+                     size_t workspace_bytes, mra_stream_t stream) {
   if (int rc = check_conv(d)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (special::im2col_eligible(*d)) return special::im2col_dgrad(*d, dy, wT, dx, workspace, workspace_bytes, st);
+  if (special::stem_eligible(*d)) return special::stem_dgrad(*d, dy, wT, dx, workspace, workspace_bytes, st);
+  if (special::head_eligible(*d)) return special::head_dgrad(*d, dy, wT, dx, workspace, workspace_bytes, st);
   if (tc::gather_eligible(*d, 1)) return tc::run_gather_tc(*d, 1, dy, wT, nullptr, dx, nullptr, st);
   NaiveGatherP P = naive_params(*d, 1, dy, wT, nullptr, dx);
   DISPATCH_DTYPE(d->dtype, { if (int rc = launch_naive_gather<T>(P, st)) return rc; });
@@ -95,7 +108,7 @@ int mra_conv3d_dgrad(const mra_conv_desc* d, const void* dy, const void* wT, voi
 }
 
 int mra_conv3d_wgrad(const mra_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias,
-                     mra_stream_t stream) {
+                     void* workspace, size_t workspace_bytes, mra_stream_t stream) {
   if (int rc = check_conv(d)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t wn = (size_t)d->k * d->k * d->k * d->cout * d->cin;
@@ -104,7 +117,13 @@ int mra_conv3d_wgrad(const mra_conv_desc* d, const void* x, const void* dy, floa
     if (dbias) MRA_CHECK_CUDA(cudaMemsetAsync(dbias, 0, (size_t)d->cout * sizeof(float), st));
   }
   if (dw) {
-    if (tc::wgrad_eligible(*d)) {
+    if (special::im2col_eligible(*d)) {
+      if (int rc = special::im2col_wgrad(*d, x, dy, dw, workspace, workspace_bytes, st)) return rc;
+    } else if (special::stem_eligible(*d)) {
+      if (int rc = special::stem_wgrad(*d, x, dy, dw, workspace, workspace_bytes, st)) return rc;
+    } else if (special::head_eligible(*d)) {
+      if (int rc = special::head_wgrad(*d, x, dy, dw, workspace, workspace_bytes, st)) return rc;
+    } else if (tc::wgrad_eligible(*d)) {
       if (int rc = tc::run_wgrad_tc(*d, x, dy, dw, st)) return rc;
     } else {
       NaiveWgradP P;

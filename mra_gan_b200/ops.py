@@ -86,6 +86,12 @@ class CudaImpl:
         d.flags = flags | (_lib.CONV_FORCE_NAIVE if self.force_naive else 0)
         return d
 
+    def _workspace(self, d, which, device):
+        nbytes = int(self.L.mra_conv3d_workspace_size(C.byref(d), which))
+        if nbytes == 0:
+            return None, 0
+        return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
+
     # -- convolution family -----------------------------------------------------------------
     def conv_fprop(self, x, w, bias, g, act=ACT_NONE, slope=0.2, want_stats=False):
         self._need(x, w, bias)
@@ -95,8 +101,9 @@ class CudaImpl:
         y = torch.empty((n,) + out_dims + (g.cout,), dtype=x.dtype, device=x.device)
         stats = torch.empty((n, g.cout, 2), dtype=torch.float64, device=x.device) if want_stats else None
         d = self._conv_desc(g, n, in_dims, out_dims, _dt(x), act, slope)
+        ws, wsb = self._workspace(d, 0, x.device)
         _lib.check(self.L.mra_conv3d_fprop(C.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(y), _ptr(stats),
-                                           self._stream()), "mra_conv3d_fprop")
+                                           _ptr(ws), wsb, self._stream()), "mra_conv3d_fprop")
         return y, stats
 
     def conv_dgrad(self, dy, wT, g, in_dims):
@@ -105,7 +112,8 @@ class CudaImpl:
         assert dy.shape[4] == g.cout and wT.shape == (g.taps, g.cin, g.cout) and wT.dtype == dy.dtype
         dx = torch.empty((n,) + tuple(in_dims) + (g.cin,), dtype=dy.dtype, device=dy.device)
         d = self._conv_desc(g, n, tuple(in_dims), out_dims, _dt(dy))
-        _lib.check(self.L.mra_conv3d_dgrad(C.byref(d), _ptr(dy), _ptr(wT), _ptr(dx), self._stream()),
+        ws, wsb = self._workspace(d, 1, dy.device)
+        _lib.check(self.L.mra_conv3d_dgrad(C.byref(d), _ptr(dy), _ptr(wT), _ptr(dx), _ptr(ws), wsb, self._stream()),
                    "mra_conv3d_dgrad")
         return dx
 
@@ -115,8 +123,9 @@ class CudaImpl:
         dw = torch.empty((g.taps, g.cout, g.cin), dtype=torch.float32, device=x.device)
         db = torch.empty((g.cout,), dtype=torch.float32, device=x.device) if want_bias else None
         d = self._conv_desc(g, n, in_dims, out_dims, _dt(x))
-        _lib.check(self.L.mra_conv3d_wgrad(C.byref(d), _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), self._stream()),
-                   "mra_conv3d_wgrad")
+        ws, wsb = self._workspace(d, 2, x.device)
+        _lib.check(self.L.mra_conv3d_wgrad(C.byref(d), _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), _ptr(ws), wsb,
+                                           self._stream()), "mra_conv3d_wgrad")
         return dw, db
 
     def conv_uses_tensor_cores(self, g, n, in_dims, dtype, which):

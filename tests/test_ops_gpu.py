@@ -30,6 +30,11 @@ TC_CONVS = [
     (ConvGeom(256, 128, 3, 2, 1, True, 1), (6, 6, 6), 2),  # G.u1
     (ConvGeom(128, 64, 4, 2, 1, True, 0), (5, 5, 5), 1),   # UNet up
     (ConvGeom(64, 64, 3, 1, 1), (9, 7, 5), 1),             # zero-padded, odd dims
+    (ConvGeom(1, 64, 7, 1, 0), (14, 15, 17), 2),           # G.c1 stem: channel-expanded lowering
+    (ConvGeom(64, 1, 7, 1, 0), (14, 15, 17), 2),           # G.c4 head: channel-expanded lowering
+    (ConvGeom(128, 1, 4, 1, 0), (7, 8, 9), 1),             # head-like, k4
+    (ConvGeom(1, 64, 4, 2, 1), (12, 12, 12), 2),           # D.1: im2col lowering
+    (ConvGeom(512, 1, 4, 1, 1), (7, 7, 7), 2),             # D.5: zero-padded head lowering
 ]
 
 

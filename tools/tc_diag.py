@@ -20,6 +20,8 @@ CASES = [
     (ConvGeom(128, 512, 4, 1, 1), (10, 10, 10), 1),
     (ConvGeom(256, 128, 3, 2, 1, True, 1), (6, 6, 6), 2),
     (ConvGeom(128, 64, 4, 2, 1, True, 0), (5, 5, 5), 1),
+    (ConvGeom(1, 64, 7, 1, 0), (14, 15, 17), 2),
+    (ConvGeom(64, 1, 7, 1, 0), (14, 15, 17), 2),
 ]
 
 
