@@ -33,7 +33,8 @@ def window_grid(shape, patch, stride_inplane, stride_layer):
 
 
 @torch.no_grad()
-def sliding_window_inference(model, volume, patch, stride_inplane, stride_layer, rank=0, world=1, dtype=None):
+def sliding_window_inference(model, volume, patch, stride_inplane, stride_layer, rank=0, world=1, dtype=None,
+                             _local_only=False):
     """``model``: a TestModel (set_input / test / get_current_visuals, like test.py:158-161).
     ``volume``: float32 (X, Y, Z) tensor on the 0..255 scale, each dim >= patch.
     Returns the (X, Y, Z) float32 result on rank 0 (other ranks get their partial sum's buffer)."""
@@ -53,6 +54,8 @@ def sliding_window_inference(model, volume, patch, stride_inplane, stride_layer,
         model.test()
         pred = model.get_current_visuals()["fake_B"]
         I.window_accumulate(pred.reshape(1, *patch, 1).contiguous(), label, weight, i0, j0, k0)
+    if _local_only:                 # test hook: this rank's partial sums, before the cross-rank reduce
+        return label, weight
     if world > 1:
         dist.reduce(label, dst=0, op=dist.ReduceOp.SUM)
         dist.reduce(weight, dst=0, op=dist.ReduceOp.SUM)
