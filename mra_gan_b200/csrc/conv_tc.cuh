@@ -155,7 +155,8 @@ struct GatherP {
   int bw, bh, bd;
   int Dl, Hl, Wl;
   int astep;
-  int Cn, n_tile, kchunks, ntaps;
+  int Cn, n_tile, n_tiles, kchunks, ntaps;
+  int total_tiles;                  // N * tilesD * tilesH * tilesW * n_tiles
   int ostep, od0, oh0, ow0;
   long long osn, osd, osh, osw;     // output strides in elements
   void* out;
@@ -166,11 +167,31 @@ struct GatherP {
   double* stats;                    // [N][Cn][2] or null
   int* err;
   int stages;
-  uint32_t tmem_cols;
+  uint32_t tmem_cols;               // 2 accumulator buffers of n_tile columns (power of two >= 32)
   int8_t tdd[kMaxTaps], tdh[kMaxTaps], tdw[kMaxTaps];
   int16_t twi[kMaxTaps];
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct TileCoord { int n, lw0, lh0, ld0, n0; };
+__device__ __forceinline__ TileCoord decode_tile(const GatherP& P, int tile) {
+  TileCoord t;
+  const int nt = tile % P.n_tiles; tile /= P.n_tiles;
+  const int tw = tile % P.tilesW; tile /= P.tilesW;
+  const int th = tile % P.tilesH; tile /= P.tilesH;
+  const int td = tile % P.tilesD;
+  t.n = tile / P.tilesD;
+  t.lw0 = tw * P.bw; t.lh0 = th * P.bh; t.ld0 = td * P.bd; t.n0 = nt * P.n_tile;
+  return t;
+}
+
+// Persistent: gridDim.x CTAs (one per SM) walk the tile list with stride gridDim.x.  The accumulator is
+// double-buffered in TMEM so the epilogue of tile j overlaps the MMAs of tile j+1; InstanceNorm
+// statistics are accumulated per CTA in registers and flushed with one fp64 atomic per channel when the
+// sample index changes (instead of per tile).
 __global__ void __launch_bounds__(kThreads, 1)
 gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ GatherP P) {
@@ -180,26 +201,18 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t stage_bytes = kABytes + b_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + P.stages;
-  uint64_t* accum_bar = empty_bar + P.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* acc_full = empty_bar + P.stages;      // [2]
+  uint64_t* acc_empty = acc_full + 2;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // tile decode
-  int tile = blockIdx.x;
-  const int tw = tile % P.tilesW; tile /= P.tilesW;
-  const int th = tile % P.tilesH; tile /= P.tilesH;
-  const int td = tile % P.tilesD;
-  const int n = tile / P.tilesD;
-  const int lw0 = tw * P.bw, lh0 = th * P.bh, ld0 = td * P.bd;
-  const int n0 = blockIdx.y * P.n_tile;
   const int iters = P.ntaps * P.kchunks;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(accum_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, P.tmem_cols);
@@ -210,89 +223,134 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % P.stages;
-        const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
-        if (!mbar_wait(&empty_bar[s], ph ^ 1u, P.err, 1)) break;
-        const int tap = it / P.kchunks, kc = it - tap * P.kchunks;
-        uint8_t* sa = smem + (size_t)s * stage_bytes;
-        mbar_expect_tx(&full_bar[s], stage_bytes);
-        tma_load_5d(sa, &tmA, &full_bar[s], kc * 64, lw0 * P.astep + P.tdw[tap], lh0 * P.astep + P.tdh[tap],
-                    ld0 * P.astep + P.tdd[tap], n);
-        tma_load_2d(sa + kABytes, &tmB, &full_bar[s], kc * 64, (int)P.twi[tap] * P.Cn + n0);
+      uint32_t git = 0;                                    // global k-iteration counter (stage ring position)
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < P.total_tiles && ok; tile += gridDim.x) {
+        const TileCoord t = decode_tile(P, tile);
+        for (int it = 0; it < iters; ++it, ++git) {
+          const int s = git % P.stages;
+          const uint32_t ph = (git / P.stages) & 1u;
+          if (!mbar_wait(&empty_bar[s], ph ^ 1u, P.err, 1)) { ok = false; break; }
+          const int tap = it / P.kchunks, kc = it - tap * P.kchunks;
+          uint8_t* sa = smem + (size_t)s * stage_bytes;
+          mbar_expect_tx(&full_bar[s], stage_bytes);
+          tma_load_5d(sa, &tmA, &full_bar[s], kc * 64, t.lw0 * P.astep + P.tdw[tap], t.lh0 * P.astep + P.tdh[tap],
+                      t.ld0 * P.astep + P.tdd[tap], t.n);
+          tma_load_2d(sa + kABytes, &tmB, &full_bar[s], kc * 64, (int)P.twi[tap] * P.Cn + t.n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc(P.n_tile, 0, 0);
+      uint32_t git = 0;
       bool ok = true;
-      for (int it = 0; it < iters && ok; ++it) {
-        const int s = it % P.stages;
-        const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
-        ok = mbar_wait(&full_bar[s], ph, P.err, 2);
-        if (!ok) break;
+      int j = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles && ok; tile += gridDim.x, ++j) {
+        const int buf = j & 1;
+        const uint32_t aph = ((uint32_t)j >> 1) & 1u;
+        if (!mbar_wait(&acc_empty[buf], aph ^ 1u, P.err, 4)) { ok = false; break; }   // epilogue drained this buffer
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t sb = sa + kABytes;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * P.n_tile);
+        for (int it = 0; it < iters; ++it, ++git) {
+          const int s = git % P.stages;
+          const uint32_t ph = (git / P.stages) & 1u;
+          if (!mbar_wait(&full_bar[s], ph, P.err, 2)) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t sb = sa + kABytes;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16(tmem_base, desc_kmajor_sw128(sa + k * 32), desc_kmajor_sw128(sb + k * 32), idesc,
-                   (uint32_t)((it | k) != 0));
-        umma_commit(&empty_bar[s]);
+          for (int k = 0; k < 4; ++k)
+            umma_f16(d_tmem, desc_kmajor_sw128(sa + k * 32), desc_kmajor_sw128(sb + k * 32), idesc,
+                     (uint32_t)((it | k) != 0));
+          umma_commit(&empty_bar[s]);
+        }
+        if (ok) umma_commit(&acc_full[buf]);
       }
-      umma_commit(accum_bar);
     }
   } else {
     // epilogue warps 2..5 -> TMEM lane quadrant (warp % 4)
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int lw = lw0 + row % P.bw, lh = lh0 + (row / P.bw) % P.bh, ld = ld0 + row / (P.bw * P.bh);
-    const bool valid = lw < P.Wl && lh < P.Hl && ld < P.Dl;
-    const long long obase = (long long)n * P.osn + (long long)(ld * P.ostep + P.od0) * P.osd +
-                            (long long)(lh * P.ostep + P.oh0) * P.osh + (long long)(lw * P.ostep + P.ow0) * P.osw + n0;
-    const bool ok = mbar_wait(accum_bar, 0, P.err, 3);
-    tc_fence_after();
-    if (ok) {
-      for (int c0 = 0; c0 < P.n_tile; c0 += 32) {
+    const int rw = row % P.bw, rh = (row / P.bw) % P.bh, rd = row / (P.bw * P.bh);
+    const int nchunks = P.n_tile / 32;
+    double st_s[8], st_q[8];                 // per-lane running sums for column (chunk*32 + lane)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { st_s[c] = 0.0; st_q[c] = 0.0; }
+    int st_n = -1, st_n0 = 0;
+    auto flush_stats = [&]() {
+      if (st_n >= 0) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c < nchunks) {
+            double* st = P.stats + ((long long)st_n * P.Cn + st_n0 + c * 32 + lane) * 2;
+            atomicAdd(st, st_s[c]);
+            atomicAdd(st + 1, st_q[c]);
+            st_s[c] = 0.0; st_q[c] = 0.0;
+          }
+      }
+    };
+    int j = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; tile < P.total_tiles && ok; tile += gridDim.x, ++j) {
+      const TileCoord t = decode_tile(P, tile);
+      const int buf = j & 1;
+      const uint32_t aph = ((uint32_t)j >> 1) & 1u;
+      const int lw = t.lw0 + rw, lh = t.lh0 + rh, ld = t.ld0 + rd;
+      const bool valid = lw < P.Wl && lh < P.Hl && ld < P.Dl;
+      const long long obase = (long long)t.n * P.osn + (long long)(ld * P.ostep + P.od0) * P.osd +
+                              (long long)(lh * P.ostep + P.oh0) * P.osh + (long long)(lw * P.ostep + P.ow0) * P.osw + t.n0;
+      if (P.stats && (t.n != st_n || t.n0 != st_n0)) { flush_stats(); st_n = t.n; st_n0 = t.n0; }
+      ok = mbar_wait(&acc_full[buf], aph, P.err, 3);
+      if (!ok) break;
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * P.n_tile);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (c >= nchunks) break;
+        const int c0 = c * 32;
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld32(t_addr + (uint32_t)c0, r);
         tmem_wait_ld();
+        if (c == nchunks - 1) {                 // accumulator fully read: hand the buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
         if (P.bias) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += __ldg(P.bias + n0 + c0 + j);
+          for (int i = 0; i < 32; ++i) v[i] += __ldg(P.bias + t.n0 + c0 + i);
         }
         if (P.stats) {
           float s1[32], s2[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { s1[j] = valid ? v[j] : 0.f; s2[j] = s1[j] * s1[j]; }
-          const float a = warp_colsum32(s1, lane);
-          const float b = warp_colsum32(s2, lane);
-          double* st = P.stats + ((long long)n * P.Cn + n0 + c0 + lane) * 2;
-          atomicAdd(st, (double)a);
-          atomicAdd(st + 1, (double)b);
+          for (int i = 0; i < 32; ++i) { s1[i] = valid ? v[i] : 0.f; s2[i] = s1[i] * s1[i]; }
+          st_s[c] += (double)warp_colsum32(s1, lane);
+          st_q[c] += (double)warp_colsum32(s2, lane);
         }
         if (P.act != MRA_ACT_NONE) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], P.act, P.slope);
+          for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], P.act, P.slope);
         }
         if (valid) {
           if (P.out_bf16) {
             uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(P.out) + obase + c0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              o[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+            for (int i = 0; i < 4; ++i)
+              o[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
           } else {
             float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + obase + c0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           }
         }
       }
     }
+    if (P.stats) flush_stats();
   }
   tc_fence_before();
   __syncthreads();
@@ -549,7 +607,10 @@ inline int run_gather_tc(const GatherPlan& plan, const GatherRun& R, cudaStream_
     P.Dl = L.dims[0]; P.Hl = L.dims[1]; P.Wl = L.dims[2];
     P.tilesD = (P.Dl + P.bd - 1) / P.bd; P.tilesH = (P.Hl + P.bh - 1) / P.bh; P.tilesW = (P.Wl + P.bw - 1) / P.bw;
     P.astep = L.astep;
-    P.Cn = plan.cn; P.n_tile = n_tile; P.kchunks = plan.ck / 64; P.ntaps = (int)L.taps.size();
+    P.Cn = plan.cn; P.n_tile = n_tile; P.n_tiles = plan.cn / n_tile; P.kchunks = plan.ck / 64; P.ntaps = (int)L.taps.size();
+    const long long total_tiles = (long long)plan.n * P.tilesD * P.tilesH * P.tilesW * P.n_tiles;
+    MRA_REQUIRE(total_tiles < (1ll << 31), "too many tiles");
+    P.total_tiles = (int)total_tiles;
     P.ostep = L.ostep; P.od0 = L.o0[0]; P.oh0 = L.o0[1]; P.ow0 = L.o0[2];
     P.osw = plan.cn;
     P.osh = (long long)plan.odims[2] * P.osw;
@@ -567,14 +628,14 @@ inline int run_gather_tc(const GatherPlan& plan, const GatherRun& R, cudaStream_
     int stages = (int)((kSmemLimit - 2048) / stage_bytes);
     if (stages > 6) stages = 6;
     P.stages = stages;
-    P.tmem_cols = pow2_cols(n_tile);
+    P.tmem_cols = pow2_cols(2 * n_tile);
     const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
     CUtensorMap tmA;
     if (int rc = make_act_map(&tmA, R.a, plan.n, plan.adims[0], plan.adims[1], plan.adims[2], plan.ck, P.bw, P.bh, P.bd,
                               P.astep))
       return rc;
-    dim3 grid((unsigned)((long long)plan.n * P.tilesD * P.tilesH * P.tilesW), (unsigned)(plan.cn / n_tile));
-    gather_tc_kernel<<<grid, kThreads, smem, st>>>(tmA, tmB, P);
+    const int ctas = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
+    gather_tc_kernel<<<ctas, kThreads, smem, st>>>(tmA, tmB, P);
     MRA_LAUNCH_CHECK();
   }
   return 0;
