@@ -47,6 +47,18 @@ struct GatherPlan {
   std::vector<GatherLaunch> launches;
 };
 
+// One wgrad launch: a list of filter taps processed `gpi` at a time by one CTA (the accumulators of
+// all taps of an item live side by side in TMEM, so the dense operand is loaded once per item).
+// With share == 2 consecutive taps form pairs that read the SAME shared-memory box of the shifted
+// operand (box extended by `ext`), each through its own row shift -- the halo is loaded once.
+struct WgradLaunch {
+  int share;                 // 1 or 2
+  int gpi;                   // taps per item (multiple of share)
+  int ext[3];                // box extension (d, h, w) of the shifted operand's box (zeros when share == 1)
+  std::vector<int> taps;     // indices into WgradPlan::taps, item by item
+  std::vector<Tap> origin;   // per entry: offset of its box origin (shared by both taps of a pair); widx unused
+};
+
 struct WgradPlan {
   int n, cm, cn;      // dW is [taps][cm][cn] with cm = cout, cn = cin
   int qdims[3];       // dense position space
@@ -55,6 +67,8 @@ struct WgradPlan {
   int m_is_shifted;   // 1: dy (M side) is the shifted operand (ConvTranspose3d)
   std::vector<Tap> taps;
   int box[3];         // K-block box (d, h, w), product 64
+  int ncc;            // 64-channel chunks of the shifted operand per tap (accumulator width = 64 * ncc)
+  std::vector<WgradLaunch> launches;
 };
 
 // Pick power-of-two box extents (d,h,w) with product `total` minimising the padded volume of the
@@ -159,6 +173,18 @@ inline bool build_gather_plan(const mra_conv_desc& d, int which, GatherPlan& P) 
   return build_gather_plan(geom_from_desc(d), which, P);
 }
 
+inline void wgrad_add_launch(WgradPlan& P, const std::vector<int>& idx, int share, int gpi, int ed, int eh, int ew) {
+  if (idx.empty()) return;
+  WgradLaunch L;
+  L.share = share; L.gpi = gpi; L.ext[0] = ed; L.ext[1] = eh; L.ext[2] = ew;
+  L.taps = idx;
+  for (size_t i = 0; i < idx.size(); ++i) {
+    const Tap& a = P.taps[idx[i - (share == 2 ? i % 2 : 0)]];      // first tap of the pair holds the minimum offsets
+    L.origin.push_back(Tap{a.dd, a.dh, a.dw, 0});
+  }
+  P.launches.push_back(L);
+}
+
 inline bool build_wgrad_plan(const GeomEx& d, WgradPlan& P) {
   const int s = d.stride;
   if (s != 1 && s != 2) return false;
@@ -174,6 +200,38 @@ inline bool build_wgrad_plan(const GeomEx& d, WgradPlan& P) {
   for (int kd = 0; kd < d.k[0]; ++kd) for (int kh = 0; kh < d.k[1]; ++kh) for (int kw = 0; kw < d.k[2]; ++kw)
     P.taps.push_back(Tap{kd - d.pad[0], kh - d.pad[1], kw - d.pad[2], (kd * d.k[1] + kh) * d.k[2] + kw});
   choose_box(P.qdims, 64, 256 / s, P.box);
+  // ---- launch structure (tensor-core kernel only; needs 64-channel multiples) ----
+  P.launches.clear();
+  const int cs = d.transposed ? d.cout : d.cin;          // channels of the shifted operand
+  P.ncc = cs % 256 == 0 ? 4 : (cs % 128 == 0 ? 2 : 1);
+  const int cap = 8 / P.ncc;                             // taps whose accumulators fit TMEM (512 columns)
+  const int K0 = d.k[0], K1 = d.k[1], K2 = d.k[2];
+  auto ti = [&](int a, int b, int c) { return (a * K1 + b) * K2 + c; };
+  std::vector<int> wpairs, hpairs, rest;
+  const bool can_share = s == 1 && P.box[2] % 16 == 0 && cap >= 2;
+  if (can_share) {
+    std::vector<int> left;                               // taps left over after pairing along w
+    for (int kd = 0; kd < K0; ++kd) for (int kh = 0; kh < K1; ++kh) {
+      int kw = 0;
+      for (; kw + 1 < K2; kw += 2) { wpairs.push_back(ti(kd, kh, kw)); wpairs.push_back(ti(kd, kh, kw + 1)); }
+      if (kw < K2) left.push_back(ti(kd, kh, kw));
+    }
+    // the leftovers all have kw = K2-1: pair them along h
+    for (int kd = 0; kd < K0 && (K2 & 1); ++kd) {
+      int kh = 0;
+      for (; kh + 1 < K1; kh += 2) { hpairs.push_back(ti(kd, kh, K2 - 1)); hpairs.push_back(ti(kd, kh + 1, K2 - 1)); }
+      if (kh < K1) rest.push_back(ti(kd, kh, K2 - 1));
+    }
+  } else {
+    for (int i = 0; i < (int)P.taps.size(); ++i) rest.push_back(i);
+  }
+  const int gshare = cap - (cap & 1);
+  wgrad_add_launch(P, wpairs, 2, gshare, 0, 0, 1);
+  wgrad_add_launch(P, hpairs, 2, gshare, 0, 1, 0);
+  // unshared taps: each tap needs its own ncc boxes per stage; keep the stage small enough for >= 3 stages
+  int gsolo = cap;
+  while (gsolo > 1 && gsolo * P.ncc > 5) --gsolo;
+  wgrad_add_launch(P, rest, 1, gsolo, 0, 0, 0);
   return true;
 }
 inline bool build_wgrad_plan(const mra_conv_desc& d, WgradPlan& P) { return build_wgrad_plan(geom_from_desc(d), P); }
@@ -182,7 +240,7 @@ inline bool build_wgrad_plan(const mra_conv_desc& d, WgradPlan& P) { return buil
 //  gather: [0, n, ck, cn, adims[3], odims[3], nlaunch, then per launch:
 //           o0[3], ostep, dims[3], astep, box[3], ntaps, ntaps x (dd, dh, dw, widx)]
 //  wgrad : [1, n, cm, cn, qdims[3], mdims[3], ndims[3], sstep, m_is_shifted, box[3], ntaps,
-//           ntaps x (dd, dh, dw, widx)]
+//           ntaps x (dd, dh, dw, widx), ncc, nlaunch, per launch: share, gpi, ext[3], n, n x (tap, odd, odh, odw)]
 inline int describe(const GatherPlan& P, int32_t* out, int cap) {
   std::vector<int32_t> v = {0, P.n, P.ck, P.cn};
   for (int i = 0; i < 3; ++i) v.push_back(P.adims[i]);
@@ -210,6 +268,16 @@ inline int describe(const WgradPlan& P, int32_t* out, int cap) {
   for (int i = 0; i < 3; ++i) v.push_back(P.box[i]);
   v.push_back((int)P.taps.size());
   for (const auto& t : P.taps) { v.push_back(t.dd); v.push_back(t.dh); v.push_back(t.dw); v.push_back(t.widx); }
+  // launch structure: ncc, nlaunch, then per launch: share, gpi, ext[3], n, n x (tap index, origin dd, dh, dw)
+  v.push_back(P.ncc); v.push_back((int)P.launches.size());
+  for (const auto& L : P.launches) {
+    v.push_back(L.share); v.push_back(L.gpi);
+    for (int i = 0; i < 3; ++i) v.push_back(L.ext[i]);
+    v.push_back((int)L.taps.size());
+    for (size_t i = 0; i < L.taps.size(); ++i) {
+      v.push_back(L.taps[i]); v.push_back(L.origin[i].dd); v.push_back(L.origin[i].dh); v.push_back(L.origin[i].dw);
+    }
+  }
   if ((int)v.size() > cap) return -2;
   for (size_t i = 0; i < v.size(); ++i) out[i] = v[i];
   return (int)v.size();

@@ -358,21 +358,38 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ------------------------------------------------------------------ wgrad kernel
+// D[tap][m][n] = sum_{positions q} Dense[q][m] * Shifted[q*sstep + tap][n]
+//   Dense   = the operand read at the K-block positions themselves (dy for Conv3d, x for ConvTranspose3d),
+//   Shifted = the other one (x for Conv3d, dy for ConvTranspose3d).
+// One CTA = (item, 128-row m tile, n tile of 64*ncc channels) x one split of the position space.  An item
+// is up to 8/ncc filter taps whose accumulators sit side by side in TMEM (<= 512 columns), so the dense
+// tile of a K-block (64 positions) is loaded once for all of them.  With share == 2 two taps that are
+// neighbours along w (or h) read ONE shared-memory box of the shifted operand, extended by one column
+// (row): the UMMA descriptor of the second tap simply starts `rshift` rows later (the SWIZZLE_128B pattern
+// is a function of the absolute shared-memory address, so row-shifted starts are legal; verified by
+// tools/halo_probe.cu).  Both operands are position-major = MN-major for the MMA.
 struct WgradP {
   int tilesW, tilesH, tilesD;       // K-block boxes per dim of the dense position space
-  int bw, bh, bd;                   // box (product 64)
+  int bw, bh, bd;                   // K-block box (product 64)
   int N;
   int sstep;
-  int m_is_shifted;
-  int Cm, Cn, n_tile;
-  int m_tiles, n_tiles, ntaps;
+  int Km, Kn;                       // channels of the dense / shifted operand
+  int m_chunks;                     // 64-channel chunks of the dense operand per m tile (1 or 2)
+  int ncc;                          // 64-channel chunks of the shifted operand per tap
+  int gpi, share;                   // taps per item, taps per box set
+  int pitch_w, pitch_h;             // rows per h line / per d plane of a shifted-operand box
+  int box_bytes;                    // shared-memory slot of one 64-channel box of the shifted operand (multiple of 1024)
+  int box_tx;                       // bytes one such box actually delivers
+  int n_items, m_tiles, n_tiles, ntaps;
   int splits;
-  float* dw;                        // [taps][Cm][Cn]
+  float* dw;
+  long long tap_stride, m_stride, n_stride;   // element strides of dw[tap][m][n] in memory
   int* err;
   int stages;
   uint32_t tmem_cols;
-  int8_t tdd[kMaxTaps], tdh[kMaxTaps], tdw[kMaxTaps];
-  int16_t twi[kMaxTaps];
+  int8_t odd[kMaxTaps], odh[kMaxTaps], odw[kMaxTaps];   // box origin offset per tap (launch order)
+  int16_t rshift[kMaxTaps];                             // row shift of the tap inside its box
+  int16_t twi[kMaxTaps];                                // weight slab index of the tap
 };
 
 constexpr uint32_t kChunkBytes = 64 * 128;       // 64 positions x 64 bf16
@@ -382,19 +399,24 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
                 const __grid_constant__ WgradP P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int n_chunks = P.n_tile / 64;
-  const uint32_t stage_bytes = (2 + n_chunks) * kChunkBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
-  uint64_t* empty_bar = full_bar + P.stages;
-  uint64_t* accum_bar = empty_bar + P.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   int w = blockIdx.x;
   const int nt = w % P.n_tiles; w /= P.n_tiles;
   const int mt = w % P.m_tiles;
-  const int tap = w / P.m_tiles;
-  const int m0 = mt * 128, n0 = nt * P.n_tile;
+  const int item = w / P.m_tiles;
+  const int m0 = mt * 128, n0 = nt * P.ncc * 64;
+  const int tap0 = item * P.gpi;
+  const int ntap = min(P.gpi, P.ntaps - tap0);              // taps of this item
+  const int nsets = (ntap + P.share - 1) / P.share;         // box sets loaded per K-block
+  const uint32_t m_bytes = 2 * kChunkBytes;                  // the m tile always owns two chunk slots
+  const uint32_t set_bytes = (uint32_t)P.ncc * (uint32_t)P.box_bytes;
+  const uint32_t stage_bytes = m_bytes + (uint32_t)(P.gpi / P.share) * set_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + P.stages;
+  uint64_t* accum_bar = empty_bar + P.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
   const long long boxes_per_sample = (long long)P.tilesW * P.tilesH * P.tilesD;
   const long long total_boxes = boxes_per_sample * P.N;
   const long long per_split = (total_boxes + P.splits - 1) / P.splits;
@@ -410,15 +432,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
     mbar_init(accum_bar, 1);
     fence_barrier_init();
   }
+  if (P.m_chunks == 1) {
+    // the second chunk slot of the m tile is never loaded: keep it finite (its rows are discarded)
+    for (int s = 0; s < P.stages; ++s) {
+      uint4* z = reinterpret_cast<uint4*>(smem + (size_t)s * stage_bytes + kChunkBytes);
+      for (int i = threadIdx.x; i < (int)(kChunkBytes / 16); i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async();
+  }
   if (warp == 1) tmem_alloc(tmem_slot, P.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tx_bytes = (uint32_t)P.m_chunks * kChunkBytes + (uint32_t)(nsets * P.ncc) * (uint32_t)P.box_tx;
 
   if (warp == 0) {
     if (lane == 0) {
-      const int dd = P.tdd[tap], dh = P.tdh[tap], dw_ = P.tdw[tap];
       for (int it = 0; it < iters; ++it) {
         const int s = it % P.stages;
         const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
@@ -429,21 +459,30 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
         const int qw = (r % P.tilesW) * P.bw; r /= P.tilesW;
         const int qh = (r % P.tilesH) * P.bh;
         const int qd = (r / P.tilesH) * P.bd;
-        // dense coords (qw,qh,qd); shifted coords q*sstep + tap offset
-        const int sw_ = qw * P.sstep + dw_, sh_ = qh * P.sstep + dh, sd_ = qd * P.sstep + dd;
-        const int mw = P.m_is_shifted ? sw_ : qw, mh = P.m_is_shifted ? sh_ : qh, md = P.m_is_shifted ? sd_ : qd;
-        const int nw = P.m_is_shifted ? qw : sw_, nh = P.m_is_shifted ? qh : sh_, nd = P.m_is_shifted ? qd : sd_;
         uint8_t* sa = smem + (size_t)s * stage_bytes;
-        mbar_expect_tx(&full_bar[s], stage_bytes);
-        tma_load_5d(sa, &tmM, &full_bar[s], m0, mw, mh, md, n);
-        tma_load_5d(sa + kChunkBytes, &tmM, &full_bar[s], m0 + 64, mw, mh, md, n);
-        for (int j = 0; j < n_chunks; ++j)
-          tma_load_5d(sa + (2 + j) * kChunkBytes, &tmN, &full_bar[s], n0 + 64 * j, nw, nh, nd, n);
+        mbar_expect_tx(&full_bar[s], tx_bytes);
+        for (int c = 0; c < P.m_chunks; ++c)
+          tma_load_5d(sa + c * kChunkBytes, &tmM, &full_bar[s], m0 + 64 * c, qw, qh, qd, n);
+        for (int bs = 0; bs < nsets; ++bs) {
+          const int t = tap0 + bs * P.share;
+          const int cw = qw * P.sstep + P.odw[t], ch = qh * P.sstep + P.odh[t], cd = qd * P.sstep + P.odd[t];
+          uint8_t* sb = sa + m_bytes + (size_t)bs * set_bytes;
+          for (int j = 0; j < P.ncc; ++j)
+            tma_load_5d(sb + (size_t)j * P.box_bytes, &tmN, &full_bar[s], n0 + 64 * j, cw, ch, cd, n);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && iters > 0) {
-      const uint32_t idesc = make_idesc(P.n_tile, 1, 1);
+      const uint32_t idesc = make_idesc(P.ncc * 64, 1, 1);
+      // row of the shifted box that pairs with dense row 16*j (dense rows are (d, h, w) over the K-block box)
+      uint32_t rowmap[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = 16 * j;
+        const int kw_ = k % P.bw, kh_ = (k / P.bw) % P.bh, kd_ = k / (P.bw * P.bh);
+        rowmap[j] = (uint32_t)(kd_ * P.pitch_h + kh_ * P.pitch_w + kw_);
+      }
       bool ok = true;
       for (int it = 0; it < iters && ok; ++it) {
         const int s = it % P.stages;
@@ -452,34 +491,49 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
         if (!ok) break;
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t sb = sa + 2 * kChunkBytes;
+        const uint32_t sb = sa + m_bytes;
+        for (int g = 0; g < ntap; ++g) {
+          const uint32_t bset = sb + (uint32_t)(g / P.share) * set_bytes + (uint32_t)P.rshift[tap0 + g] * 128u;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(g * P.ncc * 64);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)      // 16 positions (rows of 128 B) per MMA
-          umma_f16(tmem_base, desc_mnmajor_sw128(sa + k * 2048, kChunkBytes),
-                   desc_mnmajor_sw128(sb + k * 2048, kChunkBytes), idesc, (uint32_t)((it | k) != 0));
+          for (int k = 0; k < 4; ++k)      // 16 positions (rows of 128 B) per MMA
+            umma_f16(d_tmem, desc_mnmajor_sw128(sa + k * 2048, kChunkBytes),
+                     desc_mnmajor_sw128(bset + rowmap[k] * 128u, (uint32_t)P.box_bytes), idesc, (uint32_t)((it | k) != 0));
+        }
         umma_commit(&empty_bar[s]);
       }
       umma_commit(accum_bar);
     }
   } else if (iters > 0) {
     const int q = warp & 3;
-    const int cm = m0 + q * 32 + lane;
-    const bool valid = cm < P.Cm;
+    const int ml = q * 32 + lane;
+    const int m = m0 + ml;
+    const bool valid = ml < 64 * P.m_chunks && m < P.Km;
     const bool ok = mbar_wait(accum_bar, 0, P.err, 13);
     tc_fence_after();
     if (ok) {
-      float* orow = P.dw + ((long long)P.twi[tap] * P.Cm + cm) * P.Cn + n0;
-      for (int c0 = 0; c0 < P.n_tile; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-        tmem_wait_ld();
-        if (valid) {
+      const int ncols = P.ncc * 64;
+      for (int g = 0; g < ntap; ++g) {
+        float* obase = P.dw + (long long)P.twi[tap0 + g] * P.tap_stride + (long long)m * P.m_stride;
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * ncols + c0), r);
+          tmem_wait_ld();
+          if (!valid) continue;
+          if (P.n_stride == 1) {
+            float* o = obase + n0 + c0;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + c0 + j),
-                         "f"(__uint_as_float(r[j])), "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])),
-                         "f"(__uint_as_float(r[j + 3]))
-                         : "memory");
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(__uint_as_float(r[j])),
+                           "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                           : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              asm volatile("red.global.add.f32 [%0], %1;" ::"l"(obase + (long long)(n0 + c0 + j) * P.n_stride),
+                           "f"(__uint_as_float(r[j]))
+                           : "memory");
+          }
         }
       }
     }
@@ -649,51 +703,84 @@ inline int run_gather_tc(const mra_conv_desc& d, int which, const void* a, const
   return run_gather_tc(plan, R, st);
 }
 
+// shifted-operand box: channels-last bf16 [N][D][H][W][C] -> box (64, (bw+ew)*s, (bh+eh)*s, (bd+ed)*s, 1)
+inline int make_shifted_map(CUtensorMap* tm, const void* base, int N, int D, int H, int W, int C, int xw, int xh, int xd,
+                            int step) {
+  return make_act_map(tm, base, N, D, H, W, C, xw, xh, xd, step);
+}
+
 inline int run_wgrad_tc(const WgradPlan& plan, const void* x, const void* dy, float* dw, cudaStream_t st) {
   int* err = tc_err_flag();
-  MRA_REQUIRE(pick_n_tile(plan.cn) > 0 && plan.cm % 64 == 0 && (int)plan.taps.size() <= kMaxTaps,
+  MRA_REQUIRE(plan.cm % 64 == 0 && plan.cn % 64 == 0 && (int)plan.taps.size() <= kMaxTaps,
               "shape not eligible for the tensor-core wgrad path");
   static bool attr_set = false;
   if (!attr_set) {
     MRA_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
     attr_set = true;
   }
-  WgradP P;
-  memset(&P, 0, sizeof(P));
-  P.bd = plan.box[0]; P.bh = plan.box[1]; P.bw = plan.box[2];
-  P.tilesD = (plan.qdims[0] + P.bd - 1) / P.bd; P.tilesH = (plan.qdims[1] + P.bh - 1) / P.bh;
-  P.tilesW = (plan.qdims[2] + P.bw - 1) / P.bw;
-  P.N = plan.n; P.sstep = plan.sstep; P.m_is_shifted = plan.m_is_shifted;
-  P.Cm = plan.cm; P.Cn = plan.cn;
-  P.n_tile = pick_n_tile(plan.cn);
-  P.m_tiles = (plan.cm + 127) / 128; P.n_tiles = plan.cn / P.n_tile; P.ntaps = (int)plan.taps.size();
-  P.dw = dw; P.err = err;
-  for (int i = 0; i < P.ntaps; ++i) {
-    P.tdd[i] = (int8_t)plan.taps[i].dd; P.tdh[i] = (int8_t)plan.taps[i].dh; P.tdw[i] = (int8_t)plan.taps[i].dw;
-    P.twi[i] = (int16_t)plan.taps[i].widx;
+  // dense operand on the M side of the MMA, shifted operand on the N side
+  const bool sw = plan.m_is_shifted != 0;                  // ConvTranspose3d: dense = x, shifted = dy
+  const void* dense = sw ? x : dy;
+  const void* shifted = sw ? dy : x;
+  const int* ddims = sw ? plan.ndims : plan.mdims;
+  const int* sdims = sw ? plan.mdims : plan.ndims;
+  const int Km = sw ? plan.cn : plan.cm, Kn = sw ? plan.cm : plan.cn;
+  CUtensorMap tmM;
+  if (int rc = make_act_map(&tmM, dense, plan.n, ddims[0], ddims[1], ddims[2], Km, plan.box[2], plan.box[1], plan.box[0], 1))
+    return rc;
+  for (const WgradLaunch& L : plan.launches) {
+    WgradP P;
+    memset(&P, 0, sizeof(P));
+    P.bd = plan.box[0]; P.bh = plan.box[1]; P.bw = plan.box[2];
+    P.tilesD = (plan.qdims[0] + P.bd - 1) / P.bd; P.tilesH = (plan.qdims[1] + P.bh - 1) / P.bh;
+    P.tilesW = (plan.qdims[2] + P.bw - 1) / P.bw;
+    P.N = plan.n; P.sstep = plan.sstep;
+    P.Km = Km; P.Kn = Kn;
+    P.m_chunks = Km >= 128 ? 2 : 1;
+    P.ncc = plan.ncc;
+    P.gpi = L.gpi; P.share = L.share;
+    const int xd = P.bd + L.ext[0], xh = P.bh + L.ext[1], xw = P.bw + L.ext[2];
+    P.pitch_w = xw; P.pitch_h = xh * xw;
+    P.box_tx = xd * xh * xw * 128;
+    P.box_bytes = (P.box_tx + 1023) / 1024 * 1024;
+    P.ntaps = (int)L.taps.size();
+    P.n_items = (P.ntaps + P.gpi - 1) / P.gpi;
+    P.m_tiles = (Km + 127) / 128;
+    P.n_tiles = Kn / (64 * P.ncc);
+    P.dw = dw; P.err = err;
+    // dw memory is [taps][cm][cn] (cm = cout, cn = cin); kernel rows m index the dense operand's channels
+    P.tap_stride = (long long)plan.cm * plan.cn;
+    if (!sw) { P.m_stride = plan.cn; P.n_stride = 1; }
+    else     { P.m_stride = 1; P.n_stride = plan.cn; }
+    for (int i = 0; i < P.ntaps; ++i) {
+      const Tap& t = plan.taps[L.taps[i]];
+      const Tap& o = L.origin[i];
+      P.odd[i] = (int8_t)o.dd; P.odh[i] = (int8_t)o.dh; P.odw[i] = (int8_t)o.dw;
+      const int r = ((t.dd - o.dd) * xh + (t.dh - o.dh)) * xw + (t.dw - o.dw);
+      MRA_REQUIRE(r >= 0 && t.dd - o.dd <= L.ext[0] && t.dh - o.dh <= L.ext[1] && t.dw - o.dw <= L.ext[2],
+                  "wgrad plan: tap outside its shared box");
+      P.rshift[i] = (int16_t)r;
+      P.twi[i] = (int16_t)t.widx;
+    }
+    const size_t stage_bytes = 2 * kChunkBytes + (size_t)(P.gpi / P.share) * P.ncc * P.box_bytes;
+    int stages = (int)((kSmemLimit - 2048) / stage_bytes);
+    MRA_REQUIRE(stages >= 2, "wgrad plan: stage does not fit shared memory");
+    if (stages > 6) stages = 6;
+    P.stages = stages;
+    P.tmem_cols = pow2_cols(P.gpi * P.ncc * 64);
+    const long long work = (long long)P.n_items * P.m_tiles * P.n_tiles;
+    const long long total_boxes = (long long)P.tilesW * P.tilesH * P.tilesD * plan.n;
+    long long splits = ((long long)num_sms() * 2) / work;
+    if (splits > total_boxes) splits = total_boxes;
+    if (splits < 1) splits = 1;
+    P.splits = (int)splits;
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+    CUtensorMap tmN;
+    if (int rc = make_shifted_map(&tmN, shifted, plan.n, sdims[0], sdims[1], sdims[2], Kn, xw, xh, xd, plan.sstep)) return rc;
+    dim3 grid((unsigned)work, (unsigned)splits);
+    wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(tmM, tmN, P);
+    MRA_LAUNCH_CHECK();
   }
-  const size_t stage_bytes = (size_t)(2 + P.n_tile / 64) * kChunkBytes;
-  int stages = (int)((kSmemLimit - 2048) / stage_bytes);
-  if (stages > 6) stages = 6;
-  P.stages = stages;
-  P.tmem_cols = pow2_cols(P.n_tile);
-  const long long work = (long long)P.ntaps * P.m_tiles * P.n_tiles;
-  const long long total_boxes = (long long)P.tilesW * P.tilesH * P.tilesD * plan.n;
-  long long splits = ((long long)num_sms() * 3 + work - 1) / work;
-  if (splits > total_boxes) splits = total_boxes;
-  if (splits < 1) splits = 1;
-  P.splits = (int)splits;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
-  // M operand = dy, N operand = x; the shifted one carries the element stride
-  const int mstep = plan.m_is_shifted ? plan.sstep : 1, nstep = plan.m_is_shifted ? 1 : plan.sstep;
-  CUtensorMap tmM, tmN;
-  if (int rc = make_act_map(&tmM, dy, plan.n, plan.mdims[0], plan.mdims[1], plan.mdims[2], plan.cm, P.bw, P.bh, P.bd, mstep))
-    return rc;
-  if (int rc = make_act_map(&tmN, x, plan.n, plan.ndims[0], plan.ndims[1], plan.ndims[2], plan.cn, P.bw, P.bh, P.bd, nstep))
-    return rc;
-  dim3 grid((unsigned)work, (unsigned)splits);
-  wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(tmM, tmN, P);
-  MRA_LAUNCH_CHECK();
   return 0;
 }
 inline int run_wgrad_tc(const mra_conv_desc& d, const void* x, const void* dy, float* dw, cudaStream_t st) {

@@ -111,3 +111,46 @@ def test_box_selection_baseline_shapes():
     # k4 s2 p1 transposed: 8 phases x 8 taps
     p = parse_gather(ops.plan_describe(ConvGeom(512, 256, 4, 2, 1, True, 0), 1, (8, 8, 8), 0))
     assert [len(L["taps"]) for L in p["launches"]] == [8] * 8
+
+
+def parse_wgrad_launches(words):
+    nt = words[18]
+    taps = [words[19 + 4 * i: 23 + 4 * i] for i in range(nt)]
+    p = 19 + 4 * nt
+    ncc, nl = words[p], words[p + 1]
+    p += 2
+    launches = []
+    for _ in range(nl):
+        share, gpi = words[p], words[p + 1]
+        ext = words[p + 2:p + 5]
+        n = words[p + 5]
+        p += 6
+        ent = [words[p + 4 * i: p + 4 * i + 4] for i in range(n)]
+        p += 4 * n
+        launches.append(dict(share=share, gpi=gpi, ext=ext, entries=ent))
+    assert p == len(words)
+    return taps, ncc, launches, words[15:18]
+
+
+@pytest.mark.parametrize("g,dims", [(ConvGeom(256, 256, 3, 1, 0), (34, 34, 34)), (ConvGeom(256, 512, 4, 1, 1), (16, 16, 16)),
+                                    (ConvGeom(64, 128, 3, 2, 1), (64, 64, 64)), (ConvGeom(128, 64, 3, 2, 1, True, 1), (16, 16, 16)),
+                                    (ConvGeom(64, 128, 4, 2, 1), (32, 32, 32)), (ConvGeom(128, 128, 4, 1, 1), (33, 33, 33))],
+                         ids=["rb", "d4", "g_d1", "g_u2", "d2", "k4s1_w32"])
+def test_wgrad_launch_structure(g, dims):
+    """Every tap appears exactly once; taps that share a shared-memory box sit inside the extended box;
+    the accumulators of one item fit the 512 TMEM columns."""
+    taps, ncc, launches, box = parse_wgrad_launches(ops.plan_describe(g, 1, dims, 2))
+    seen = []
+    for L in launches:
+        assert L["share"] in (1, 2) and L["gpi"] % L["share"] == 0 and L["gpi"] * ncc * 64 <= 512
+        if L["share"] == 2:
+            assert g.stride == 1 and box[2] % 16 == 0
+        for i, (ti, odd, odh, odw) in enumerate(L["entries"]):
+            seen.append(ti)
+            dd, dh, dw, _ = taps[ti]
+            assert 0 <= dd - odd <= L["ext"][0] and 0 <= dh - odh <= L["ext"][1] and 0 <= dw - odw <= L["ext"][2]
+            if L["share"] == 2 and i % 2 == 1 and (i // L["gpi"]) == ((i - 1) // L["gpi"]):
+                assert L["entries"][i - 1][1:] == [odd, odh, odw]
+    assert sorted(seen) == list(range(len(taps)))
+    if g == ConvGeom(256, 256, 3, 1, 0):
+        assert [(L["share"], len(L["entries"])) for L in launches] == [(2, 18), (2, 6), (1, 3)]
