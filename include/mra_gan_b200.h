@@ -159,6 +159,10 @@ int mra_conv_plan_describe(const mra_conv_desc* d, int which, int32_t* out, int 
  * bounded mbarrier wait expires.  Synchronises the device; for tests / debugging only. */
 int mra_debug_tc_error(int reset);
 
+/* Reads (reset != 0: and clears) 8 device-side cycle counters that the tensor-core kernels fill when run
+ * with the MRA_WGRAD_DEBUG / MRA_GATHER_DEBUG environment bit 1 set (pipeline diagnosis; synchronises). */
+int mra_debug_counters(unsigned long long* out, int reset);
+
 /* Number of kernels this library has launched in this process (host-side counter). */
 long long mra_debug_launch_count(void);
 

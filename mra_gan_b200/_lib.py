@@ -39,6 +39,7 @@ _SIGNATURES = {
     "mra_last_error": ([], C.c_char_p),
     "mra_debug_tc_error": ([_I], C.c_int),
     "mra_debug_launch_count": ([], C.c_longlong),
+    "mra_debug_counters": ([C.POINTER(C.c_ulonglong), _I], C.c_int),
     "mra_conv3d_fprop": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, C.c_size_t, _P], C.c_int),
     "mra_conv3d_dgrad": ([C.POINTER(ConvDesc), _P, _P, _P, _P, C.c_size_t, _P], C.c_int),
     "mra_conv3d_wgrad": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, C.c_size_t, _P], C.c_int),

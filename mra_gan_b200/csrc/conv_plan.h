@@ -20,6 +20,7 @@
 // emulate it against torch's conv3d / conv_transpose3d without a GPU.
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 #include <vector>
 
 #include "../../include/mra_gan_b200.h"
@@ -217,7 +218,9 @@ inline bool build_wgrad_plan(const GeomEx& d, WgradPlan& P) {
       if (kw < K2) left.push_back(ti(kd, kh, kw));
     }
     // the leftovers all have kw = K2-1: pair them along h
-    for (int kd = 0; kd < K0 && (K2 & 1); ++kd) {
+    const bool no_hpairs = getenv("MRA_WGRAD_NO_HPAIRS") != nullptr;
+    if (no_hpairs) rest = left;
+    for (int kd = 0; kd < K0 && (K2 & 1) && !no_hpairs; ++kd) {
       int kh = 0;
       for (; kh + 1 < K1; kh += 2) { hpairs.push_back(ti(kd, kh, K2 - 1)); hpairs.push_back(ti(kd, kh + 1, K2 - 1)); }
       if (kh < K1) rest.push_back(ti(kd, kh, K2 - 1));
@@ -228,9 +231,8 @@ inline bool build_wgrad_plan(const GeomEx& d, WgradPlan& P) {
   const int gshare = cap - (cap & 1);
   wgrad_add_launch(P, wpairs, 2, gshare, 0, 0, 1);
   wgrad_add_launch(P, hpairs, 2, gshare, 0, 1, 0);
-  // unshared taps: each tap needs its own ncc boxes per stage; keep the stage small enough for >= 3 stages
-  int gsolo = cap;
-  while (gsolo > 1 && gsolo * P.ncc > 5) --gsolo;
+  // unshared taps: each tap needs its own ncc boxes per stage; 4 / ncc taps = 256 accumulator columns = one MMA
+  const int gsolo = P.ncc >= 4 ? 1 : 4 / P.ncc;
   wgrad_add_launch(P, rest, 1, gsolo, 0, 0, 0);
   return true;
 }

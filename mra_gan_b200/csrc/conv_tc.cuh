@@ -361,13 +361,24 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // D[tap][m][n] = sum_{positions q} Dense[q][m] * Shifted[q*sstep + tap][n]
 //   Dense   = the operand read at the K-block positions themselves (dy for Conv3d, x for ConvTranspose3d),
 //   Shifted = the other one (x for Conv3d, dy for ConvTranspose3d).
-// One CTA = (item, 128-row m tile, n tile of 64*ncc channels) x one split of the position space.  An item
-// is up to 8/ncc filter taps whose accumulators sit side by side in TMEM (<= 512 columns), so the dense
-// tile of a K-block (64 positions) is loaded once for all of them.  With share == 2 two taps that are
-// neighbours along w (or h) read ONE shared-memory box of the shifted operand, extended by one column
-// (row): the UMMA descriptor of the second tap simply starts `rshift` rows later (the SWIZZLE_128B pattern
-// is a function of the absolute shared-memory address, so row-shifted starts are legal; verified by
+// Work item = (item, 128-row m tile, n tile of 64*ncc channels).  An item is up to 8/ncc filter taps whose
+// accumulators sit side by side in TMEM (<= 512 columns), so the dense tile of a K-block (64 positions) is
+// loaded once for all of them.  Taps come in up to 4 GROUPS; in a group with share == 2 two taps that are
+// neighbours along w (or h) read ONE shared-memory box of the shifted operand, extended by one column (row):
+// the UMMA descriptor of the second tap simply starts `rshift` rows later (the SWIZZLE_128B pattern is a
+// function of the absolute shared-memory address, so row-shifted starts are legal; verified by
 // tools/halo_probe.cu).  Both operands are position-major = MN-major for the MMA.
+// Scheduling is stream-K: the (work item x K-block) space, weighted by taps per item, is cut into
+// gridDim.x equal contiguous ranges (one CTA per SM, one wave); a CTA whose range crosses a work-item
+// boundary flushes its accumulators (fp32 red.global.add) and continues with the next item.
+constexpr int kMaxWGroups = 4;
+struct WGroup {
+  int tap0, ntaps;                  // range in the launch-ordered tap arrays
+  int item0, n_items;               // range of items
+  int gpi, share;                   // taps per item, taps per box set
+  int pitch_w, pitch_h;             // rows per h line / per d plane of a shifted-operand box
+  int box_tx;                       // bytes one 64-channel box delivers
+};
 struct WgradP {
   int tilesW, tilesH, tilesD;       // K-block boxes per dim of the dense position space
   int bw, bh, bd;                   // K-block box (product 64)
@@ -376,60 +387,103 @@ struct WgradP {
   int Km, Kn;                       // channels of the dense / shifted operand
   int m_chunks;                     // 64-channel chunks of the dense operand per m tile (1 or 2)
   int ncc;                          // 64-channel chunks of the shifted operand per tap
-  int gpi, share;                   // taps per item, taps per box set
-  int pitch_w, pitch_h;             // rows per h line / per d plane of a shifted-operand box
-  int box_bytes;                    // shared-memory slot of one 64-channel box of the shifted operand (multiple of 1024)
-  int box_tx;                       // bytes one such box actually delivers
-  int n_items, m_tiles, n_tiles, ntaps;
-  int splits;
+  int box_bytes;                    // shared-memory slot of one 64-channel shifted box (multiple of 1024, max over groups)
+  int sets_max;                     // box sets per stage slot (max over groups)
+  int n_groups, n_items, m_tiles, n_tiles;
+  long long total_cost;             // sum over work items of taps(item) * K-blocks
   float* dw;
   long long tap_stride, m_stride, n_stride;   // element strides of dw[tap][m][n] in memory
   int* err;
   int stages;
   uint32_t tmem_cols;
+  WGroup grp[kMaxWGroups];
   int8_t odd[kMaxTaps], odh[kMaxTaps], odw[kMaxTaps];   // box origin offset per tap (launch order)
   int16_t rshift[kMaxTaps];                             // row shift of the tap inside its box
   int16_t twi[kMaxTaps];                                // weight slab index of the tap
+  int debug;                                            // bit 0: skip the global reductions, bit 1: cycle counters
+  unsigned long long* dbg;
 };
+struct WMaps { CUtensorMap m[kMaxWGroups]; };
 
 constexpr uint32_t kChunkBytes = 64 * 128;       // 64 positions x 64 bf16
 
+// One contiguous piece of a CTA's stream-K range that lies inside a single work item.
+struct WSeg { int item, mt, nt, g, tap0, ntap, kb0, kb1; };
+struct WSegIter {
+  long long pos, end, woff;
+  int work;
+};
+__device__ __forceinline__ int wg_item_group(const WgradP& P, int item) {
+  int g = 0;
+  while (g + 1 < P.n_groups && item >= P.grp[g + 1].item0) ++g;
+  return g;
+}
+__device__ __forceinline__ int wg_item_ntap(const WgradP& P, int g, int item) {
+  const WGroup& G = P.grp[g];
+  return min(G.gpi, G.ntaps - (item - G.item0) * G.gpi);
+}
+__device__ __forceinline__ void wseg_begin(const WgradP& P, long long kblocks, WSegIter& it) {
+  const long long share = (P.total_cost + gridDim.x - 1) / gridDim.x;
+  it.pos = (long long)blockIdx.x * share;
+  it.end = min(it.pos + share, P.total_cost);
+  it.work = 0; it.woff = 0;
+  const int per_item = P.m_tiles * P.n_tiles;
+  const int n_work = P.n_items * per_item;
+  while (it.work < n_work) {                       // skip the work items that end before this CTA's range
+    const int item = it.work / per_item;
+    const long long span = (long long)wg_item_ntap(P, wg_item_group(P, item), item) * kblocks;
+    if (it.woff + span > it.pos) break;
+    it.woff += span; ++it.work;
+  }
+}
+__device__ __forceinline__ bool wseg_next(const WgradP& P, long long kblocks, WSegIter& it, WSeg& sg) {
+  const int per_item = P.m_tiles * P.n_tiles;
+  const int n_work = P.n_items * per_item;
+  while (it.pos < it.end && it.work < n_work) {
+    const int item = it.work / per_item;
+    const int g = wg_item_group(P, item);
+    const int ntap = wg_item_ntap(P, g, item);
+    const long long span = (long long)ntap * kblocks;
+    const long long lo = it.pos, hi = min(it.end, it.woff + span);
+    const int kb0 = (int)((lo - it.woff) / ntap);
+    const int kb1 = hi == it.woff + span ? (int)kblocks : (int)((hi - it.woff) / ntap);
+    const int w = it.work;
+    it.pos = hi;
+    if (hi == it.woff + span) { it.woff += span; ++it.work; }
+    if (kb1 > kb0) {
+      const int rem = w - item * per_item;
+      sg.item = item; sg.mt = rem / P.n_tiles; sg.nt = rem - sg.mt * P.n_tiles; sg.g = g;
+      sg.tap0 = P.grp[g].tap0 + (item - P.grp[g].item0) * P.grp[g].gpi; sg.ntap = ntap; sg.kb0 = kb0; sg.kb1 = kb1;
+      return true;
+    }
+  }
+  return false;
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmN,
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ WMaps tmN,
                 const __grid_constant__ WgradP P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  int w = blockIdx.x;
-  const int nt = w % P.n_tiles; w /= P.n_tiles;
-  const int mt = w % P.m_tiles;
-  const int item = w / P.m_tiles;
-  const int m0 = mt * 128, n0 = nt * P.ncc * 64;
-  const int tap0 = item * P.gpi;
-  const int ntap = min(P.gpi, P.ntaps - tap0);              // taps of this item
-  const int nsets = (ntap + P.share - 1) / P.share;         // box sets loaded per K-block
   const uint32_t m_bytes = 2 * kChunkBytes;                  // the m tile always owns two chunk slots
   const uint32_t set_bytes = (uint32_t)P.ncc * (uint32_t)P.box_bytes;
-  const uint32_t stage_bytes = m_bytes + (uint32_t)(P.gpi / P.share) * set_bytes;
+  const uint32_t stage_bytes = m_bytes + (uint32_t)P.sets_max * set_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + P.stages;
-  uint64_t* accum_bar = empty_bar + P.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* acc_full = empty_bar + P.stages;
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
-  const long long boxes_per_sample = (long long)P.tilesW * P.tilesH * P.tilesD;
-  const long long total_boxes = boxes_per_sample * P.N;
-  const long long per_split = (total_boxes + P.splits - 1) / P.splits;
-  const long long b0 = (long long)blockIdx.y * per_split;
-  long long b1 = b0 + per_split;
-  if (b1 > total_boxes) b1 = total_boxes;
-  const int iters = b1 > b0 ? (int)(b1 - b0) : 0;
+  const int boxes_per_sample = P.tilesW * P.tilesH * P.tilesD;
+  const long long kblocks = (long long)boxes_per_sample * P.N;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmM);
-    prefetch_tmap(&tmN);
+    for (int g = 0; g < P.n_groups; ++g) prefetch_tmap(&tmN.m[g]);
     for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(accum_bar, 1);
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 4);
     fence_barrier_init();
   }
   if (P.m_chunks == 1) {
@@ -445,76 +499,130 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tx_bytes = (uint32_t)P.m_chunks * kChunkBytes + (uint32_t)(nsets * P.ncc) * (uint32_t)P.box_tx;
+  const bool prof = (P.debug & 2) != 0;
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % P.stages;
-        const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
-        if (!mbar_wait(&empty_bar[s], ph ^ 1u, P.err, 11)) break;
-        long long b = b0 + it;
-        const int n = (int)(b / boxes_per_sample);
-        int r = (int)(b - (long long)n * boxes_per_sample);
-        const int qw = (r % P.tilesW) * P.bw; r /= P.tilesW;
-        const int qh = (r % P.tilesH) * P.bh;
-        const int qd = (r / P.tilesH) * P.bd;
-        uint8_t* sa = smem + (size_t)s * stage_bytes;
-        mbar_expect_tx(&full_bar[s], tx_bytes);
-        for (int c = 0; c < P.m_chunks; ++c)
-          tma_load_5d(sa + c * kChunkBytes, &tmM, &full_bar[s], m0 + 64 * c, qw, qh, qd, n);
-        for (int bs = 0; bs < nsets; ++bs) {
-          const int t = tap0 + bs * P.share;
-          const int cw = qw * P.sstep + P.odw[t], ch = qh * P.sstep + P.odh[t], cd = qd * P.sstep + P.odd[t];
-          uint8_t* sb = sa + m_bytes + (size_t)bs * set_bytes;
-          for (int j = 0; j < P.ncc; ++j)
-            tma_load_5d(sb + (size_t)j * P.box_bytes, &tmN, &full_bar[s], n0 + 64 * j, cw, ch, cd, n);
+    // ---- TMA producer: lane j issues box j of every stage (box 0..m_chunks-1 dense, then the shifted boxes)
+    WSegIter it; WSeg sg;
+    wseg_begin(P, kblocks, it);
+    uint32_t git = 0;
+    long long t_wait = 0, t_begin = prof ? clock64() : 0;
+    bool ok = true;
+    while (ok && wseg_next(P, kblocks, it, sg)) {
+      const WGroup& G = P.grp[sg.g];
+      const int nsets = (sg.ntap + G.share - 1) / G.share;
+      const int nboxes = P.m_chunks + nsets * P.ncc;
+      const uint32_t tx_bytes = (uint32_t)P.m_chunks * kChunkBytes + (uint32_t)(nsets * P.ncc) * (uint32_t)G.box_tx;
+      // this lane's box
+      const bool active = lane < nboxes;
+      const bool dense = lane < P.m_chunks;
+      int c0 = 0, ow = 0, oh = 0, od = 0, step = 1;
+      uint32_t soff = 0;
+      const CUtensorMap* tm = &tmM;
+      if (active) {
+        if (dense) { c0 = sg.mt * 128 + 64 * lane; soff = (uint32_t)lane * kChunkBytes; }
+        else {
+          const int bi = lane - P.m_chunks, bs = bi / P.ncc, j = bi - bs * P.ncc;
+          const int t = sg.tap0 + bs * G.share;
+          c0 = sg.nt * P.ncc * 64 + 64 * j; ow = P.odw[t]; oh = P.odh[t]; od = P.odd[t]; step = P.sstep;
+          soff = m_bytes + (uint32_t)bs * set_bytes + (uint32_t)j * (uint32_t)P.box_bytes;
+          tm = &tmN.m[sg.g];
         }
       }
+      // K-block coordinates, advanced incrementally
+      int n = sg.kb0 / boxes_per_sample;
+      int r = sg.kb0 - n * boxes_per_sample;
+      int tw = r % P.tilesW; r /= P.tilesW;
+      int th = r % P.tilesH;
+      int td = r / P.tilesH;
+      for (int kb = sg.kb0; kb < sg.kb1; ++kb, ++git) {
+        const int s = git % P.stages;
+        const uint32_t ph = (git / P.stages) & 1u;
+        const long long tw0 = prof ? clock64() : 0;
+        if (!mbar_wait(&empty_bar[s], ph ^ 1u, P.err, 11)) { ok = false; break; }
+        if (prof) t_wait += clock64() - tw0;
+        if (lane == 0) mbar_expect_tx(&full_bar[s], tx_bytes);
+        __syncwarp();
+        if (active)
+          tma_load_5d(smem + (size_t)s * stage_bytes + soff, tm, &full_bar[s], c0, tw * P.bw * step + ow,
+                      th * P.bh * step + oh, td * P.bd * step + od, n);
+        if (++tw == P.tilesW) { tw = 0; if (++th == P.tilesH) { th = 0; if (++td == P.tilesD) { td = 0; ++n; } } }
+      }
     }
+    if (prof && lane == 0) { atomicAdd(P.dbg + 0, (unsigned long long)t_wait); atomicAdd(P.dbg + 1, (unsigned long long)(clock64() - t_begin)); }
   } else if (warp == 1) {
-    if (lane == 0 && iters > 0) {
+    if (lane == 0) {
       const uint32_t idesc = make_idesc(P.ncc * 64, 1, 1);
-      // row of the shifted box that pairs with dense row 16*j (dense rows are (d, h, w) over the K-block box)
-      uint32_t rowmap[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int k = 16 * j;
-        const int kw_ = k % P.bw, kh_ = (k / P.bw) % P.bh, kd_ = k / (P.bw * P.bh);
-        rowmap[j] = (uint32_t)(kd_ * P.pitch_h + kh_ * P.pitch_w + kw_);
-      }
+      WSegIter it; WSeg sg;
+      wseg_begin(P, kblocks, it);
+      uint32_t git = 0;
+      int nseg = 0;
       bool ok = true;
-      for (int it = 0; it < iters && ok; ++it) {
-        const int s = it % P.stages;
-        const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
-        ok = mbar_wait(&full_bar[s], ph, P.err, 12);
-        if (!ok) break;
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t sb = sa + m_bytes;
-        for (int g = 0; g < ntap; ++g) {
-          const uint32_t bset = sb + (uint32_t)(g / P.share) * set_bytes + (uint32_t)P.rshift[tap0 + g] * 128u;
-          const uint32_t d_tmem = tmem_base + (uint32_t)(g * P.ncc * 64);
+      long long t_wait = 0, t_begin = prof ? clock64() : 0;
+      while (ok && wseg_next(P, kblocks, it, sg)) {
+        const WGroup& G = P.grp[sg.g];
+        // row of the shifted box that pairs with dense row 16*j (dense rows are (d, h, w) over the K-block box)
+        uint32_t rowmap[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k)      // 16 positions (rows of 128 B) per MMA
-            umma_f16(d_tmem, desc_mnmajor_sw128(sa + k * 2048, kChunkBytes),
-                     desc_mnmajor_sw128(bset + rowmap[k] * 128u, (uint32_t)P.box_bytes), idesc, (uint32_t)((it | k) != 0));
+        for (int j = 0; j < 4; ++j) {
+          const int k = 16 * j;
+          const int kw_ = k % P.bw, kh_ = (k / P.bw) % P.bh, kd_ = k / (P.bw * P.bh);
+          rowmap[j] = (uint32_t)(kd_ * G.pitch_h + kh_ * G.pitch_w + kw_);
         }
-        umma_commit(&empty_bar[s]);
+        if (nseg > 0) {                                   // the epilogue must have drained the previous item
+          if (!mbar_wait(acc_empty, (uint32_t)(nseg - 1) & 1u, P.err, 15)) { ok = false; break; }
+          tc_fence_after();
+        }
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb, ++git) {
+          const int s = git % P.stages;
+          const uint32_t ph = (git / P.stages) & 1u;
+          const long long tw0 = prof ? clock64() : 0;
+          if (!mbar_wait(&full_bar[s], ph, P.err, 12)) { ok = false; break; }
+          if (prof) t_wait += clock64() - tw0;
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t sb = sa + m_bytes;
+          // taps that own their boxes (share == 1) sit back to back in the stage: up to 256 accumulator
+          // columns (4 / ncc taps) go into ONE MMA, the chunk stride (LBO) being the box slot size
+          const int tpm = G.share == 1 ? (P.ncc >= 4 ? 1 : 4 / P.ncc) : 1;
+          for (int g = 0; g < sg.ntap; g += tpm) {
+            const int nt = min(tpm, sg.ntap - g);
+            const uint32_t bset = sb + (uint32_t)(g / G.share) * set_bytes + (uint32_t)P.rshift[sg.tap0 + g] * 128u;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(g * P.ncc * 64);
+            const uint32_t id = nt == 1 ? idesc : make_idesc(nt * P.ncc * 64, 1, 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)      // 16 positions (rows of 128 B) per MMA
+              umma_f16(d_tmem, desc_mnmajor_sw128(sa + k * 2048, kChunkBytes),
+                       desc_mnmajor_sw128(bset + rowmap[k] * 128u, (uint32_t)P.box_bytes), id,
+                       (uint32_t)((kb != sg.kb0) | (k != 0)));
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        if (ok) umma_commit(acc_full);
+        ++nseg;
       }
-      umma_commit(accum_bar);
+      if (prof) {
+        atomicAdd(P.dbg + 2, (unsigned long long)t_wait); atomicAdd(P.dbg + 3, (unsigned long long)(clock64() - t_begin));
+        atomicAdd(P.dbg + 5, 1ull);
+      }
     }
-  } else if (iters > 0) {
+  } else {
     const int q = warp & 3;
     const int ml = q * 32 + lane;
-    const int m = m0 + ml;
-    const bool valid = ml < 64 * P.m_chunks && m < P.Km;
-    const bool ok = mbar_wait(accum_bar, 0, P.err, 13);
-    tc_fence_after();
-    if (ok) {
-      const int ncols = P.ncc * 64;
-      for (int g = 0; g < ntap; ++g) {
-        float* obase = P.dw + (long long)P.twi[tap0 + g] * P.tap_stride + (long long)m * P.m_stride;
+    WSegIter it; WSeg sg;
+    wseg_begin(P, kblocks, it);
+    int nseg = 0;
+    long long t_epi = 0;
+    const int ncols = P.ncc * 64;
+    while (wseg_next(P, kblocks, it, sg)) {
+      if (!mbar_wait(acc_full, (uint32_t)nseg & 1u, P.err, 13)) break;
+      tc_fence_after();
+      const long long te0 = prof ? clock64() : 0;
+      const int m = sg.mt * 128 + ml;
+      const int n0 = sg.nt * ncols;
+      const bool valid = ml < 64 * P.m_chunks && m < P.Km && !(P.debug & 1);
+      for (int g = 0; g < sg.ntap; ++g) {
+        float* obase = P.dw + (long long)P.twi[sg.tap0 + g] * P.tap_stride + (long long)m * P.m_stride;
         for (int c0 = 0; c0 < ncols; c0 += 32) {
           uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * ncols + c0), r);
@@ -528,7 +636,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
                            "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
                            : "memory");
           } else {
-#pragma unroll
+#pragma unroll 8
             for (int j = 0; j < 32; ++j)
               asm volatile("red.global.add.f32 [%0], %1;" ::"l"(obase + (long long)(n0 + c0 + j) * P.n_stride),
                            "f"(__uint_as_float(r[j]))
@@ -536,7 +644,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
           }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);              // accumulators are free for the next item
+      if (prof) t_epi += clock64() - te0;
+      ++nseg;
     }
+    if (prof && threadIdx.x == 64) atomicAdd(P.dbg + 4, (unsigned long long)t_epi);
   }
   tc_fence_before();
   __syncthreads();
@@ -603,6 +717,18 @@ inline int* tc_err_flag() {
     cudaMemset(flag, 0, sizeof(int));
   }
   return flag;
+}
+
+// device-side cycle counters for pipeline diagnosis (filled only when a kernel runs with a debug bit set):
+// [0] producer cycles waiting for a free stage, [1] producer total, [2] MMA cycles waiting for data,
+// [3] MMA total, [4] epilogue cycles, [5] CTAs counted
+inline unsigned long long* tc_dbg_counters() {
+  static unsigned long long* buf = nullptr;
+  if (!buf) {
+    if (cudaMalloc(&buf, 8 * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+    cudaMemset(buf, 0, 8 * sizeof(unsigned long long));
+  }
+  return buf;
 }
 
 inline int pick_n_tile(int cn) {
@@ -703,16 +829,11 @@ inline int run_gather_tc(const mra_conv_desc& d, int which, const void* a, const
   return run_gather_tc(plan, R, st);
 }
 
-// shifted-operand box: channels-last bf16 [N][D][H][W][C] -> box (64, (bw+ew)*s, (bh+eh)*s, (bd+ed)*s, 1)
-inline int make_shifted_map(CUtensorMap* tm, const void* base, int N, int D, int H, int W, int C, int xw, int xh, int xd,
-                            int step) {
-  return make_act_map(tm, base, N, D, H, W, C, xw, xh, xd, step);
-}
-
 inline int run_wgrad_tc(const WgradPlan& plan, const void* x, const void* dy, float* dw, cudaStream_t st) {
   int* err = tc_err_flag();
   MRA_REQUIRE(plan.cm % 64 == 0 && plan.cn % 64 == 0 && (int)plan.taps.size() <= kMaxTaps,
               "shape not eligible for the tensor-core wgrad path");
+  MRA_REQUIRE(!plan.launches.empty() && (int)plan.launches.size() <= kMaxWGroups, "wgrad plan: bad group count");
   static bool attr_set = false;
   if (!attr_set) {
     MRA_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
@@ -728,59 +849,74 @@ inline int run_wgrad_tc(const WgradPlan& plan, const void* x, const void* dy, fl
   CUtensorMap tmM;
   if (int rc = make_act_map(&tmM, dense, plan.n, ddims[0], ddims[1], ddims[2], Km, plan.box[2], plan.box[1], plan.box[0], 1))
     return rc;
-  for (const WgradLaunch& L : plan.launches) {
-    WgradP P;
-    memset(&P, 0, sizeof(P));
-    P.bd = plan.box[0]; P.bh = plan.box[1]; P.bw = plan.box[2];
-    P.tilesD = (plan.qdims[0] + P.bd - 1) / P.bd; P.tilesH = (plan.qdims[1] + P.bh - 1) / P.bh;
-    P.tilesW = (plan.qdims[2] + P.bw - 1) / P.bw;
-    P.N = plan.n; P.sstep = plan.sstep;
-    P.Km = Km; P.Kn = Kn;
-    P.m_chunks = Km >= 128 ? 2 : 1;
-    P.ncc = plan.ncc;
-    P.gpi = L.gpi; P.share = L.share;
+  WMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  WgradP P;
+  memset(&P, 0, sizeof(P));
+  P.bd = plan.box[0]; P.bh = plan.box[1]; P.bw = plan.box[2];
+  P.tilesD = (plan.qdims[0] + P.bd - 1) / P.bd; P.tilesH = (plan.qdims[1] + P.bh - 1) / P.bh;
+  P.tilesW = (plan.qdims[2] + P.bw - 1) / P.bw;
+  P.N = plan.n; P.sstep = plan.sstep;
+  P.Km = Km; P.Kn = Kn;
+  P.m_chunks = Km >= 128 ? 2 : 1;
+  P.ncc = plan.ncc;
+  P.m_tiles = (Km + 127) / 128;
+  P.n_tiles = Kn / (64 * P.ncc);
+  P.dw = dw; P.err = err;
+  { const char* e = getenv("MRA_WGRAD_DEBUG"); P.debug = e ? atoi(e) : 0; }
+  P.dbg = tc_dbg_counters();
+  // dw memory is [taps][cm][cn] (cm = cout, cn = cin); kernel rows m index the dense operand's channels
+  P.tap_stride = (long long)plan.cm * plan.cn;
+  if (!sw) { P.m_stride = plan.cn; P.n_stride = 1; }
+  else     { P.m_stride = 1; P.n_stride = plan.cn; }
+  const long long kblocks = (long long)P.tilesW * P.tilesH * P.tilesD * plan.n;
+  P.n_groups = (int)plan.launches.size();
+  int tapc = 0, itemc = 0, max_cols = 0;
+  for (int gi = 0; gi < P.n_groups; ++gi) {
+    const WgradLaunch& L = plan.launches[gi];
+    WGroup& G = P.grp[gi];
     const int xd = P.bd + L.ext[0], xh = P.bh + L.ext[1], xw = P.bw + L.ext[2];
-    P.pitch_w = xw; P.pitch_h = xh * xw;
-    P.box_tx = xd * xh * xw * 128;
-    P.box_bytes = (P.box_tx + 1023) / 1024 * 1024;
-    P.ntaps = (int)L.taps.size();
-    P.n_items = (P.ntaps + P.gpi - 1) / P.gpi;
-    P.m_tiles = (Km + 127) / 128;
-    P.n_tiles = Kn / (64 * P.ncc);
-    P.dw = dw; P.err = err;
-    // dw memory is [taps][cm][cn] (cm = cout, cn = cin); kernel rows m index the dense operand's channels
-    P.tap_stride = (long long)plan.cm * plan.cn;
-    if (!sw) { P.m_stride = plan.cn; P.n_stride = 1; }
-    else     { P.m_stride = 1; P.n_stride = plan.cn; }
-    for (int i = 0; i < P.ntaps; ++i) {
+    G.tap0 = tapc; G.ntaps = (int)L.taps.size();
+    G.gpi = L.gpi; G.share = L.share;
+    G.item0 = itemc; G.n_items = (G.ntaps + G.gpi - 1) / G.gpi;
+    G.pitch_w = xw; G.pitch_h = xh * xw;
+    G.box_tx = xd * xh * xw * 128;
+    const int slot = (G.box_tx + 1023) / 1024 * 1024;
+    if (slot > P.box_bytes) P.box_bytes = slot;
+    if (G.gpi / G.share > P.sets_max) P.sets_max = G.gpi / G.share;
+    if (G.gpi * P.ncc * 64 > max_cols) max_cols = G.gpi * P.ncc * 64;
+    for (int i = 0; i < G.ntaps; ++i) {
       const Tap& t = plan.taps[L.taps[i]];
       const Tap& o = L.origin[i];
-      P.odd[i] = (int8_t)o.dd; P.odh[i] = (int8_t)o.dh; P.odw[i] = (int8_t)o.dw;
+      P.odd[tapc + i] = (int8_t)o.dd; P.odh[tapc + i] = (int8_t)o.dh; P.odw[tapc + i] = (int8_t)o.dw;
       const int r = ((t.dd - o.dd) * xh + (t.dh - o.dh)) * xw + (t.dw - o.dw);
       MRA_REQUIRE(r >= 0 && t.dd - o.dd <= L.ext[0] && t.dh - o.dh <= L.ext[1] && t.dw - o.dw <= L.ext[2],
                   "wgrad plan: tap outside its shared box");
-      P.rshift[i] = (int16_t)r;
-      P.twi[i] = (int16_t)t.widx;
+      P.rshift[tapc + i] = (int16_t)r;
+      P.twi[tapc + i] = (int16_t)t.widx;
     }
-    const size_t stage_bytes = 2 * kChunkBytes + (size_t)(P.gpi / P.share) * P.ncc * P.box_bytes;
-    int stages = (int)((kSmemLimit - 2048) / stage_bytes);
-    MRA_REQUIRE(stages >= 2, "wgrad plan: stage does not fit shared memory");
-    if (stages > 6) stages = 6;
-    P.stages = stages;
-    P.tmem_cols = pow2_cols(P.gpi * P.ncc * 64);
-    const long long work = (long long)P.n_items * P.m_tiles * P.n_tiles;
-    const long long total_boxes = (long long)P.tilesW * P.tilesH * P.tilesD * plan.n;
-    long long splits = ((long long)num_sms() * 2) / work;
-    if (splits > total_boxes) splits = total_boxes;
-    if (splits < 1) splits = 1;
-    P.splits = (int)splits;
-    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
-    CUtensorMap tmN;
-    if (int rc = make_shifted_map(&tmN, shifted, plan.n, sdims[0], sdims[1], sdims[2], Kn, xw, xh, xd, plan.sstep)) return rc;
-    dim3 grid((unsigned)work, (unsigned)splits);
-    wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(tmM, tmN, P);
-    MRA_LAUNCH_CHECK();
+    for (int it = 0; it < G.n_items; ++it) {
+      const int nt = G.ntaps - it * G.gpi < G.gpi ? G.ntaps - it * G.gpi : G.gpi;
+      P.total_cost += (long long)nt * kblocks * P.m_tiles * P.n_tiles;
+    }
+    tapc += G.ntaps; itemc += G.n_items;
+    if (int rc = make_act_map(&maps.m[gi], shifted, plan.n, sdims[0], sdims[1], sdims[2], Kn, xw, xh, xd, plan.sstep)) return rc;
   }
+  MRA_REQUIRE(tapc <= kMaxTaps, "wgrad plan: too many taps");
+  P.n_items = itemc;
+  const size_t stage_bytes = 2 * kChunkBytes + (size_t)P.sets_max * P.ncc * P.box_bytes;
+  int stages = (int)((kSmemLimit - 2048) / stage_bytes);
+  MRA_REQUIRE(stages >= 2, "wgrad plan: stage does not fit shared memory");
+  if (stages > 6) stages = 6;
+  P.stages = stages;
+  P.tmem_cols = pow2_cols(max_cols);
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  // one wave: a CTA per SM (fewer when there is less than ~4 K-blocks of work per CTA)
+  long long ctas = num_sms();
+  if (P.total_cost < ctas * 4) ctas = (P.total_cost + 3) / 4;
+  if (ctas < 1) ctas = 1;
+  wgrad_tc_kernel<<<(unsigned)ctas, kThreads, smem, st>>>(tmM, maps, P);
+  MRA_LAUNCH_CHECK();
   return 0;
 }
 inline int run_wgrad_tc(const mra_conv_desc& d, const void* x, const void* dy, float* dw, cudaStream_t st) {

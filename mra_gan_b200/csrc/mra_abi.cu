@@ -365,4 +365,13 @@ int mra_debug_tc_error(int reset) {
   return v;
 }
 
+// Reads (and optionally clears) the tensor-core kernels' debug cycle counters (8 x uint64).  Synchronises.
+int mra_debug_counters(unsigned long long* out, int reset) {
+  unsigned long long* buf = tc::tc_dbg_counters();
+  if (!buf || !out) return -1;
+  if (cudaMemcpy(out, buf, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+  if (reset) cudaMemset(buf, 0, 8 * sizeof(unsigned long long));
+  return 0;
+}
+
 }  // extern "C"

@@ -294,6 +294,11 @@ class CudaImpl:
     def tc_error(self, reset=True):
         return int(self.L.mra_debug_tc_error(int(reset)))
 
+    def debug_counters(self, reset=True):
+        buf = (C.c_ulonglong * 8)()
+        _lib.check(self.L.mra_debug_counters(buf, int(reset)), "mra_debug_counters")
+        return list(buf)
+
     def launch_count(self):
         return int(self.L.mra_debug_launch_count())
 
