@@ -170,6 +170,8 @@ struct GatherP {
   uint32_t tmem_cols;               // 2 accumulator buffers of n_tile columns (power of two >= 32)
   int8_t tdd[kMaxTaps], tdh[kMaxTaps], tdw[kMaxTaps];
   int16_t twi[kMaxTaps];
+  int debug;                        // bit 1: cycle counters into dbg (see tc_dbg_counters)
+  unsigned long long* dbg;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -225,12 +227,16 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       uint32_t git = 0;                                    // global k-iteration counter (stage ring position)
       bool ok = true;
+      const bool prof = (P.debug & 2) != 0;
+      long long t_wait = 0, t_begin = prof ? clock64() : 0;
       for (int tile = blockIdx.x; tile < P.total_tiles && ok; tile += gridDim.x) {
         const TileCoord t = decode_tile(P, tile);
         for (int it = 0; it < iters; ++it, ++git) {
           const int s = git % P.stages;
           const uint32_t ph = (git / P.stages) & 1u;
+          const long long tw0 = prof ? clock64() : 0;
           if (!mbar_wait(&empty_bar[s], ph ^ 1u, P.err, 1)) { ok = false; break; }
+          if (prof) t_wait += clock64() - tw0;
           const int tap = it / P.kchunks, kc = it - tap * P.kchunks;
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           mbar_expect_tx(&full_bar[s], stage_bytes);
@@ -239,6 +245,7 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tma_load_2d(sa + kABytes, &tmB, &full_bar[s], kc * 64, (int)P.twi[tap] * P.Cn + t.n0);
         }
       }
+      if (prof) { atomicAdd(P.dbg + 0, (unsigned long long)t_wait); atomicAdd(P.dbg + 1, (unsigned long long)(clock64() - t_begin)); }
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -246,16 +253,22 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t git = 0;
       bool ok = true;
       int j = 0;
+      const bool prof = (P.debug & 2) != 0;
+      long long t_wait = 0, t_wacc = 0, t_begin = prof ? clock64() : 0;
       for (int tile = blockIdx.x; tile < P.total_tiles && ok; tile += gridDim.x, ++j) {
         const int buf = j & 1;
         const uint32_t aph = ((uint32_t)j >> 1) & 1u;
+        const long long ta0 = prof ? clock64() : 0;
         if (!mbar_wait(&acc_empty[buf], aph ^ 1u, P.err, 4)) { ok = false; break; }   // epilogue drained this buffer
+        if (prof) t_wacc += clock64() - ta0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * P.n_tile);
         for (int it = 0; it < iters; ++it, ++git) {
           const int s = git % P.stages;
           const uint32_t ph = (git / P.stages) & 1u;
+          const long long tw0 = prof ? clock64() : 0;
           if (!mbar_wait(&full_bar[s], ph, P.err, 2)) { ok = false; break; }
+          if (prof) t_wait += clock64() - tw0;
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t sb = sa + kABytes;
@@ -266,6 +279,10 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           umma_commit(&empty_bar[s]);
         }
         if (ok) umma_commit(&acc_full[buf]);
+      }
+      if (prof) {
+        atomicAdd(P.dbg + 2, (unsigned long long)t_wait); atomicAdd(P.dbg + 3, (unsigned long long)(clock64() - t_begin));
+        atomicAdd(P.dbg + 6, (unsigned long long)t_wacc); atomicAdd(P.dbg + 5, 1ull);
       }
     }
   } else {
@@ -304,6 +321,7 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ok = mbar_wait(&acc_full[buf], aph, P.err, 3);
       if (!ok) break;
       tc_fence_after();
+      const long long te0 = (P.debug & 2) ? clock64() : 0;
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * P.n_tile);
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -349,6 +367,7 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      if ((P.debug & 2) && threadIdx.x == 64) atomicAdd(P.dbg + 4, (unsigned long long)(clock64() - te0));
     }
     if (P.stats) flush_stats();
   }
@@ -799,6 +818,8 @@ inline int run_gather_tc(const GatherPlan& plan, const GatherRun& R, cudaStream_
     P.out = R.out; P.out_bf16 = R.out_bf16;
     P.bias = R.bias; P.act = R.act; P.slope = R.slope;
     P.stats = R.stats; P.err = err;
+    { const char* e = getenv("MRA_GATHER_DEBUG"); P.debug = e ? atoi(e) : 0; }
+    P.dbg = tc_dbg_counters();
     for (int i = 0; i < P.ntaps; ++i) {
       MRA_REQUIRE(L.taps[i].dd >= -128 && L.taps[i].dd < 128 && L.taps[i].widx < R.slabs, "tap out of range");
       P.tdd[i] = (int8_t)L.taps[i].dd; P.tdh[i] = (int8_t)L.taps[i].dh; P.tdw[i] = (int8_t)L.taps[i].dw;
