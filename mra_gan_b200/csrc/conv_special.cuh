@@ -19,7 +19,7 @@
 #pragma once
 #include "common.cuh"
 #include "conv_plan.h"
-#include "conv_tc.cuh"
+#include "conv_tc_halo.cuh"
 
 namespace mra {
 namespace special {

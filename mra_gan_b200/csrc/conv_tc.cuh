@@ -53,6 +53,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
+// non-blocking probe of a phase (never suspends the thread): used to "peek" at the next stage's barrier so that
+// the probe's latency overlaps the MMA issue of the current stage
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
 // bounded wait: returns false (and raises the error flag) instead of hanging
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
   for (uint32_t it = 0; it < (1u << 24); ++it)
@@ -229,20 +240,23 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       bool ok = true;
       const bool prof = (P.debug & 2) != 0;
       long long t_wait = 0, t_begin = prof ? clock64() : 0;
+      int s = 0;
+      uint32_t ph = 0;
+      (void)git;
       for (int tile = blockIdx.x; tile < P.total_tiles && ok; tile += gridDim.x) {
         const TileCoord t = decode_tile(P, tile);
-        for (int it = 0; it < iters; ++it, ++git) {
-          const int s = git % P.stages;
-          const uint32_t ph = (git / P.stages) & 1u;
+        int tap = 0, kc = 0;
+        for (int it = 0; it < iters; ++it) {
           const long long tw0 = prof ? clock64() : 0;
           if (!mbar_wait(&empty_bar[s], ph ^ 1u, P.err, 1)) { ok = false; break; }
           if (prof) t_wait += clock64() - tw0;
-          const int tap = it / P.kchunks, kc = it - tap * P.kchunks;
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           mbar_expect_tx(&full_bar[s], stage_bytes);
           tma_load_5d(sa, &tmA, &full_bar[s], kc * 64, t.lw0 * P.astep + P.tdw[tap], t.lh0 * P.astep + P.tdh[tap],
                       t.ld0 * P.astep + P.tdd[tap], t.n);
           tma_load_2d(sa + kABytes, &tmB, &full_bar[s], kc * 64, (int)P.twi[tap] * P.Cn + t.n0);
+          if (++s == P.stages) { s = 0; ph ^= 1u; }
+          if (++kc == P.kchunks) { kc = 0; ++tap; }
         }
       }
       if (prof) { atomicAdd(P.dbg + 0, (unsigned long long)t_wait); atomicAdd(P.dbg + 1, (unsigned long long)(clock64() - t_begin)); }
@@ -250,7 +264,10 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc(P.n_tile, 0, 0);
-      uint32_t git = 0;
+      const uint64_t desc0 = desc_kmajor_sw128(0);
+      const uint32_t smem_u = smem_u32(smem) >> 4, stage_u = stage_bytes >> 4;
+      int s = 0;
+      uint32_t ph = 0;
       bool ok = true;
       int j = 0;
       const bool prof = (P.debug & 2) != 0;
@@ -263,20 +280,21 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (prof) t_wacc += clock64() - ta0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * P.n_tile);
-        for (int it = 0; it < iters; ++it, ++git) {
-          const int s = git % P.stages;
-          const uint32_t ph = (git / P.stages) & 1u;
+        // single issuing thread: no divisions, descriptors advance by constants (16-byte units)
+        for (int it = 0; it < iters; ++it) {
           const long long tw0 = prof ? clock64() : 0;
           if (!mbar_wait(&full_bar[s], ph, P.err, 2)) { ok = false; break; }
           if (prof) t_wait += clock64() - tw0;
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t sb = sa + kABytes;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16(d_tmem, desc_kmajor_sw128(sa + k * 32), desc_kmajor_sw128(sb + k * 32), idesc,
-                     (uint32_t)((it | k) != 0));
+          const uint32_t sa_u = smem_u + (uint32_t)s * stage_u;
+          const uint64_t ad = desc0 | (uint64_t)(sa_u & 0x3FFFu);
+          const uint64_t bd = desc0 | (uint64_t)((sa_u + (kABytes >> 4)) & 0x3FFFu);
+          umma_f16(d_tmem, ad, bd, idesc, (uint32_t)(it != 0));
+          umma_f16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+          umma_f16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+          umma_f16(d_tmem, ad + 6, bd + 6, idesc, 1u);
           umma_commit(&empty_bar[s]);
+          if (++s == P.stages) { s = 0; ph ^= 1u; }
         }
         if (ok) umma_commit(&acc_full[buf]);
       }
@@ -524,7 +542,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
     // ---- TMA producer: lane j issues box j of every stage (box 0..m_chunks-1 dense, then the shifted boxes)
     WSegIter it; WSeg sg;
     wseg_begin(P, kblocks, it);
-    uint32_t git = 0;
+    int s = 0;
+    uint32_t ph = 0;
     long long t_wait = 0, t_begin = prof ? clock64() : 0;
     bool ok = true;
     while (ok && wseg_next(P, kblocks, it, sg)) {
@@ -554,9 +573,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
       int tw = r % P.tilesW; r /= P.tilesW;
       int th = r % P.tilesH;
       int td = r / P.tilesH;
-      for (int kb = sg.kb0; kb < sg.kb1; ++kb, ++git) {
-        const int s = git % P.stages;
-        const uint32_t ph = (git / P.stages) & 1u;
+      for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
         const long long tw0 = prof ? clock64() : 0;
         if (!mbar_wait(&empty_bar[s], ph ^ 1u, P.err, 11)) { ok = false; break; }
         if (prof) t_wait += clock64() - tw0;
@@ -566,15 +583,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
           tma_load_5d(smem + (size_t)s * stage_bytes + soff, tm, &full_bar[s], c0, tw * P.bw * step + ow,
                       th * P.bh * step + oh, td * P.bd * step + od, n);
         if (++tw == P.tilesW) { tw = 0; if (++th == P.tilesH) { th = 0; if (++td == P.tilesD) { td = 0; ++n; } } }
+        if (++s == P.stages) { s = 0; ph ^= 1u; }
       }
     }
     if (prof && lane == 0) { atomicAdd(P.dbg + 0, (unsigned long long)t_wait); atomicAdd(P.dbg + 1, (unsigned long long)(clock64() - t_begin)); }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(P.ncc * 64, 1, 1);
       WSegIter it; WSeg sg;
       wseg_begin(P, kblocks, it);
-      uint32_t git = 0;
+      const uint32_t smem_u = smem_u32(smem) >> 4, stage_u = stage_bytes >> 4;
+      int s = 0;
+      uint32_t ph = 0;
       int nseg = 0;
       bool ok = true;
       long long t_wait = 0, t_begin = prof ? clock64() : 0;
@@ -592,30 +611,45 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
           if (!mbar_wait(acc_empty, (uint32_t)(nseg - 1) & 1u, P.err, 15)) { ok = false; break; }
           tc_fence_after();
         }
-        for (int kb = sg.kb0; kb < sg.kb1; ++kb, ++git) {
-          const int s = git % P.stages;
-          const uint32_t ph = (git / P.stages) & 1u;
+        // Per-segment table of the MMAs of one K-block: everything that does not depend on the stage is folded
+        // into constants (descriptor offsets in 16-byte units), so the per-stage loop of this single issuing
+        // thread is a wait, a handful of adds and the MMAs.
+        const int tpm = G.share == 1 ? (P.ncc >= 4 ? 1 : 4 / P.ncc) : 1;     // taps per MMA (unshared boxes sit back to back)
+        uint32_t m_boff[8], m_dcol[8], m_idesc[8];
+        const int nmma = (sg.ntap + tpm - 1) / tpm;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int g = i * tpm;
+          const int nt = max(1, min(tpm, sg.ntap - g));
+          const int gi = min(g, sg.ntap - 1);
+          m_boff[i] = (m_bytes + (uint32_t)(gi / G.share) * set_bytes + (uint32_t)P.rshift[sg.tap0 + gi] * 128u) >> 4;
+          m_dcol[i] = (uint32_t)(gi * P.ncc * 64);
+          m_idesc[i] = make_idesc(nt * P.ncc * 64, 1, 1);
+        }
+        const uint64_t a_desc0 = desc_mnmajor_sw128(0, kChunkBytes);
+        const uint64_t b_desc0 = desc_mnmajor_sw128(0, (uint32_t)P.box_bytes);
+        const uint32_t rm0 = rowmap[0] * 8u, rm1 = rowmap[1] * 8u, rm2 = rowmap[2] * 8u, rm3 = rowmap[3] * 8u;
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
           const long long tw0 = prof ? clock64() : 0;
           if (!mbar_wait(&full_bar[s], ph, P.err, 12)) { ok = false; break; }
           if (prof) t_wait += clock64() - tw0;
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t sb = sa + m_bytes;
-          // taps that own their boxes (share == 1) sit back to back in the stage: up to 256 accumulator
-          // columns (4 / ncc taps) go into ONE MMA, the chunk stride (LBO) being the box slot size
-          const int tpm = G.share == 1 ? (P.ncc >= 4 ? 1 : 4 / P.ncc) : 1;
-          for (int g = 0; g < sg.ntap; g += tpm) {
-            const int nt = min(tpm, sg.ntap - g);
-            const uint32_t bset = sb + (uint32_t)(g / G.share) * set_bytes + (uint32_t)P.rshift[sg.tap0 + g] * 128u;
-            const uint32_t d_tmem = tmem_base + (uint32_t)(g * P.ncc * 64);
-            const uint32_t id = nt == 1 ? idesc : make_idesc(nt * P.ncc * 64, 1, 1);
+          const uint32_t sa_u = smem_u + (uint32_t)s * stage_u;
+          const uint64_t ad = a_desc0 | (uint64_t)(sa_u & 0x3FFFu);
+          const uint32_t accf = (uint32_t)(kb != sg.kb0);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)      // 16 positions (rows of 128 B) per MMA
-              umma_f16(d_tmem, desc_mnmajor_sw128(sa + k * 2048, kChunkBytes),
-                       desc_mnmajor_sw128(bset + rowmap[k] * 128u, (uint32_t)P.box_bytes), id,
-                       (uint32_t)((kb != sg.kb0) | (k != 0)));
+          for (int i = 0; i < 8; ++i) {
+            if (i >= nmma) break;
+            const uint32_t d_tmem = tmem_base + m_dcol[i];
+            const uint32_t bu = sa_u + m_boff[i];
+            const uint32_t id = m_idesc[i];
+            umma_f16(d_tmem, ad, b_desc0 | (uint64_t)((bu + rm0) & 0x3FFFu), id, accf);
+            umma_f16(d_tmem, ad + 128, b_desc0 | (uint64_t)((bu + rm1) & 0x3FFFu), id, 1u);
+            umma_f16(d_tmem, ad + 256, b_desc0 | (uint64_t)((bu + rm2) & 0x3FFFu), id, 1u);
+            umma_f16(d_tmem, ad + 384, b_desc0 | (uint64_t)((bu + rm3) & 0x3FFFu), id, 1u);
           }
           umma_commit(&empty_bar[s]);
+          if (++s == P.stages) { s = 0; ph ^= 1u; }
         }
         if (ok) umma_commit(acc_full);
         ++nseg;
@@ -785,69 +819,54 @@ struct GatherRun {
   double* stats;
 };
 
-// Run every launch of a gather plan on the tensor cores.
-inline int run_gather_tc(const GatherPlan& plan, const GatherRun& R, cudaStream_t st) {
-  int* err = tc_err_flag();
-  const int n_tile = pick_n_tile(plan.cn);
-  MRA_REQUIRE(n_tile > 0 && plan.ck % 64 == 0, "channel counts not eligible for the tensor-core path");
-  const long long rows = (long long)R.slabs * plan.cn;
-  CUtensorMap tmB;
-  if (int rc = make_weight_map(&tmB, R.b, rows, plan.ck, n_tile)) return rc;
+// One launch of a gather plan on gather_tc_kernel (one TMA box per filter tap).
+inline int run_gather_v1_launch(const GatherPlan& plan, const GatherLaunch& L, const GatherRun& R, const CUtensorMap& tmB,
+                                int n_tile, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
     attr_set = true;
   }
-  for (const GatherLaunch& L : plan.launches) {
-    MRA_REQUIRE((int)L.taps.size() <= kMaxTaps, "too many taps for the tensor-core path");
-    GatherP P;
-    memset(&P, 0, sizeof(P));
-    P.bd = L.box[0]; P.bh = L.box[1]; P.bw = L.box[2];
-    P.Dl = L.dims[0]; P.Hl = L.dims[1]; P.Wl = L.dims[2];
-    P.tilesD = (P.Dl + P.bd - 1) / P.bd; P.tilesH = (P.Hl + P.bh - 1) / P.bh; P.tilesW = (P.Wl + P.bw - 1) / P.bw;
-    P.astep = L.astep;
-    P.Cn = plan.cn; P.n_tile = n_tile; P.n_tiles = plan.cn / n_tile; P.kchunks = plan.ck / 64; P.ntaps = (int)L.taps.size();
-    const long long total_tiles = (long long)plan.n * P.tilesD * P.tilesH * P.tilesW * P.n_tiles;
-    MRA_REQUIRE(total_tiles < (1ll << 31), "too many tiles");
-    P.total_tiles = (int)total_tiles;
-    P.ostep = L.ostep; P.od0 = L.o0[0]; P.oh0 = L.o0[1]; P.ow0 = L.o0[2];
-    P.osw = plan.cn;
-    P.osh = (long long)plan.odims[2] * P.osw;
-    P.osd = (long long)plan.odims[1] * P.osh;
-    P.osn = (long long)plan.odims[0] * P.osd;
-    P.out = R.out; P.out_bf16 = R.out_bf16;
-    P.bias = R.bias; P.act = R.act; P.slope = R.slope;
-    P.stats = R.stats; P.err = err;
-    { const char* e = getenv("MRA_GATHER_DEBUG"); P.debug = e ? atoi(e) : 0; }
-    P.dbg = tc_dbg_counters();
-    for (int i = 0; i < P.ntaps; ++i) {
-      MRA_REQUIRE(L.taps[i].dd >= -128 && L.taps[i].dd < 128 && L.taps[i].widx < R.slabs, "tap out of range");
-      P.tdd[i] = (int8_t)L.taps[i].dd; P.tdh[i] = (int8_t)L.taps[i].dh; P.tdw[i] = (int8_t)L.taps[i].dw;
-      P.twi[i] = (int16_t)L.taps[i].widx;
-    }
-    const size_t stage_bytes = kABytes + (size_t)n_tile * 128;
-    int stages = (int)((kSmemLimit - 2048) / stage_bytes);
-    if (stages > 6) stages = 6;
-    P.stages = stages;
-    P.tmem_cols = pow2_cols(2 * n_tile);
-    const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
-    CUtensorMap tmA;
-    if (int rc = make_act_map(&tmA, R.a, plan.n, plan.adims[0], plan.adims[1], plan.adims[2], plan.ck, P.bw, P.bh, P.bd,
-                              P.astep))
-      return rc;
-    const int ctas = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
-    gather_tc_kernel<<<ctas, kThreads, smem, st>>>(tmA, tmB, P);
-    MRA_LAUNCH_CHECK();
+  MRA_REQUIRE((int)L.taps.size() <= kMaxTaps, "too many taps for the tensor-core path");
+  GatherP P;
+  memset(&P, 0, sizeof(P));
+  P.bd = L.box[0]; P.bh = L.box[1]; P.bw = L.box[2];
+  P.Dl = L.dims[0]; P.Hl = L.dims[1]; P.Wl = L.dims[2];
+  P.tilesD = (P.Dl + P.bd - 1) / P.bd; P.tilesH = (P.Hl + P.bh - 1) / P.bh; P.tilesW = (P.Wl + P.bw - 1) / P.bw;
+  P.astep = L.astep;
+  P.Cn = plan.cn; P.n_tile = n_tile; P.n_tiles = plan.cn / n_tile; P.kchunks = plan.ck / 64; P.ntaps = (int)L.taps.size();
+  const long long total_tiles = (long long)plan.n * P.tilesD * P.tilesH * P.tilesW * P.n_tiles;
+  MRA_REQUIRE(total_tiles < (1ll << 31), "too many tiles");
+  P.total_tiles = (int)total_tiles;
+  P.ostep = L.ostep; P.od0 = L.o0[0]; P.oh0 = L.o0[1]; P.ow0 = L.o0[2];
+  P.osw = plan.cn;
+  P.osh = (long long)plan.odims[2] * P.osw;
+  P.osd = (long long)plan.odims[1] * P.osh;
+  P.osn = (long long)plan.odims[0] * P.osd;
+  P.out = R.out; P.out_bf16 = R.out_bf16;
+  P.bias = R.bias; P.act = R.act; P.slope = R.slope;
+  P.stats = R.stats; P.err = tc_err_flag();
+  { const char* e = getenv("MRA_GATHER_DEBUG"); P.debug = e ? atoi(e) : 0; }
+  P.dbg = tc_dbg_counters();
+  for (int i = 0; i < P.ntaps; ++i) {
+    MRA_REQUIRE(L.taps[i].dd >= -128 && L.taps[i].dd < 128 && L.taps[i].widx < R.slabs, "tap out of range");
+    P.tdd[i] = (int8_t)L.taps[i].dd; P.tdh[i] = (int8_t)L.taps[i].dh; P.tdw[i] = (int8_t)L.taps[i].dw;
+    P.twi[i] = (int16_t)L.taps[i].widx;
   }
+  const size_t stage_bytes = kABytes + (size_t)n_tile * 128;
+  int stages = (int)((kSmemLimit - 2048) / stage_bytes);
+  if (stages > 6) stages = 6;
+  P.stages = stages;
+  P.tmem_cols = pow2_cols(2 * n_tile);
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  CUtensorMap tmA;
+  if (int rc = make_act_map(&tmA, R.a, plan.n, plan.adims[0], plan.adims[1], plan.adims[2], plan.ck, P.bw, P.bh, P.bd,
+                            P.astep))
+    return rc;
+  const int ctas = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
+  gather_tc_kernel<<<ctas, kThreads, smem, st>>>(tmA, tmB, P);
+  MRA_LAUNCH_CHECK();
   return 0;
-}
-
-inline int run_gather_tc(const mra_conv_desc& d, int which, const void* a, const void* b, const float* bias, void* out,
-                         double* stats, cudaStream_t st) {
-  GatherPlan plan;
-  MRA_REQUIRE(build_gather_plan(d, which, plan), "unsupported conv geometry");
-  GatherRun R{a, b, d.k * d.k * d.k, bias, out, 1, which == 0 ? d.act : MRA_ACT_NONE, d.slope, stats};
-  return run_gather_tc(plan, R, st);
 }
 
 inline int run_wgrad_tc(const WgradPlan& plan, const void* x, const void* dy, float* dw, cudaStream_t st) {

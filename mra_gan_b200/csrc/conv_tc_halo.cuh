@@ -1,0 +1,583 @@
+// Halo-plane implicit-GEMM gather kernel (stride-1 launches of conv_plan.h's GATHER computation).
+//
+// gather_tc_kernel (conv_tc.cuh) loads one 128-row A tile per filter tap: 27 loads of nearly the same
+// input voxels for a 3x3x3 filter.  A convolution can do better than a GEMM here: all (kh, kw) taps of one
+// input d-plane read shifted windows of ONE halo tile.  This kernel keeps that halo tile (a "plane": the
+// (Hb x Wb) input rows under a 128-position output tile, 64 channels wide) in shared memory and feeds every
+// tap from it by moving the UMMA descriptor's start address (row shift) -- the SWIZZLE_128B pattern is a
+// function of the absolute shared-memory address, so row-shifted starts and a non-1024-byte group stride
+// are legal (verified on B200 by tools/halo_probe.cu).  A traffic drops by ~kh*kw/1.4 (k3: 6.4x); only the
+// weights (B) are still streamed per tap.
+//
+// Output tile (M = 128 positions of one launch-space d-plane) in one of two shapes:
+//   2D   : 16 h x 8 w.  MMA row m = (h, w) = (m / 8, m % 8); the 8-row groups are Wb = 8 + kw - 1 plane rows
+//          apart (descriptor SBO = Wb * 128 B).  No wasted rows when H % 16 == 0 and W % 8 == 0.
+//   flat : 128 consecutive positions f of the plane flattened with pitch Wb = W + kw - 1 (SBO = 1024 B as in a
+//          dense tile); the kw - 1 positions per line that wrap around are computed and discarded.  Used when
+//          the 2D shape would waste more (e.g. the 34^3 dgrad of the residual blocks: 90 % vs 60 % useful rows).
+//
+// Warp roles: 0 = TMA producer of the weight ring, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue,
+// 6 = TMA producer of the plane ring.  Persistent over tiles, accumulators double-buffered in TMEM.
+#pragma once
+#include "conv_tc.cuh"
+
+namespace mra {
+namespace tc {
+
+constexpr int kThreadsHalo = 224;
+
+struct HaloP {
+  int Dl, Hl, Wl;                   // launch-space (output) dims
+  int N;
+  int mode;                         // 0 = 2D tile (16 x 8), 1 = flat
+  int tiles_hw, tiles_w;            // tiles per d-plane; 2D: tiles along w
+  int Wb, Hb;                       // plane box extents in w / h (rows = Wb * Hb)
+  int sbo;                          // descriptor stride between 8-row groups, bytes
+  int slot_bytes, plane_tx;         // shared-memory slot / bytes delivered per plane
+  int NP, NB;                       // plane ring / weight ring depth
+  int kd, kh, kw;                   // tap box extents (taps ordered td, th, tw)
+  int dmin, hmin, wmin;             // smallest tap offsets
+  int Cn, n_tile, n_tiles, kchunks;
+  int total_tiles;
+  int ostep, od0, oh0, ow0;
+  long long osn, osd, osh, osw;     // output strides in elements
+  void* out;
+  int out_bf16;
+  const float* bias;
+  int act;
+  float slope;
+  double* stats;
+  int* err;
+  uint32_t tmem_cols;
+  int16_t twi[kMaxTaps];            // weight slab of tap (td, th, tw)
+  int debug;
+  unsigned long long* dbg;
+  int pair;                         // 1: cta_group::2 pairs (host-side choice of the kernel instantiation)
+};
+
+__device__ __forceinline__ uint64_t desc_kmajor_sw128_sbo(uint32_t saddr, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+
+struct HaloTile { int n, d, n0, h0, w0, f0, hs, roff; };
+// work index -> coordinates.  Order: n_tile fastest, then the tiles of a plane, then d (pair mode: pairs of
+// planes, CTA rank r takes d = 2 * dp + r so both tiles share the weight slab and the in-plane geometry), then n.
+__device__ __forceinline__ HaloTile halo_decode(const HaloP& P, int tile, int pair, int rank) {
+  HaloTile t;
+  const int nt = tile % P.n_tiles; tile /= P.n_tiles;
+  const int j = tile % P.tiles_hw; tile /= P.tiles_hw;
+  const int dsteps = pair ? (P.Dl + 1) / 2 : P.Dl;
+  const int dq = tile % dsteps;
+  t.d = pair ? 2 * dq + rank : dq;            // may be == Dl for the odd plane's partner: loads hit zero fill, nothing is stored
+  t.n = tile / dsteps;
+  t.n0 = nt * P.n_tile;
+  if (P.mode == 0) {
+    t.h0 = (j / P.tiles_w) * 16; t.w0 = (j % P.tiles_w) * 8;
+    t.f0 = 0; t.hs = t.h0; t.roff = 0;
+  } else {
+    t.f0 = j * 128; t.hs = t.f0 / P.Wb; t.roff = t.f0 - t.hs * P.Wb;
+    t.h0 = 0; t.w0 = 0;
+  }
+  return t;
+}
+
+// ---- cta_group::2 (CTA pair) flavours of the PTX wrappers.  In pair mode two CTAs of a cluster (one TPC) each
+// own a 128-row tile and HALF of the weight slab; the leader (cluster rank 0) issues one M = 256 MMA for both,
+// so every CTA streams only half of the weights from L2.  TMA loads of both CTAs signal the LEADER's barrier
+// (peer bit 24 of the shared::cluster address cleared), tcgen05.commit multicasts to both CTAs' barriers.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <bool kPair>
+__device__ __forceinline__ void tma_load_5d_g(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                              int c4) {
+  if constexpr (kPair) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+  } else {
+    tma_load_5d(dst, tm, bar, c0, c1, c2, c3, c4);
+  }
+}
+template <bool kPair>
+__device__ __forceinline__ void tma_load_2d_g(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  if constexpr (kPair) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+  } else {
+    tma_load_2d(dst, tm, bar, c0, c1);
+  }
+}
+template <bool kPair>
+__device__ __forceinline__ void umma_commit_g(uint64_t* bar) {
+  if constexpr (kPair) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+  } else {
+    umma_commit(bar);
+  }
+}
+template <bool kPair>
+__device__ __forceinline__ void umma_f16_g(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kPair) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    umma_f16(d_tmem, adesc, bdesc, idesc, accumulate);
+  }
+}
+// arrive on the barrier at the same offset in the pair's leader CTA
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_m(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <bool kPair>
+__global__ void __launch_bounds__(kThreadsHalo, 1)
+gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ HaloP P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kCtas = kPair ? 2 : 1;
+  const uint32_t b_rows = (uint32_t)P.n_tile / kCtas;            // weight rows this CTA holds (pair: half the slab)
+  const uint32_t b_bytes = b_rows * 128u;
+  uint8_t* planes = smem;
+  uint8_t* bring = smem + (size_t)P.NP * P.slot_bytes;
+  uint64_t* p_full = reinterpret_cast<uint64_t*>(bring + (size_t)P.NB * b_bytes);
+  uint64_t* p_empty = p_full + P.NP;
+  uint64_t* b_full = p_empty + P.NP;
+  uint64_t* b_empty = b_full + P.NB;
+  uint64_t* acc_full = b_empty + P.NB;           // [2]
+  uint64_t* acc_empty = acc_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = kPair ? (int)cluster_ctarank() : 0;
+  const bool leader = rank == 0;
+  const int work0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int wstride = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int taps_hw = P.kh * P.kw;
+  const bool prof = (P.debug & 2) != 0;
+  // Every CTA walks the (channel chunk, td) planes and the (th, tw) taps of a plane in its own ROTATED order
+  // (the sum over taps is order-free): at any moment the SMs then stream different weight slabs, instead of
+  // all 148 hammering the same 32 KB of L2 at once.
+  const int nplanes = P.kchunks * P.kd;
+  const int rot_p = work0 % nplanes;
+  const int rot_t = (work0 / nplanes) % taps_hw;
+  const int rot_kc0 = rot_p / P.kd, rot_td0 = rot_p - rot_kc0 * P.kd;
+  const int rot_th0 = rot_t / P.kw, rot_tw0 = rot_t - rot_th0 * P.kw;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < P.NP; ++s) { mbar_init(&p_full[s], 1); mbar_init(&p_empty[s], 1); }
+    for (int s = 0; s < P.NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4 * kCtas); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    if constexpr (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(P.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      tmem_alloc(tmem_slot, P.tmem_cols);
+    }
+  }
+  tc_fence_before();
+  if constexpr (kPair) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const bool dbg_nob = (P.debug & 4) != 0, dbg_nop = (P.debug & 8) != 0;     // timing experiments: no weight / plane traffic
+  if (warp == 6) {
+    // ---- plane producer: one halo plane per (work item, channel chunk, td); each CTA loads its own tile's planes
+    if (lane == 0 && !dbg_nop) {
+      int s = 0;
+      uint32_t ph = 0;
+      bool ok = true;
+      for (int w = work0; w < P.total_tiles && ok; w += wstride) {
+        const HaloTile t = halo_decode(P, w, kPair, rank);
+        int kc = rot_kc0, td = rot_td0;
+        for (int pi = 0; pi < nplanes; ++pi) {
+          if (!mbar_wait(&p_empty[s], ph ^ 1u, P.err, 21)) { ok = false; break; }
+          if (leader) mbar_expect_tx(&p_full[s], (uint32_t)P.plane_tx * kCtas);
+          tma_load_5d_g<kPair>(planes + (size_t)s * P.slot_bytes, &tmA, &p_full[s], kc * 64, t.w0 + P.wmin, t.hs + P.hmin,
+                               t.d + P.dmin + td, t.n);
+          if (++s == P.NP) { s = 0; ph ^= 1u; }
+          if (++td == P.kd) { td = 0; if (++kc == P.kchunks) kc = 0; }
+        }
+      }
+    }
+  } else if (warp == 0) {
+    // ---- weight producer: one (64 x n_tile) slab per (work item, channel chunk, tap); pair: each CTA its half
+    if (lane == 0 && !dbg_nob) {
+      int s = 0;
+      uint32_t ph = 0;
+      bool ok = true;
+      long long t_wait = 0, t_begin = prof ? clock64() : 0;
+      for (int w = work0; w < P.total_tiles && ok; w += wstride) {
+        const int n0 = (w % P.n_tiles) * P.n_tile + rank * (int)b_rows;
+        int kc = rot_kc0, td = rot_td0;
+        for (int pi = 0; pi < nplanes && ok; ++pi) {
+          int tap = rot_t;                                   // (th, tw) index inside the plane, rotated start
+          for (int i = 0; i < taps_hw; ++i) {
+            const long long tw0 = prof ? clock64() : 0;
+            if (!mbar_wait(&b_empty[s], ph ^ 1u, P.err, 22)) { ok = false; break; }
+            if (prof) t_wait += clock64() - tw0;
+            if (leader) mbar_expect_tx(&b_full[s], b_bytes * kCtas);
+            tma_load_2d_g<kPair>(bring + (size_t)s * b_bytes, &tmB, &b_full[s], kc * 64,
+                                 (int)P.twi[td * taps_hw + tap] * P.Cn + n0);
+            if (++s == P.NB) { s = 0; ph ^= 1u; }
+            if (++tap == taps_hw) tap = 0;
+          }
+          if (++td == P.kd) { td = 0; if (++kc == P.kchunks) kc = 0; }
+        }
+      }
+      if (prof) { atomicAdd(P.dbg + 0, (unsigned long long)t_wait); atomicAdd(P.dbg + 1, (unsigned long long)(clock64() - t_begin)); }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // The issue loop is a single thread: keep it to a few dozen instructions per stage (no divisions, the
+      // descriptors advance by adding constants to their 16-byte-unit address field).
+      const uint32_t idesc = make_idesc_m(128 * kCtas, P.n_tile);
+      const uint64_t a_desc0 = desc_kmajor_sw128_sbo(0, (uint32_t)P.sbo);      // address field filled per plane
+      const uint64_t b_desc0 = desc_kmajor_sw128(0);
+      const uint32_t planes_u = smem_u32(planes) >> 4, bring_u = smem_u32(bring) >> 4;
+      const uint32_t slot_u = (uint32_t)P.slot_bytes >> 4, bst_u = b_bytes >> 4;
+      const uint32_t row_u = 128u >> 4;                                        // one plane row, in 16-byte units
+      const int kh = P.kh, kw = P.kw, NP = P.NP, NB = P.NB;
+      const uint32_t line_step = (uint32_t)(P.Wb - (kw - 1)) * row_u;          // from the last tap of a line to the next line's first
+      const uint32_t rot_a_u = (uint32_t)(rot_th0 * P.Wb + rot_tw0) * row_u;
+      int ps = 0, bs = 0;
+      uint32_t pph = 0, bph = 0;
+      bool ok = true, b_ready = false;
+      int j = 0;
+      long long t_wait = 0, t_waitp = 0, t_wacc = 0, t_begin = prof ? clock64() : 0;
+      for (int w = work0; w < P.total_tiles && ok; w += wstride, ++j) {
+        const int buf = j & 1;
+        const uint32_t aph = ((uint32_t)j >> 1) & 1u;
+        uint32_t roff_u = 0;
+        if (P.mode != 0) {                                     // flat tiles start inside their first plane line
+          const int f0 = ((w / P.n_tiles) % P.tiles_hw) * 128;
+          roff_u = (uint32_t)(f0 % P.Wb) * row_u;
+        }
+        const long long ta0 = prof ? clock64() : 0;
+        if (!mbar_wait(&acc_empty[buf], aph ^ 1u, P.err, 24)) { ok = false; break; }
+        if (prof) t_wacc += clock64() - ta0;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * P.n_tile);
+        uint32_t acc = 0;
+        for (int pi = 0; pi < nplanes && ok; ++pi) {
+          const long long tp0 = prof ? clock64() : 0;
+          if (!dbg_nop && !mbar_wait(&p_full[ps], pph, P.err, 25)) { ok = false; break; }
+          if (prof) t_waitp += clock64() - tp0;
+          const uint32_t base_u = planes_u + (uint32_t)ps * slot_u + roff_u;
+          uint32_t a_u = base_u + rot_a_u;
+          int th = rot_th0, tw = rot_tw0;
+          for (int i = 0; i < taps_hw; ++i) {
+            const long long tw0 = prof ? clock64() : 0;
+            if (!b_ready && !dbg_nob && !mbar_wait(&b_full[bs], bph, P.err, 26)) { ok = false; break; }
+            if (prof) t_wait += clock64() - tw0;
+            tc_fence_after();
+            const uint64_t ad = a_desc0 | (uint64_t)(a_u & 0x3FFFu);
+            const uint64_t bd = b_desc0 | (uint64_t)((bring_u + (uint32_t)bs * bst_u) & 0x3FFFu);
+            uint64_t* done_bar = &b_empty[bs];
+            if (++bs == NB) { bs = 0; bph ^= 1u; }
+            b_ready = mbar_test_wait(&b_full[bs], bph);          // peek at the next stage while this one is issued
+            umma_f16_g<kPair>(d_tmem, ad, bd, idesc, acc);
+            umma_f16_g<kPair>(d_tmem, ad + 2, bd + 2, idesc, 1u);
+            umma_f16_g<kPair>(d_tmem, ad + 4, bd + 4, idesc, 1u);
+            umma_f16_g<kPair>(d_tmem, ad + 6, bd + 6, idesc, 1u);
+            acc = 1u;
+            umma_commit_g<kPair>(done_bar);
+            if (++tw == kw) {
+              tw = 0;
+              if (++th == kh) { th = 0; a_u = base_u; } else a_u += line_step;
+            } else {
+              a_u += row_u;
+            }
+          }
+          if (ok) umma_commit_g<kPair>(&p_empty[ps]);
+          if (++ps == NP) { ps = 0; pph ^= 1u; }
+        }
+        if (ok) umma_commit_g<kPair>(&acc_full[buf]);
+      }
+      if (prof) {
+        atomicAdd(P.dbg + 2, (unsigned long long)t_wait); atomicAdd(P.dbg + 3, (unsigned long long)(clock64() - t_begin));
+        atomicAdd(P.dbg + 6, (unsigned long long)t_wacc); atomicAdd(P.dbg + 7, (unsigned long long)t_waitp);
+        atomicAdd(P.dbg + 5, 1ull);
+      }
+    }
+  } else {
+    // ---- epilogue warps 2..5 -> TMEM lane quadrant (warp % 4)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int nchunks = P.n_tile / 32;
+    double st_s[8], st_q[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { st_s[c] = 0.0; st_q[c] = 0.0; }
+    int st_n = -1, st_n0 = 0;
+    auto flush_stats = [&]() {
+      if (st_n >= 0) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c < nchunks) {
+            double* st = P.stats + ((long long)st_n * P.Cn + st_n0 + c * 32 + lane) * 2;
+            atomicAdd(st, st_s[c]);
+            atomicAdd(st + 1, st_q[c]);
+            st_s[c] = 0.0; st_q[c] = 0.0;
+          }
+      }
+    };
+    int j = 0;
+    bool ok = true;
+    for (int w = work0; w < P.total_tiles && ok; w += wstride, ++j) {
+      const HaloTile t = halo_decode(P, w, kPair, rank);
+      const int buf = j & 1;
+      const uint32_t aph = ((uint32_t)j >> 1) & 1u;
+      int lh, lw;
+      if (P.mode == 0) { lh = t.h0 + (row >> 3); lw = t.w0 + (row & 7); }
+      else { const int f = t.roff + row; const int hh = f / P.Wb; lh = t.hs + hh; lw = f - hh * P.Wb; }
+      const bool valid = lw < P.Wl && lh < P.Hl && t.d < P.Dl;
+      const long long obase = (long long)t.n * P.osn + (long long)(t.d * P.ostep + P.od0) * P.osd +
+                              (long long)(lh * P.ostep + P.oh0) * P.osh + (long long)(lw * P.ostep + P.ow0) * P.osw + t.n0;
+      if (P.stats && (t.n != st_n || t.n0 != st_n0)) { flush_stats(); st_n = t.n; st_n0 = t.n0; }
+      ok = mbar_wait(&acc_full[buf], aph, P.err, 23);
+      if (!ok) break;
+      tc_fence_after();
+      const long long te0 = prof ? clock64() : 0;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * P.n_tile);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (c >= nchunks) break;
+        const int c0 = c * 32;
+        uint32_t r[32];
+        tmem_ld32(t_addr + (uint32_t)c0, r);
+        tmem_wait_ld();
+        if (c == nchunks - 1) {                 // accumulator fully read: hand the buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { if constexpr (kPair) mbar_arrive_leader(&acc_empty[buf]); else mbar_arrive(&acc_empty[buf]); }
+        }
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if (P.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += __ldg(P.bias + t.n0 + c0 + i);
+        }
+        if (P.stats) {
+          float s1[32], s2[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { s1[i] = valid ? v[i] : 0.f; s2[i] = s1[i] * s1[i]; }
+          st_s[c] += (double)warp_colsum32(s1, lane);
+          st_q[c] += (double)warp_colsum32(s2, lane);
+        }
+        if (P.act != MRA_ACT_NONE) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], P.act, P.slope);
+        }
+        if (valid) {
+          if (P.out_bf16) {
+            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(P.out) + obase + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              o[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+          } else {
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + obase + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+        }
+      }
+      if (prof && threadIdx.x == 64) atomicAdd(P.dbg + 4, (unsigned long long)(clock64() - te0));
+    }
+    if (P.stats) flush_stats();
+  }
+  tc_fence_before();
+  if constexpr (kPair) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    if constexpr (kPair)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols) : "memory");
+    else
+      tmem_dealloc(tmem_base, P.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+// Can this launch run on the halo kernel?  Needs unit A step, taps forming a full (kd, kh, kw) box and a plane
+// that fits the shared-memory budget.  Fills P's geometry fields on success.
+inline bool halo_setup(const GatherLaunch& L, int n, int ck, int cn, bool pair, HaloP& P) {
+  if (L.astep != 1 || L.taps.empty()) return false;
+  int lo[3] = {1 << 30, 1 << 30, 1 << 30}, hi[3] = {-(1 << 30), -(1 << 30), -(1 << 30)};
+  for (const Tap& t : L.taps) {
+    const int o[3] = {t.dd, t.dh, t.dw};
+    for (int i = 0; i < 3; ++i) { if (o[i] < lo[i]) lo[i] = o[i]; if (o[i] > hi[i]) hi[i] = o[i]; }
+  }
+  const int kd = hi[0] - lo[0] + 1, kh = hi[1] - lo[1] + 1, kw = hi[2] - lo[2] + 1;
+  if ((long long)kd * kh * kw != (long long)L.taps.size() || (int)L.taps.size() > kMaxTaps) return false;
+  P.kd = kd; P.kh = kh; P.kw = kw; P.dmin = lo[0]; P.hmin = lo[1]; P.wmin = lo[2];
+  for (int i = 0; i < kMaxTaps; ++i) P.twi[i] = -1;
+  for (const Tap& t : L.taps) {
+    const int idx = ((t.dd - lo[0]) * kh + (t.dh - lo[1])) * kw + (t.dw - lo[2]);
+    if (P.twi[idx] != -1) return false;
+    P.twi[idx] = (int16_t)t.widx;
+  }
+  P.Dl = L.dims[0]; P.Hl = L.dims[1]; P.Wl = L.dims[2]; P.N = n;
+  const int n_tile = pick_n_tile(cn);
+  if (n_tile == 0 || ck % 64 != 0) return false;
+  P.Cn = cn; P.n_tile = n_tile; P.n_tiles = cn / n_tile; P.kchunks = ck / 64;
+  // tile shape: 2D (16 x 8) or flat, whichever wastes fewer MMA rows (and fits)
+  const long long hw = (long long)P.Hl * P.Wl;
+  const int t2h = (P.Hl + 15) / 16, t2w = (P.Wl + 7) / 8;
+  const int Wb2 = 8 + kw - 1, Hb2 = 16 + kh - 1;
+  const long long rows2 = (long long)t2h * t2w * 128;
+  const int Wbf = P.Wl + kw - 1;
+  const long long flat_len = (long long)(P.Hl - 1) * Wbf + P.Wl;          // last valid flat position + 1
+  const int tf = (int)((flat_len + 127) / 128);
+  const int Hbf = (Wbf - 1 + 128 + (kh - 1) * Wbf + (kw - 1) + Wbf - 1) / Wbf;   // lines covering any 128-run + halo
+  const long long rowsf = (long long)tf * 128;
+  const size_t budget = kSmemLimit - 2048;
+  auto fits = [&](int Wb, int Hb) {
+    if (Wb > 256 || Hb > 256) return false;
+    const size_t slot = ((size_t)Wb * Hb * 128 + 1023) / 1024 * 1024;
+    return 2 * slot + 2 * (size_t)n_tile * 128 / (pair ? 2 : 1) <= budget;
+  };
+  const bool ok2 = fits(Wb2, Hb2), okf = fits(Wbf, Hbf);
+  if (!ok2 && !okf) return false;
+  const bool use_flat = okf && (!ok2 || rowsf * 100 < rows2 * 97);      // flat only when clearly better
+  (void)hw;
+  if (!use_flat) {
+    P.mode = 0; P.tiles_w = t2w; P.tiles_hw = t2h * t2w; P.Wb = Wb2; P.Hb = Hb2; P.sbo = Wb2 * 128;
+  } else {
+    P.mode = 1; P.tiles_w = 1; P.tiles_hw = tf; P.Wb = Wbf; P.Hb = Hbf; P.sbo = 1024;
+  }
+  P.plane_tx = P.Wb * P.Hb * 128;
+  P.slot_bytes = (P.plane_tx + 1023) / 1024 * 1024;
+  // ring depths: weights get what the planes leave (>= 2 each)
+  const size_t bB = (size_t)n_tile * 128 / (pair ? 2 : 1);
+  P.pair = pair ? 1 : 0;
+  int NP = kd >= 3 ? 3 : 2;
+  if (kd * P.kchunks == 1) NP = 2;
+  int NB = (int)((budget - (size_t)NP * P.slot_bytes) / bB);
+  while (NB < 3 && NP > 2) { --NP; NB = (int)((budget - (size_t)NP * P.slot_bytes) / bB); }
+  if (NB < 2) return false;
+  if (NB > 8) NB = 8;
+  // spare room goes to a deeper plane ring (up to 4)
+  while (NP < 4 && (size_t)(NP + 1) * P.slot_bytes + (size_t)NB * bB <= budget) ++NP;
+  P.NP = NP; P.NB = NB;
+  const long long total = (long long)n * (pair ? (P.Dl + 1) / 2 : P.Dl) * P.tiles_hw * P.n_tiles;
+  if (total >= (1ll << 31)) return false;
+  P.total_tiles = (int)total;
+  return true;
+}
+
+inline int run_gather_halo(const GatherPlan& plan, const GatherLaunch& L, HaloP& P, const GatherRun& R, const CUtensorMap& tmB_in,
+                           cudaStream_t st) {
+  CUtensorMap tmB = tmB_in;
+  if (P.pair) {          // each CTA of a pair loads half of the slab's rows
+    if (int rc = make_weight_map(&tmB, R.b, (long long)R.slabs * plan.cn, plan.ck, P.n_tile / 2)) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    attr_set = true;
+  }
+  P.ostep = L.ostep; P.od0 = L.o0[0]; P.oh0 = L.o0[1]; P.ow0 = L.o0[2];
+  P.osw = plan.cn;
+  P.osh = (long long)plan.odims[2] * P.osw;
+  P.osd = (long long)plan.odims[1] * P.osh;
+  P.osn = (long long)plan.odims[0] * P.osd;
+  P.out = R.out; P.out_bf16 = R.out_bf16;
+  P.bias = R.bias; P.act = R.act; P.slope = R.slope;
+  P.stats = R.stats; P.err = tc_err_flag();
+  { const char* e = getenv("MRA_GATHER_DEBUG"); P.debug = e ? atoi(e) : 0; }
+  P.dbg = tc_dbg_counters();
+  P.tmem_cols = pow2_cols(2 * P.n_tile);
+  CUtensorMap tmA;
+  if (int rc = make_act_map(&tmA, R.a, plan.n, plan.adims[0], plan.adims[1], plan.adims[2], plan.ck, P.Wb, P.Hb, 1, 1)) return rc;
+  const size_t smem = (size_t)P.NP * P.slot_bytes + (size_t)P.NB * P.n_tile * 128 / (P.pair ? 2 : 1) + 1024 + 256;
+  if (!P.pair) {
+    const int ctas = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
+    gather_halo_kernel<false><<<ctas, kThreadsHalo, smem, st>>>(tmA, tmB, P);
+  } else {
+    int pairs = num_sms() / 2;
+    if (P.total_tiles < pairs) pairs = P.total_tiles;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * pairs), 1, 1);
+    cfg.blockDim = dim3(kThreadsHalo, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    MRA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gather_halo_kernel<true>, tmA, tmB, P));
+  }
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+
+// Run every launch of a gather plan on the tensor cores: stride-1 launches on the halo-plane kernel, the
+// rest (and anything the halo kernel cannot host) on the per-tap kernel.
+inline int run_gather_tc(const GatherPlan& plan, const GatherRun& R, cudaStream_t st) {
+  const int n_tile = pick_n_tile(plan.cn);
+  MRA_REQUIRE(n_tile > 0 && plan.ck % 64 == 0, "channel counts not eligible for the tensor-core path");
+  const long long rows = (long long)R.slabs * plan.cn;
+  CUtensorMap tmB;
+  if (int rc = make_weight_map(&tmB, R.b, rows, plan.ck, n_tile)) return rc;
+  // MRA_GATHER_MODE (experiments): v1 = per-tap kernel only, single = halo kernel without CTA pairs
+  const char* gm = getenv("MRA_GATHER_MODE");
+  const bool force_v1 = gm && !strcmp(gm, "v1");
+  const bool no_pair = gm && !strcmp(gm, "single");
+  for (const GatherLaunch& L : plan.launches) {
+    HaloP P;
+    memset(&P, 0, sizeof(P));
+    // the halo kernel pays off when several taps share a plane (kh * kw >= 4)
+    int lo[2] = {1 << 30, 1 << 30}, hi[2] = {-(1 << 30), -(1 << 30)};
+    for (const Tap& t : L.taps) {
+      if (t.dh < lo[0]) lo[0] = t.dh; if (t.dh > hi[0]) hi[0] = t.dh;
+      if (t.dw < lo[1]) lo[1] = t.dw; if (t.dw > hi[1]) hi[1] = t.dw;
+    }
+    const bool reuse = !L.taps.empty() && (hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) >= 4;
+    bool halo = !force_v1 && reuse && halo_setup(L, plan.n, plan.ck, plan.cn, !no_pair, P);
+    if (halo) for (const Tap& t : L.taps) if (t.widx >= R.slabs) halo = false;
+    if (halo) { if (int rc = run_gather_halo(plan, L, P, R, tmB, st)) return rc; }
+    else      { if (int rc = run_gather_v1_launch(plan, L, R, tmB, n_tile, st)) return rc; }
+  }
+  return 0;
+}
+
+inline int run_gather_tc(const mra_conv_desc& d, int which, const void* a, const void* b, const float* bias, void* out,
+                         double* stats, cudaStream_t st) {
+  GatherPlan plan;
+  MRA_REQUIRE(build_gather_plan(d, which, plan), "unsupported conv geometry");
+  GatherRun R{a, b, d.k * d.k * d.k, bias, out, 1, which == 0 ? d.act : MRA_ACT_NONE, d.slope, stats};
+  return run_gather_tc(plan, R, st);
+}
+
+}  // namespace tc
+}  // namespace mra

@@ -4,7 +4,7 @@
 #include "common.cuh"
 #include "conv_naive.cuh"
 #include "conv_plan.h"
-#include "conv_tc.cuh"
+#include "conv_tc_halo.cuh"
 #include "conv_special.cuh"
 #include "misc.cuh"
 #include "norm.cuh"

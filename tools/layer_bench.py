@@ -29,5 +29,5 @@ for name, fn in (("fprop", lambda: I.conv_fprop(x, w, None, g, want_stats=g.cout
     if c[5]:
         print("   per CTA: producer wait %.0f / total %.0f clk ; mma wait %.0f / total %.0f clk ; epilogue %.0f clk ; CTAs %d" % (
             c[0] / c[5], c[1] / c[5], c[2] / c[5], c[3] / c[5], c[4] / c[5], c[5]))
-        print("   mma wait for a free accumulator %.0f clk" % (c[6] / c[5]))
+        print("   mma wait for a free accumulator %.0f clk ; mma wait for a halo plane %.0f clk" % (c[6] / c[5], c[7] / c[5]))
     print("%s %.4f ms  %.1f TFLOP/s  (flag %d)" % (name, t, 2 * macs / t / 1e9, I.tc_error()), flush=True)
