@@ -66,8 +66,17 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
 }
 // bounded wait: returns false (and raises the error flag) instead of hanging
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
+#pragma unroll 1
   for (uint32_t it = 0; it < (1u << 24); ++it)
     if (mbar_try_wait(bar, parity)) return true;
+  if (err) atomicExch(err, code);
+  return false;
+}
+// polling variant (mbarrier.test_wait never suspends the thread)
+__device__ __forceinline__ bool mbar_wait_poll(uint64_t* bar, uint32_t parity, int* err, int code) {
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 26); ++it)
+    if (mbar_test_wait(bar, parity)) return true;
   if (err) atomicExch(err, code);
   return false;
 }
@@ -158,6 +167,96 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
     }
   }
   return v[0];
+}
+
+
+// ------------------------------------------------------------------ shared epilogue of the gather kernels
+// Instruction footprint matters: the epilogue warps run next to the single MMA-issuing thread, and a fully
+// unrolled epilogue (hundreds of KB of SASS) evicts that thread's loop from the instruction cache every tile.
+// So the 32-column chunk loop stays ROLLED, the per-chunk InstanceNorm partial sums live in a small per-thread
+// array indexed at run time, and the transcendental activations are out of line.
+struct EpiArgs {
+  void* out; int out_bf16;
+  const float* bias;
+  int act; float slope;
+  bool stats;
+};
+__device__ __noinline__ float act_slow(float v, int act) {
+  return act == MRA_ACT_TANH ? tanhf(v) : 1.f / (1.f + expf(-v));
+}
+// One accumulator tile (this warp's 32 TMEM lanes x nchunks * 32 columns) -> bias / stats / activation / store.
+// `release` is called once all TMEM reads of the tile are done.
+template <typename Release>
+__device__ __forceinline__ void epilogue_tile(const EpiArgs& E, uint32_t t_addr, int nchunks, bool valid, long long obase, int n0,
+                                              int lane, double* st_s, double* st_q, Release release) {
+  const bool lin_act = E.act == MRA_ACT_RELU || E.act == MRA_ACT_LRELU;
+  const float nslope = E.act == MRA_ACT_RELU ? 0.f : E.slope;
+#pragma unroll 1
+  for (int c = 0; c < nchunks; ++c) {
+    const int c0 = c * 32;
+    uint32_t r[32];
+    tmem_ld32(t_addr + (uint32_t)c0, r);
+    tmem_wait_ld();
+    if (c == nchunks - 1) release();
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    if (E.bias) {
+      const float4* b4 = reinterpret_cast<const float4*>(E.bias + n0 + c0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = __ldg(b4 + i);
+        v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+      }
+    }
+    if (E.stats) {
+      float s1[32], s2[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { s1[i] = valid ? v[i] : 0.f; s2[i] = s1[i] * s1[i]; }
+      st_s[c] += (double)warp_colsum32(s1, lane);
+      st_q[c] += (double)warp_colsum32(s2, lane);
+    }
+    if (lin_act) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * nslope;
+    } else if (E.act != MRA_ACT_NONE) {
+#pragma unroll 1
+      for (int i = 0; i < 32; ++i) {
+        // dynamic index into a register array would spill; go through a select chain on a rotating copy instead
+        float x = v[0];
+#pragma unroll
+        for (int k = 1; k < 32; ++k) x = (k == i) ? v[k] : x;
+        const float y = act_slow(x, E.act);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = (k == i) ? y : v[k];
+      }
+    }
+    if (valid) {
+      if (E.out_bf16) {
+        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(E.out) + obase + c0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          o[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                            pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+      } else {
+        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(E.out) + obase + c0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+    }
+  }
+}
+// add this warp's per-chunk partial sums to stats[n][Cn][2] (lane = column inside the chunk) and clear them
+__device__ __forceinline__ void epilogue_flush_stats(double* stats, int n, int Cn, int n0, int nchunks, int lane, double* st_s,
+                                                     double* st_q) {
+  if (n < 0) return;
+#pragma unroll 1
+  for (int c = 0; c < nchunks; ++c) {
+    double* st = stats + ((long long)n * Cn + n0 + c * 32 + lane) * 2;
+    atomicAdd(st, st_s[c]);
+    atomicAdd(st + 1, st_q[c]);
+    st_s[c] = 0.0; st_q[c] = 0.0;
+  }
 }
 
 // ------------------------------------------------------------------ gather (fprop / dgrad) kernel
@@ -313,18 +412,7 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
     for (int c = 0; c < 8; ++c) { st_s[c] = 0.0; st_q[c] = 0.0; }
     int st_n = -1, st_n0 = 0;
-    auto flush_stats = [&]() {
-      if (st_n >= 0) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          if (c < nchunks) {
-            double* st = P.stats + ((long long)st_n * P.Cn + st_n0 + c * 32 + lane) * 2;
-            atomicAdd(st, st_s[c]);
-            atomicAdd(st + 1, st_q[c]);
-            st_s[c] = 0.0; st_q[c] = 0.0;
-          }
-      }
-    };
+    const EpiArgs E{P.out, P.out_bf16, P.bias, P.act, P.slope, P.stats != nullptr};
     int j = 0;
     bool ok = true;
     for (int tile = blockIdx.x; tile < P.total_tiles && ok; tile += gridDim.x, ++j) {
@@ -335,59 +423,24 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool valid = lw < P.Wl && lh < P.Hl && ld < P.Dl;
       const long long obase = (long long)t.n * P.osn + (long long)(ld * P.ostep + P.od0) * P.osd +
                               (long long)(lh * P.ostep + P.oh0) * P.osh + (long long)(lw * P.ostep + P.ow0) * P.osw + t.n0;
-      if (P.stats && (t.n != st_n || t.n0 != st_n0)) { flush_stats(); st_n = t.n; st_n0 = t.n0; }
+      if (P.stats && (t.n != st_n || t.n0 != st_n0)) {
+        epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, nchunks, lane, st_s, st_q);
+        st_n = t.n; st_n0 = t.n0;
+      }
       ok = mbar_wait(&acc_full[buf], aph, P.err, 3);
       if (!ok) break;
       tc_fence_after();
       const long long te0 = (P.debug & 2) ? clock64() : 0;
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * P.n_tile);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        if (c >= nchunks) break;
-        const int c0 = c * 32;
-        uint32_t r[32];
-        tmem_ld32(t_addr + (uint32_t)c0, r);
-        tmem_wait_ld();
-        if (c == nchunks - 1) {                 // accumulator fully read: hand the buffer back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[buf]);
-        }
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        if (P.bias) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += __ldg(P.bias + t.n0 + c0 + i);
-        }
-        if (P.stats) {
-          float s1[32], s2[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) { s1[i] = valid ? v[i] : 0.f; s2[i] = s1[i] * s1[i]; }
-          st_s[c] += (double)warp_colsum32(s1, lane);
-          st_q[c] += (double)warp_colsum32(s2, lane);
-        }
-        if (P.act != MRA_ACT_NONE) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], P.act, P.slope);
-        }
-        if (valid) {
-          if (P.out_bf16) {
-            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(P.out) + obase + c0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              o[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                                pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
-          } else {
-            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + obase + c0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          }
-        }
-      }
+      uint64_t* rel_bar = &acc_empty[buf];
+      epilogue_tile(E, t_addr, nchunks, valid, obase, t.n0, lane, st_s, st_q, [&]() {
+        tc_fence_before();                      // accumulator fully read: hand the buffer back to the MMA warp
+        __syncwarp();
+        if (lane == 0) mbar_arrive(rel_bar);
+      });
       if ((P.debug & 2) && threadIdx.x == 64) atomicAdd(P.dbg + 4, (unsigned long long)(clock64() - te0));
     }
-    if (P.stats) flush_stats();
+    if (P.stats) epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, nchunks, lane, st_s, st_q);
   }
   tc_fence_before();
   __syncthreads();

@@ -38,7 +38,9 @@ struct HaloP {
   int kd, kh, kw;                   // tap box extents (taps ordered td, th, tw)
   int dmin, hmin, wmin;             // smallest tap offsets
   int Cn, n_tile, n_tiles, kchunks;
-  int total_tiles;
+  int total_tiles;                  // full-width work items
+  int split_from, total_work;       // work items >= split_from are HALF-width (n_tile / 2): two per tile, so that the
+                                    // last, partial round of the persistent schedule costs half a round
   int ostep, od0, oh0, ow0;
   long long osn, osd, osh, osw;     // output strides in elements
   void* out;
@@ -53,6 +55,7 @@ struct HaloP {
   int debug;
   unsigned long long* dbg;
   int pair;                         // 1: cta_group::2 pairs (host-side choice of the kernel instantiation)
+  int b_tx_dbg;                     // timing experiments: bytes per weight box when the box was shrunk (debug bit 5)
 };
 
 __device__ __forceinline__ uint64_t desc_kmajor_sw128_sbo(uint32_t saddr, uint32_t sbo_bytes) {
@@ -60,18 +63,24 @@ __device__ __forceinline__ uint64_t desc_kmajor_sw128_sbo(uint32_t saddr, uint32
          (2ull << 61);
 }
 
-struct HaloTile { int n, d, n0, h0, w0, f0, hs, roff; };
+struct HaloTile { int n, d, n0, h0, w0, f0, hs, roff, width; };
 // work index -> coordinates.  Order: n_tile fastest, then the tiles of a plane, then d (pair mode: pairs of
 // planes, CTA rank r takes d = 2 * dp + r so both tiles share the weight slab and the in-plane geometry), then n.
-__device__ __forceinline__ HaloTile halo_decode(const HaloP& P, int tile, int pair, int rank) {
+__device__ __forceinline__ HaloTile halo_decode(const HaloP& P, int work, int pair, int rank) {
   HaloTile t;
+  int tile = work, half = 0;
+  t.width = P.n_tile;
+  if (work >= P.split_from) {
+    const int k = work - P.split_from;
+    tile = P.split_from + (k >> 1); half = k & 1; t.width = P.n_tile >> 1;
+  }
   const int nt = tile % P.n_tiles; tile /= P.n_tiles;
   const int j = tile % P.tiles_hw; tile /= P.tiles_hw;
   const int dsteps = pair ? (P.Dl + 1) / 2 : P.Dl;
   const int dq = tile % dsteps;
   t.d = pair ? 2 * dq + rank : dq;            // may be == Dl for the odd plane's partner: loads hit zero fill, nothing is stored
   t.n = tile / dsteps;
-  t.n0 = nt * P.n_tile;
+  t.n0 = nt * P.n_tile + half * t.width;
   if (P.mode == 0) {
     t.h0 = (j / P.tiles_w) * 16; t.w0 = (j % P.tiles_w) * 8;
     t.f0 = 0; t.hs = t.h0; t.roff = 0;
@@ -215,7 +224,7 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       int s = 0;
       uint32_t ph = 0;
       bool ok = true;
-      for (int w = work0; w < P.total_tiles && ok; w += wstride) {
+      for (int w = work0; w < P.total_work && ok; w += wstride) {
         const HaloTile t = halo_decode(P, w, kPair, rank);
         int kc = rot_kc0, td = rot_td0;
         for (int pi = 0; pi < nplanes; ++pi) {
@@ -235,16 +244,17 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       uint32_t ph = 0;
       bool ok = true;
       long long t_wait = 0, t_begin = prof ? clock64() : 0;
-      for (int w = work0; w < P.total_tiles && ok; w += wstride) {
-        const int n0 = (w % P.n_tiles) * P.n_tile + rank * (int)b_rows;
+      for (int w = work0; w < P.total_work && ok; w += wstride) {
+        const HaloTile t = halo_decode(P, w, kPair, 0);
+        const int n0 = t.n0 + rank * (t.width / kCtas);      // half-width items use the first rows of the (full-size) box
         int kc = rot_kc0, td = rot_td0;
         for (int pi = 0; pi < nplanes && ok; ++pi) {
           int tap = rot_t;                                   // (th, tw) index inside the plane, rotated start
           for (int i = 0; i < taps_hw; ++i) {
             const long long tw0 = prof ? clock64() : 0;
-            if (!mbar_wait(&b_empty[s], ph ^ 1u, P.err, 22)) { ok = false; break; }
+            if (!((P.debug & 64) ? mbar_wait_poll(&b_empty[s], ph ^ 1u, P.err, 22) : mbar_wait(&b_empty[s], ph ^ 1u, P.err, 22))) { ok = false; break; }
             if (prof) t_wait += clock64() - tw0;
-            if (leader) mbar_expect_tx(&b_full[s], b_bytes * kCtas);
+            if (leader) mbar_expect_tx(&b_full[s], (P.b_tx_dbg ? (uint32_t)P.b_tx_dbg : b_bytes) * kCtas);
             tma_load_2d_g<kPair>(bring + (size_t)s * b_bytes, &tmB, &b_full[s], kc * 64,
                                  (int)P.twi[td * taps_hw + tap] * P.Cn + n0);
             if (++s == P.NB) { s = 0; ph ^= 1u; }
@@ -259,7 +269,7 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (lane == 0 && leader) {
       // The issue loop is a single thread: keep it to a few dozen instructions per stage (no divisions, the
       // descriptors advance by adding constants to their 16-byte-unit address field).
-      const uint32_t idesc = make_idesc_m(128 * kCtas, P.n_tile);
+      const uint32_t idesc_full = make_idesc_m(128 * kCtas, P.n_tile), idesc_half = make_idesc_m(128 * kCtas, P.n_tile >> 1);
       const uint64_t a_desc0 = desc_kmajor_sw128_sbo(0, (uint32_t)P.sbo);      // address field filled per plane
       const uint64_t b_desc0 = desc_kmajor_sw128(0);
       const uint32_t planes_u = smem_u32(planes) >> 4, bring_u = smem_u32(bring) >> 4;
@@ -272,15 +282,13 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       uint32_t pph = 0, bph = 0;
       bool ok = true, b_ready = false;
       int j = 0;
-      long long t_wait = 0, t_waitp = 0, t_wacc = 0, t_begin = prof ? clock64() : 0;
-      for (int w = work0; w < P.total_tiles && ok; w += wstride, ++j) {
+      long long t_wait = 0, t_waitp = 0, t_wacc = 0, t_begin = (prof || (P.debug & 128)) ? clock64() : 0;
+      for (int w = work0; w < P.total_work && ok; w += wstride, ++j) {
         const int buf = j & 1;
         const uint32_t aph = ((uint32_t)j >> 1) & 1u;
-        uint32_t roff_u = 0;
-        if (P.mode != 0) {                                     // flat tiles start inside their first plane line
-          const int f0 = ((w / P.n_tiles) % P.tiles_hw) * 128;
-          roff_u = (uint32_t)(f0 % P.Wb) * row_u;
-        }
+        const HaloTile t = halo_decode(P, w, kPair, 0);
+        const uint32_t roff_u = (uint32_t)t.roff * row_u;      // flat tiles start inside their first plane line
+        const uint32_t idesc = t.width == P.n_tile ? idesc_full : idesc_half;
         const long long ta0 = prof ? clock64() : 0;
         if (!mbar_wait(&acc_empty[buf], aph ^ 1u, P.err, 24)) { ok = false; break; }
         if (prof) t_wacc += clock64() - ta0;
@@ -322,7 +330,7 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
         if (ok) umma_commit_g<kPair>(&acc_full[buf]);
       }
-      if (prof) {
+      if (prof || (P.debug & 128)) {
         atomicAdd(P.dbg + 2, (unsigned long long)t_wait); atomicAdd(P.dbg + 3, (unsigned long long)(clock64() - t_begin));
         atomicAdd(P.dbg + 6, (unsigned long long)t_wacc); atomicAdd(P.dbg + 7, (unsigned long long)t_waitp);
         atomicAdd(P.dbg + 5, 1ull);
@@ -332,26 +340,15 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // ---- epilogue warps 2..5 -> TMEM lane quadrant (warp % 4)
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int nchunks = P.n_tile / 32;
+    int nchunks = P.n_tile / 32;
     double st_s[8], st_q[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) { st_s[c] = 0.0; st_q[c] = 0.0; }
     int st_n = -1, st_n0 = 0;
-    auto flush_stats = [&]() {
-      if (st_n >= 0) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          if (c < nchunks) {
-            double* st = P.stats + ((long long)st_n * P.Cn + st_n0 + c * 32 + lane) * 2;
-            atomicAdd(st, st_s[c]);
-            atomicAdd(st + 1, st_q[c]);
-            st_s[c] = 0.0; st_q[c] = 0.0;
-          }
-      }
-    };
+    const EpiArgs E{P.out, P.out_bf16, P.bias, P.act, P.slope, P.stats != nullptr};
     int j = 0;
     bool ok = true;
-    for (int w = work0; w < P.total_tiles && ok; w += wstride, ++j) {
+    for (int w = work0; w < P.total_work && ok; w += wstride, ++j) {
       const HaloTile t = halo_decode(P, w, kPair, rank);
       const int buf = j & 1;
       const uint32_t aph = ((uint32_t)j >> 1) & 1u;
@@ -361,59 +358,25 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const bool valid = lw < P.Wl && lh < P.Hl && t.d < P.Dl;
       const long long obase = (long long)t.n * P.osn + (long long)(t.d * P.ostep + P.od0) * P.osd +
                               (long long)(lh * P.ostep + P.oh0) * P.osh + (long long)(lw * P.ostep + P.ow0) * P.osw + t.n0;
-      if (P.stats && (t.n != st_n || t.n0 != st_n0)) { flush_stats(); st_n = t.n; st_n0 = t.n0; }
+      if (P.stats && (t.n != st_n || t.n0 != st_n0)) {
+        epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, nchunks, lane, st_s, st_q);
+        st_n = t.n; st_n0 = t.n0;
+      }
+      nchunks = t.width / 32;
       ok = mbar_wait(&acc_full[buf], aph, P.err, 23);
       if (!ok) break;
       tc_fence_after();
       const long long te0 = prof ? clock64() : 0;
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * P.n_tile);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        if (c >= nchunks) break;
-        const int c0 = c * 32;
-        uint32_t r[32];
-        tmem_ld32(t_addr + (uint32_t)c0, r);
-        tmem_wait_ld();
-        if (c == nchunks - 1) {                 // accumulator fully read: hand the buffer back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) { if constexpr (kPair) mbar_arrive_leader(&acc_empty[buf]); else mbar_arrive(&acc_empty[buf]); }
-        }
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        if (P.bias) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += __ldg(P.bias + t.n0 + c0 + i);
-        }
-        if (P.stats) {
-          float s1[32], s2[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) { s1[i] = valid ? v[i] : 0.f; s2[i] = s1[i] * s1[i]; }
-          st_s[c] += (double)warp_colsum32(s1, lane);
-          st_q[c] += (double)warp_colsum32(s2, lane);
-        }
-        if (P.act != MRA_ACT_NONE) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], P.act, P.slope);
-        }
-        if (valid) {
-          if (P.out_bf16) {
-            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(P.out) + obase + c0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              o[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                                pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
-          } else {
-            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + obase + c0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          }
-        }
-      }
+      uint64_t* rel_bar = &acc_empty[buf];
+      epilogue_tile(E, t_addr, nchunks, valid, obase, t.n0, lane, st_s, st_q, [&]() {
+        tc_fence_before();                      // accumulator fully read: hand the buffer back to the MMA warp
+        __syncwarp();
+        if (lane == 0) { if constexpr (kPair) mbar_arrive_leader(rel_bar); else mbar_arrive(rel_bar); }
+      });
       if (prof && threadIdx.x == 64) atomicAdd(P.dbg + 4, (unsigned long long)(clock64() - te0));
     }
-    if (P.stats) flush_stats();
+    if (P.stats) epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, nchunks, lane, st_s, st_q);
   }
   tc_fence_before();
   if constexpr (kPair) cluster_sync_all(); else __syncthreads();
@@ -486,10 +449,21 @@ inline bool halo_setup(const GatherLaunch& L, int n, int ck, int cn, bool pair, 
   if (NB > 8) NB = 8;
   // spare room goes to a deeper plane ring (up to 4)
   while (NP < 4 && (size_t)(NP + 1) * P.slot_bytes + (size_t)NB * bB <= budget) ++NP;
+  { const char* e = getenv("MRA_HALO_NB"); if (e && atoi(e) >= 2 && atoi(e) <= NB) NB = atoi(e); }
+  { const char* e = getenv("MRA_HALO_NP"); if (e && atoi(e) >= 2 && atoi(e) <= NP) NP = atoi(e); }
   P.NP = NP; P.NB = NB;
   const long long total = (long long)n * (pair ? (P.Dl + 1) / 2 : P.Dl) * P.tiles_hw * P.n_tiles;
   if (total >= (1ll << 31)) return false;
   P.total_tiles = (int)total;
+  // persistent schedule: `units` CTAs (or pairs) take work items round-robin.  When the last round is at most
+  // half full, its tiles are split into two half-width items each.
+  const int units = pair ? num_sms() / 2 : num_sms();
+  const int rem = (int)(total % units);
+  P.split_from = P.total_tiles; P.total_work = P.total_tiles;
+  if (total > units && rem > 0 && 2 * rem <= units && n_tile >= 128 && getenv("MRA_GATHER_NOSPLIT") == nullptr) {
+    P.split_from = P.total_tiles - rem;
+    P.total_work = P.total_tiles + rem;
+  }
   return true;
 }
 
@@ -499,6 +473,11 @@ inline int run_gather_halo(const GatherPlan& plan, const GatherLaunch& L, HaloP&
   if (P.pair) {          // each CTA of a pair loads half of the slab's rows
     if (int rc = make_weight_map(&tmB, R.b, (long long)R.slabs * plan.cn, plan.ck, P.n_tile / 2)) return rc;
   }
+  { const char* e = getenv("MRA_GATHER_DEBUG");
+    if (e && (atoi(e) & 32)) {     // shrink the weight boxes to 8 rows: same handshakes, ~no bytes (results are garbage)
+      if (int rc = make_weight_map(&tmB, R.b, (long long)R.slabs * plan.cn, plan.ck, 8)) return rc;
+      P.b_tx_dbg = 8 * 128;
+    } }
   static bool attr_set = false;
   if (!attr_set) {
     MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
@@ -520,11 +499,11 @@ inline int run_gather_halo(const GatherPlan& plan, const GatherLaunch& L, HaloP&
   if (int rc = make_act_map(&tmA, R.a, plan.n, plan.adims[0], plan.adims[1], plan.adims[2], plan.ck, P.Wb, P.Hb, 1, 1)) return rc;
   const size_t smem = (size_t)P.NP * P.slot_bytes + (size_t)P.NB * P.n_tile * 128 / (P.pair ? 2 : 1) + 1024 + 256;
   if (!P.pair) {
-    const int ctas = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
+    const int ctas = P.total_work < num_sms() ? P.total_work : num_sms();
     gather_halo_kernel<false><<<ctas, kThreadsHalo, smem, st>>>(tmA, tmB, P);
   } else {
     int pairs = num_sms() / 2;
-    if (P.total_tiles < pairs) pairs = P.total_tiles;
+    if (P.total_work < pairs) pairs = P.total_work;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(2 * pairs), 1, 1);

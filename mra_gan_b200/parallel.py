@@ -34,6 +34,18 @@ def init_distributed(backend=None):
     return rank, world
 
 
+def _dense_view(t):
+    """A contiguous view of a dense tensor whose dims are permuted in memory (conv weights keep the kernels'
+    packed [taps][Cout][Cin] layout behind torch's logical shape); collectives need contiguous tensors."""
+    if t.is_contiguous():
+        return t
+    perm = sorted(range(t.dim()), key=lambda i: -t.stride(i))
+    v = t.permute(perm)
+    if not v.is_contiguous():
+        raise RuntimeError("parameter is not a dense permutation of a contiguous buffer")
+    return v
+
+
 class _Bucket:
     __slots__ = ("flat", "params", "pending", "work", "launched")
 
@@ -135,7 +147,7 @@ def attach(model, bucket_mb=32.0):
         for name in model.model_names:
             net = getattr(model, "net" + name)
             for t in list(net.parameters()) + list(net.buffers()):
-                dist.broadcast(t.data, src=0)
+                dist.broadcast(_dense_view(t.data), src=0)
     model.grad_sync = GradSync({"G": [model.netG_A, model.netG_B], "D": [model.netD_A, model.netD_B]},
                                bucket_mb=bucket_mb)
     return model.grad_sync
