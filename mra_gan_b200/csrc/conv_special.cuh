@@ -247,12 +247,12 @@ inline size_t workspace_bytes(const mra_conv_desc& d, int which) {
   if (stem_eligible(d)) {
     const size_t e = (size_t)d.n * d.din * d.hout * d.wout * 64;
     if (which == 0) return a256(e * 2) + wexp + 512;
-    if (which == 1) return a256(e * 4) + wexp + 512;
+    if (which == 1) return a256(e * 2) + wexp + 512;
     return a256(e * 2) + dwe + 512;
   }
   if (head_eligible(d)) {
     const size_t z = (size_t)d.n * d.dout * d.hin * d.win * 64;
-    if (which == 0) return a256(z * 4) + wexp + 512;
+    if (which == 0) return a256(z * 2) + wexp + 512;
     if (which == 1) return a256(z * 2) + wexp + 512;
     return a256(z * 2) + dwe + 512;
   }
@@ -353,15 +353,15 @@ inline int stem_wgrad(const mra_conv_desc& d, const void* x, const void* dy, flo
 inline int stem_dgrad(const mra_conv_desc& d, const void* dy, const void* wT, void* dx, void* wsp, size_t wsb, cudaStream_t st) {
   Workspace ws{(char*)wsp, wsb, 0};
   const long long rows = (long long)d.n * d.din;
-  MRA_WS_TAKE(Z, float, (size_t)rows * d.hout * d.wout * 64 * 4);
+  MRA_WS_TAKE(Z, bf16, (size_t)rows * d.hout * d.wout * 64 * 2);                    // bf16, see head_fprop
   MRA_WS_TAKE(BT, bf16, (size_t)d.k * d.cout * 64 * 2);
   wexp_kernel<<<sgrid((long long)d.k * d.cout * 64), 256, 0, st>>>((const bf16*)wT, BT, d.k, d.cout, 1);   // [kd][c][co]
   MRA_LAUNCH_CHECK();
   GatherPlan plan;
   MRA_REQUIRE(build_gather_plan(stem_geom(d), 1, plan), "stem dgrad plan");
-  tc::GatherRun R{dy, BT, d.k, nullptr, Z, 0, MRA_ACT_NONE, 0.f, nullptr};
+  tc::GatherRun R{dy, BT, d.k, nullptr, Z, 1, MRA_ACT_NONE, 0.f, nullptr};
   if (int rc = tc::run_gather_tc(plan, R, st)) return rc;
-  shift_sum_kernel<float, bf16><<<sgrid(rows * d.hin * d.win), 256, 0, st>>>(Z, (bf16*)dx, rows, d.hout, d.wout, d.hin, d.win, d.k, -1, 0,
+  shift_sum_kernel<bf16, bf16><<<sgrid(rows * d.hin * d.win), 256, 0, st>>>(Z, (bf16*)dx, rows, d.hout, d.wout, d.hin, d.win, d.k, -1, 0,
                                                                               nullptr, MRA_ACT_NONE, 0.f);
   MRA_LAUNCH_CHECK();
   return 0;
@@ -371,15 +371,17 @@ inline int head_fprop(const mra_conv_desc& d, const void* x, const void* w, cons
                       cudaStream_t st) {
   Workspace ws{(char*)wsp, wsb, 0};
   const long long rows = (long long)d.n * d.dout;
-  MRA_WS_TAKE(Z, float, (size_t)rows * d.hin * d.win * 64 * 4);
+  // Z (the per-(kh,kw) partial sums over kd and ci) is stored in bf16: its 49 terms per output are summed in fp32
+  // by shift_sum, so the rounding noise stays at the level of the bf16 output itself while the traffic halves
+  MRA_WS_TAKE(Z, bf16, (size_t)rows * d.hin * d.win * 64 * 2);
   MRA_WS_TAKE(B, bf16, (size_t)d.k * d.cin * 64 * 2);
   wexp_kernel<<<sgrid((long long)d.k * d.cin * 64), 256, 0, st>>>((const bf16*)w, B, d.k, d.cin, 1);       // [kd][c][ci]
   MRA_LAUNCH_CHECK();
   GatherPlan plan;
   MRA_REQUIRE(build_gather_plan(head_geom(d), 0, plan), "head plan");
-  tc::GatherRun R{x, B, d.k, nullptr, Z, 0, MRA_ACT_NONE, 0.f, nullptr};
+  tc::GatherRun R{x, B, d.k, nullptr, Z, 1, MRA_ACT_NONE, 0.f, nullptr};
   if (int rc = tc::run_gather_tc(plan, R, st)) return rc;
-  shift_sum_kernel<float, bf16><<<sgrid(rows * d.hout * d.wout), 256, 0, st>>>(Z, (bf16*)y, rows, d.hin, d.win, d.hout, d.wout, d.k, +1, -d.pad,
+  shift_sum_kernel<bf16, bf16><<<sgrid(rows * d.hout * d.wout), 256, 0, st>>>(Z, (bf16*)y, rows, d.hin, d.win, d.hout, d.wout, d.k, +1, -d.pad,
                                                                                 bias, d.act, d.slope);
   MRA_LAUNCH_CHECK();
   return 0;

@@ -38,6 +38,18 @@ constexpr uint32_t kABytes = 128 * 128;          // 128 rows x 64 bf16
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One elected lane of a fully active warp.  Unlike `lane == 0`, ptxas knows that exactly one thread runs the
+// guarded region, so per-thread values can be moved to the uniform registers UTCHMMA / UTMALDG need with a plain
+// R2UR instead of a per-instruction ELECT / BROADCAST "waterfall" loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -334,7 +346,7 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t git = 0;                                    // global k-iteration counter (stage ring position)
       bool ok = true;
       const bool prof = (P.debug & 2) != 0;
@@ -361,7 +373,7 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (prof) { atomicAdd(P.dbg + 0, (unsigned long long)t_wait); atomicAdd(P.dbg + 1, (unsigned long long)(clock64() - t_begin)); }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc(P.n_tile, 0, 0);
       const uint64_t desc0 = desc_kmajor_sw128(0);
       const uint32_t smem_u = smem_u32(smem) >> 4, stage_u = stage_bytes >> 4;
@@ -641,7 +653,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
     }
     if (prof && lane == 0) { atomicAdd(P.dbg + 0, (unsigned long long)t_wait); atomicAdd(P.dbg + 1, (unsigned long long)(clock64() - t_begin)); }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       WSegIter it; WSeg sg;
       wseg_begin(P, kblocks, it);
       const uint32_t smem_u = smem_u32(smem) >> 4, stage_u = stage_bytes >> 4;

@@ -1,0 +1,283 @@
+// Column gather kernel: stride-1 GATHER launches whose taps run along d only (kernel (kd, 1, 1)) with few channels
+// -- the channel-expanded stem / head lowerings of conv_special.cuh (64 -> 64 channels, kd = 7).
+//
+// For these the per-tap kernel is hopeless: every output tile re-loads kd input tiles for 28 small (N = 64) MMAs and
+// pays a barrier handshake per tap.  Here a CTA walks a COLUMN of output tiles along d and keeps
+//   * all kd weight slabs resident in shared memory (loaded once per CTA), and
+//   * a ring of input planes (one 16 x 8 position tile of one d-plane, 64 channels = 16 KB): stepping to the next
+//     output plane loads ONE new plane instead of kd, and costs ONE barrier wait for 4 * kd back-to-back MMAs.
+// Columns are cut into segments along d so that the persistent CTAs get a balanced number of work units.
+// Warp roles as in conv_tc.cuh: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue.
+#pragma once
+#include "conv_tc.cuh"
+
+namespace mra {
+namespace tc {
+
+struct ColP {
+  int Dl, Hl, Wl, N;                // launch-space (output) dims
+  int tiles_w, tiles_hw;            // 16 x 8 tiles per plane
+  int kd, dmin;                     // taps along d: offsets dmin .. dmin + kd - 1
+  int Cn, n_tile, kchunks;
+  int seg_len, nseg;                // column segments
+  int total_units;                  // N * tiles_hw * nseg
+  int NPR;                          // plane ring depth (>= kd + 1)
+  int ostep, od0, oh0, ow0;
+  long long osn, osd, osh, osw;
+  void* out;
+  int out_bf16;
+  const float* bias;
+  int act;
+  float slope;
+  double* stats;
+  int* err;
+  uint32_t tmem_cols;
+  int16_t twi[kMaxTaps];            // weight slab of tap td
+  int debug;
+  unsigned long long* dbg;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ ColP P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t slab_bytes = (uint32_t)P.n_tile * 128u;                 // one (tap, channel chunk) weight slab
+  const uint32_t w_bytes = slab_bytes * (uint32_t)(P.kd * P.kchunks);
+  const uint32_t slot_bytes = kABytes * (uint32_t)P.kchunks;             // one plane: 128 positions x 64 ch per chunk
+  uint8_t* wres = smem;
+  uint8_t* ring = smem + w_bytes;
+  uint64_t* p_full = reinterpret_cast<uint64_t*>(ring + (size_t)P.NPR * slot_bytes);
+  uint64_t* p_empty = p_full + P.NPR;
+  uint64_t* w_bar = p_empty + P.NPR;
+  uint64_t* acc_full = w_bar + 1;                // [2]
+  uint64_t* acc_empty = acc_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < P.NPR; ++s) { mbar_init(&p_full[s], 1); mbar_init(&p_empty[s], 1); }
+    mbar_init(w_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // unit -> (n, hw tile, first plane, number of planes)
+  auto unit_coords = [&](int u, int& n, int& h0, int& w0, int& d0, int& len) {
+    const int seg = u % P.nseg; u /= P.nseg;
+    const int j = u % P.tiles_hw;
+    n = u / P.tiles_hw;
+    h0 = (j / P.tiles_w) * 16; w0 = (j % P.tiles_w) * 8;
+    d0 = seg * P.seg_len;
+    len = min(P.seg_len, P.Dl - d0);
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // resident weights: every (tap, chunk) slab once
+      mbar_expect_tx(w_bar, w_bytes);
+      for (int td = 0; td < P.kd; ++td)
+        for (int kc = 0; kc < P.kchunks; ++kc)
+          tma_load_2d(wres + (size_t)(td * P.kchunks + kc) * slab_bytes, &tmB, w_bar, kc * 64, (int)P.twi[td] * P.Cn);
+      int s = 0;
+      uint32_t ph = 0;
+      bool ok = true;
+      for (int u = blockIdx.x; u < P.total_units && ok; u += gridDim.x) {
+        int n, h0, w0, d0, len;
+        unit_coords(u, n, h0, w0, d0, len);
+        const int nplanes = len + P.kd - 1;
+        for (int p = 0; p < nplanes; ++p) {
+          if (!mbar_wait(&p_empty[s], ph ^ 1u, P.err, 31)) { ok = false; break; }
+          mbar_expect_tx(&p_full[s], slot_bytes);
+          for (int kc = 0; kc < P.kchunks; ++kc)
+            tma_load_5d(ring + (size_t)s * slot_bytes + (size_t)kc * kABytes, &tmA, &p_full[s], kc * 64, w0, h0,
+                        d0 + P.dmin + p, n);
+          if (++s == P.NPR) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc(P.n_tile, 0, 0);
+      const uint64_t desc0 = desc_kmajor_sw128(0);
+      const uint32_t ring_u = smem_u32(ring) >> 4, wres_u = smem_u32(wres) >> 4;
+      const uint32_t slot_u = slot_bytes >> 4, slab_u = slab_bytes >> 4, chunk_u = kABytes >> 4;
+      const int kd = P.kd, kchunks = P.kchunks, NPR = P.NPR;
+      bool ok = mbar_wait(w_bar, 0, P.err, 32);
+      tc_fence_after();
+      int s_old = 0;                 // ring slot of the oldest plane of the current tile
+      int s_new = 0;                 // ring slot (and phase) of the next plane to wait for
+      uint32_t ph_new = 0;
+      int jt = 0;                    // tiles issued by this CTA (accumulator buffer / phase)
+      const bool prof = (P.debug & 2) != 0;
+      long long t_wacc = 0, t_wp = 0, t_begin = prof ? clock64() : 0;
+      for (int u = blockIdx.x; u < P.total_units && ok; u += gridDim.x) {
+        int n, h0, w0, d0, len;
+        unit_coords(u, n, h0, w0, d0, len);
+        int have = 0;                // planes of this unit already waited for
+        for (int j = 0; j < len && ok; ++j, ++jt) {
+          const int buf = jt & 1;
+          const uint32_t aph = ((uint32_t)jt >> 1) & 1u;
+          const long long t0 = prof ? clock64() : 0;
+          if (!mbar_wait(&acc_empty[buf], aph ^ 1u, P.err, 34)) { ok = false; break; }
+          const long long t1 = prof ? clock64() : 0;
+          while (have < j + kd) {    // first tile of a unit: kd planes; afterwards one new plane per tile
+            if (!mbar_wait(&p_full[s_new], ph_new, P.err, 35)) { ok = false; break; }
+            if (++s_new == NPR) { s_new = 0; ph_new ^= 1u; }
+            ++have;
+          }
+          if (prof) { t_wacc += t1 - t0; t_wp += clock64() - t1; }
+          if (!ok) break;
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * P.n_tile);
+          uint32_t acc = 0;
+          int s = s_old;
+          uint32_t b_u = wres_u;
+          for (int td = 0; td < kd; ++td) {
+            uint32_t a_u = ring_u + (uint32_t)s * slot_u;
+            for (int kc = 0; kc < kchunks; ++kc, a_u += chunk_u, b_u += slab_u) {
+              const uint64_t ad = desc0 | (uint64_t)(a_u & 0x3FFFu);
+              const uint64_t bd = desc0 | (uint64_t)(b_u & 0x3FFFu);
+              umma_f16(d_tmem, ad, bd, idesc, acc);
+              umma_f16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+              umma_f16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+              umma_f16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+              acc = 1u;
+            }
+            if (++s == NPR) s = 0;
+          }
+          umma_commit(&acc_full[buf]);
+          // the oldest plane is dead after this tile; after the unit's last tile so are the other kd - 1
+          const int nrel = (j == len - 1) ? kd : 1;
+          for (int r = 0; r < nrel; ++r) {
+            umma_commit(&p_empty[s_old]);
+            if (++s_old == NPR) s_old = 0;
+          }
+        }
+      }
+      if (prof) {
+        atomicAdd(P.dbg + 3, (unsigned long long)(clock64() - t_begin)); atomicAdd(P.dbg + 6, (unsigned long long)t_wacc);
+        atomicAdd(P.dbg + 7, (unsigned long long)t_wp); atomicAdd(P.dbg + 5, 1ull); atomicAdd(P.dbg + 1, (unsigned long long)jt);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int nchunks = P.n_tile / 32;
+    double st_s[8], st_q[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { st_s[c] = 0.0; st_q[c] = 0.0; }
+    int st_n = -1;
+    const EpiArgs E{P.out, P.out_bf16, P.bias, P.act, P.slope, P.stats != nullptr};
+    int jt = 0;
+    bool ok = true;
+    for (int u = blockIdx.x; u < P.total_units && ok; u += gridDim.x) {
+      int n, h0, w0, d0, len;
+      unit_coords(u, n, h0, w0, d0, len);
+      const int lh = h0 + (row >> 3), lw = w0 + (row & 7);
+      const bool valid = lw < P.Wl && lh < P.Hl;
+      if (P.stats && n != st_n) { epilogue_flush_stats(P.stats, st_n, P.Cn, 0, nchunks, lane, st_s, st_q); st_n = n; }
+      for (int j = 0; j < len && ok; ++j, ++jt) {
+        const int buf = jt & 1;
+        const uint32_t aph = ((uint32_t)jt >> 1) & 1u;
+        const long long obase = (long long)n * P.osn + (long long)((d0 + j) * P.ostep + P.od0) * P.osd +
+                                (long long)(lh * P.ostep + P.oh0) * P.osh + (long long)(lw * P.ostep + P.ow0) * P.osw;
+        ok = mbar_wait(&acc_full[buf], aph, P.err, 33);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * P.n_tile);
+        uint64_t* rel_bar = &acc_empty[buf];
+        epilogue_tile(E, t_addr, nchunks, valid, obase, 0, lane, st_s, st_q, [&]() {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(rel_bar);
+        });
+      }
+    }
+    if (P.stats) epilogue_flush_stats(P.stats, st_n, P.Cn, 0, nchunks, lane, st_s, st_q);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, P.tmem_cols);
+}
+
+// Eligibility + geometry: unit A step, taps along d only forming a contiguous range, one output-channel tile,
+// weights + a plane ring that fit shared memory.
+inline bool col_setup(const GatherLaunch& L, int n, int ck, int cn, ColP& P) {
+  if (L.astep != 1 || L.taps.size() < 2 || (int)L.taps.size() > kMaxTaps) return false;
+  int lo = 1 << 30, hi = -(1 << 30);
+  for (const Tap& t : L.taps) {
+    if (t.dh != 0 || t.dw != 0) return false;
+    if (t.dd < lo) lo = t.dd;
+    if (t.dd > hi) hi = t.dd;
+  }
+  const int kd = hi - lo + 1;
+  if (kd != (int)L.taps.size()) return false;
+  const int n_tile = pick_n_tile(cn);
+  if (n_tile == 0 || n_tile != cn || ck % 64 != 0) return false;
+  P.kd = kd; P.dmin = lo;
+  for (int i = 0; i < kMaxTaps; ++i) P.twi[i] = -1;
+  for (const Tap& t : L.taps) {
+    if (P.twi[t.dd - lo] != -1) return false;
+    P.twi[t.dd - lo] = (int16_t)t.widx;
+  }
+  P.Dl = L.dims[0]; P.Hl = L.dims[1]; P.Wl = L.dims[2]; P.N = n;
+  P.Cn = cn; P.n_tile = n_tile; P.kchunks = ck / 64;
+  P.tiles_w = (P.Wl + 7) / 8; P.tiles_hw = ((P.Hl + 15) / 16) * P.tiles_w;
+  const size_t budget = kSmemLimit - 2048;
+  const size_t w_bytes = (size_t)kd * P.kchunks * n_tile * 128;
+  const size_t slot = (size_t)kABytes * P.kchunks;
+  if (w_bytes + (size_t)(kd + 1) * slot > budget) return false;
+  int npr = (int)((budget - w_bytes) / slot);
+  if (npr > kd + 6) npr = kd + 6;
+  P.NPR = npr;
+  // segments: aim at >= 6 units per SM, but keep them long enough to amortise the kd - 1 warm-up planes
+  const long long cols = (long long)n * P.tiles_hw;
+  long long nseg = ((long long)num_sms() * 6 + cols - 1) / cols;
+  const long long max_seg = P.Dl / (2 * kd) > 1 ? P.Dl / (2 * kd) : 1;
+  if (nseg > max_seg) nseg = max_seg;
+  if (nseg < 1) nseg = 1;
+  P.seg_len = (int)((P.Dl + nseg - 1) / nseg);
+  P.nseg = (P.Dl + P.seg_len - 1) / P.seg_len;
+  const long long units = cols * P.nseg;
+  if (units >= (1ll << 31)) return false;
+  P.total_units = (int)units;
+  return true;
+}
+
+inline int run_gather_col(const GatherPlan& plan, const GatherLaunch& L, ColP& P, const GatherRun& R, const CUtensorMap& tmB,
+                          cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    attr_set = true;
+  }
+  P.ostep = L.ostep; P.od0 = L.o0[0]; P.oh0 = L.o0[1]; P.ow0 = L.o0[2];
+  P.osw = plan.cn;
+  P.osh = (long long)plan.odims[2] * P.osw;
+  P.osd = (long long)plan.odims[1] * P.osh;
+  P.osn = (long long)plan.odims[0] * P.osd;
+  P.out = R.out; P.out_bf16 = R.out_bf16;
+  P.bias = R.bias; P.act = R.act; P.slope = R.slope;
+  P.stats = R.stats; P.err = tc_err_flag();
+  { const char* e = getenv("MRA_GATHER_DEBUG"); P.debug = e ? atoi(e) : 0; }
+  P.dbg = tc_dbg_counters();
+  P.tmem_cols = pow2_cols(2 * P.n_tile);
+  CUtensorMap tmA;
+  if (int rc = make_act_map(&tmA, R.a, plan.n, plan.adims[0], plan.adims[1], plan.adims[2], plan.ck, 8, 16, 1, 1)) return rc;
+  const size_t smem = (size_t)P.kd * P.kchunks * P.n_tile * 128 + (size_t)P.NPR * kABytes * P.kchunks + 1024 + 512;
+  const int ctas = P.total_units < num_sms() ? P.total_units : num_sms();
+  gather_col_kernel<<<ctas, kThreads, smem, st>>>(tmA, tmB, P);
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace mra

@@ -20,6 +20,7 @@
 // 6 = TMA producer of the plane ring.  Persistent over tiles, accumulators double-buffered in TMEM.
 #pragma once
 #include "conv_tc.cuh"
+#include "conv_tc_col.cuh"
 
 namespace mra {
 namespace tc {
@@ -220,7 +221,7 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const bool dbg_nob = (P.debug & 4) != 0, dbg_nop = (P.debug & 8) != 0;     // timing experiments: no weight / plane traffic
   if (warp == 6) {
     // ---- plane producer: one halo plane per (work item, channel chunk, td); each CTA loads its own tile's planes
-    if (lane == 0 && !dbg_nop) {
+    if (elect_one() && !dbg_nop) {
       int s = 0;
       uint32_t ph = 0;
       bool ok = true;
@@ -239,7 +240,7 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else if (warp == 0) {
     // ---- weight producer: one (64 x n_tile) slab per (work item, channel chunk, tap); pair: each CTA its half
-    if (lane == 0 && !dbg_nob) {
+    if (elect_one() && !dbg_nob) {
       int s = 0;
       uint32_t ph = 0;
       bool ok = true;
@@ -266,7 +267,7 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (prof) { atomicAdd(P.dbg + 0, (unsigned long long)t_wait); atomicAdd(P.dbg + 1, (unsigned long long)(clock64() - t_begin)); }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
+    if (elect_one() && leader) {
       // The issue loop is a single thread: keep it to a few dozen instructions per stage (no divisions, the
       // descriptors advance by adding constants to their 16-byte-unit address field).
       const uint32_t idesc_full = make_idesc_m(128 * kCtas, P.n_tile), idesc_half = make_idesc_m(128 * kCtas, P.n_tile >> 1);
@@ -532,7 +533,16 @@ inline int run_gather_tc(const GatherPlan& plan, const GatherRun& R, cudaStream_
   const char* gm = getenv("MRA_GATHER_MODE");
   const bool force_v1 = gm && !strcmp(gm, "v1");
   const bool no_pair = gm && !strcmp(gm, "single");
+  const bool no_col = gm && !strcmp(gm, "nocol");
   for (const GatherLaunch& L : plan.launches) {
+    bool slabs_ok = true;
+    for (const Tap& t : L.taps) if (t.widx >= R.slabs) slabs_ok = false;
+    ColP CP;
+    memset(&CP, 0, sizeof(CP));
+    if (!force_v1 && !no_col && slabs_ok && col_setup(L, plan.n, plan.ck, plan.cn, CP)) {
+      if (int rc = run_gather_col(plan, L, CP, R, tmB, st)) return rc;
+      continue;
+    }
     HaloP P;
     memset(&P, 0, sizeof(P));
     // the halo kernel pays off when several taps share a plane (kh * kw >= 4)

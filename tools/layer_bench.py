@@ -29,5 +29,16 @@ for name, fn in (("fprop", lambda: I.conv_fprop(x, w, None, g, want_stats=g.cout
     if c[5]:
         print("   per CTA: producer wait %.0f / total %.0f clk ; mma wait %.0f / total %.0f clk ; epilogue %.0f clk ; CTAs %d" % (
             c[0] / c[5], c[1] / c[5], c[2] / c[5], c[3] / c[5], c[4] / c[5], c[5]))
+        print("   (col kernel: tiles per CTA %.0f)" % (c[1] / c[5]))
         print("   mma wait for a free accumulator %.0f clk ; mma wait for a halo plane %.0f clk" % (c[6] / c[5], c[7] / c[5]))
     print("%s %.4f ms  %.1f TFLOP/s  (flag %d)" % (name, t, 2 * macs / t / 1e9, I.tc_error()), flush=True)
+if os.environ.get("KERNELS"):
+    from torch.profiler import ProfilerActivity, profile
+    for name, fn in (("fprop", lambda: I.conv_fprop(x, w, None, g, want_stats=g.cout > 1)), ("dgrad", lambda: I.conv_dgrad(dy, wT, g, dims)),
+                     ("wgrad", lambda: I.conv_wgrad(x, dy, g))):
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn(); torch.cuda.synchronize()
+        print("--", name)
+        for e in prof.key_averages():
+            if e.device_time_total > 0:
+                print("   %-70s %8.1f us x%d" % (e.key[:70], e.device_time_total / max(1, e.count), e.count))
