@@ -35,7 +35,11 @@ enum { MRA_ACT_NONE = 0, MRA_ACT_RELU = 1, MRA_ACT_LRELU = 2, MRA_ACT_TANH = 3, 
 enum { MRA_LOSS_L1 = 0, MRA_LOSS_MSE_CONST = 1, MRA_LOSS_BCE_CONST = 2 };
 enum {
   MRA_CONV_FORCE_NAIVE = 1,          /* use the CUDA-core kernels even where tcgen05 is eligible */
-  MRA_CONV_ACCUMULATE  = 2           /* wgrad: add into dw/dbias instead of overwriting */
+  MRA_CONV_ACCUMULATE  = 2,          /* wgrad: add into dw/dbias instead of overwriting */
+  MRA_CONV_WS_REUSE    = 4           /* the workspace still holds the channel-expanded operand that an earlier call of
+                                        this layer on the SAME tensors left at its start (mra_conv3d_lowering() != 0:
+                                        fprop -> wgrad for lowerings 1 and 3, wgrad -> dgrad for lowering 2): skip the
+                                        expansion pass */
 };
 
 /* nn.Conv3d / nn.ConvTranspose3d geometry (cubic kernel, isotropic stride, implicit zero padding).
@@ -149,6 +153,11 @@ int mra_window_extract(const float* vol, int X, int Y, int Z, int i0, int j0, in
 int mra_window_accumulate(const void* pred, int dtype, float* label, float* weight, int X, int Y,
                           int Z, int i0, int j0, int k0, int px, int py, int pz, mra_stream_t stream);
 int mra_window_finalize(float* label, const float* weight, int64_t numel, mra_stream_t stream);
+
+/* Which channel-expanded lowering (csrc/conv_special.cuh) serves this layer: 0 none, 1 stem (Cin = 1, k x k x k),
+ * 2 head (Cout = 1), 3 im2col (Cin = 1, strided).  Callers use it to share one workspace between the calls of a
+ * layer (MRA_CONV_WS_REUSE); the workspace must then be max over the calls' mra_conv3d_workspace_size(). */
+int mra_conv3d_lowering(const mra_conv_desc* d);
 
 /* Host-only introspection of the implicit-GEMM plan (no GPU needed; used by the CPU tests).
  * Fills `out` (capacity `cap` int32 words) with the launch list and returns the number of words

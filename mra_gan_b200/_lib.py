@@ -12,7 +12,7 @@ from . import build as _build
 MRA_F32, MRA_BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
 LOSS_L1, LOSS_MSE_CONST, LOSS_BCE_CONST = 0, 1, 2
-CONV_FORCE_NAIVE, CONV_ACCUMULATE = 1, 2
+CONV_FORCE_NAIVE, CONV_ACCUMULATE, CONV_WS_REUSE = 1, 2, 4
 
 
 class ConvDesc(C.Structure):
@@ -45,6 +45,7 @@ _SIGNATURES = {
     "mra_conv3d_wgrad": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, C.c_size_t, _P], C.c_int),
     "mra_conv3d_workspace_size": ([C.POINTER(ConvDesc), _I], C.c_size_t),
     "mra_conv3d_uses_tensor_cores": ([C.POINTER(ConvDesc), _I], C.c_int),
+    "mra_conv3d_lowering": ([C.POINTER(ConvDesc)], C.c_int),
     "mra_pack_weight_t": ([_P, _I, _P, _I, _I, _I, _I, _P], C.c_int),
     "mra_convert": ([_P, _I, _P, _I, _L, _P], C.c_int),
     "mra_inorm_stats": ([C.POINTER(NormDesc), _P, _P, _P], C.c_int),

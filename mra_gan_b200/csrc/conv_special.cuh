@@ -24,54 +24,113 @@
 namespace mra {
 namespace special {
 
-// out[n,d,ho,wo,kh*8+kw] = src[n,d,ho+sgn*kh+off,wo+sgn*kw+off] (0 out of range / kh,kw >= k).  One thread = one kh row (8 ch).
+// out[n,d,ho,wo,kh*8+kw] = src[n,d,ho+sgn*kh+off,wo+sgn*kw+off] (0 out of range / kh,kw >= k).
+// One block = one output line (n*d row r, ho): the <= 8 source lines it touches are staged in shared memory
+// (zero outside the volume), then one thread per (wo, kh) writes 8 channels = 16 B; a warp writes 512 contiguous bytes.
 __global__ void __launch_bounds__(256) expand_hw_kernel(const bf16* __restrict__ src, bf16* __restrict__ out, long long rows /*N*D*/,
                                                          int Hs, int Ws, int Ho, int Wo, int k, int sgn, int off) {
-  const long long total = rows * Ho * Wo * 8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int kh = (int)(i & 7);
-    long long p = i >> 3;
-    const int wo = (int)(p % Wo); p /= Wo;
-    const int ho = (int)(p % Ho);
-    const long long r = p / Ho;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    const int hs = ho + sgn * kh + off;
-    if (kh < k && hs >= 0 && hs < Hs) {
-      const bf16* row = src + (r * Hs + hs) * Ws;
-#pragma unroll
-      for (int kw = 0; kw < 8; ++kw) {
-        const int ws = wo + sgn * kw + off;
-        if (kw < k && ws >= 0 && ws < Ws) v[kw] = __bfloat162float(row[ws]);
-      }
+  extern __shared__ bf16 s_lines[];                 // [8][Wo + 8]  (line kh holds source columns wo + sgn*kw + off for all wo, kw)
+  const int pitch = Wo + 8;
+  const long long nlines = rows * Ho;
+  for (long long line = blockIdx.x; line < nlines; line += gridDim.x) {
+    const int ho = (int)(line % Ho);
+    const long long r = line / Ho;
+    // stage: s_lines[kh][j] = src[r][ho + sgn*kh + off][j + base], base = off - (sgn < 0 ? 7 : 0), j in [0, Wo + 8)
+    const int base = off - (sgn < 0 ? 7 : 0);
+    for (int i = threadIdx.x; i < 8 * pitch; i += blockDim.x) {
+      const int kh = i / pitch, j = i - kh * pitch;
+      const int hs = ho + sgn * kh + off, ws = j + base;
+      bf16 v = __float2bfloat16_rn(0.f);
+      if (kh < k && hs >= 0 && hs < Hs && ws >= 0 && ws < Ws) v = src[(r * Hs + hs) * Ws + ws];
+      s_lines[i] = v;
     }
-    Vec8<bf16>::store(out + (i >> 3) * 64 + kh * 8, v);
+    __syncthreads();
+    bf16* oline = out + line * Wo * 64;
+    for (int i = threadIdx.x; i < Wo * 8; i += blockDim.x) {
+      const int kh = i & 7, wo = i >> 3;
+      const bf16* sl = s_lines + kh * pitch + wo - base + off;      // + sgn*kw walks the line
+      float v[8];
+#pragma unroll
+      for (int kw = 0; kw < 8; ++kw) v[kw] = (kw < k && kh < k) ? __bfloat162float(sl[sgn * kw]) : 0.f;
+      Vec8<bf16>::store(oline + (long long)wo * 64 + kh * 8, v);
+    }
+    __syncthreads();
   }
 }
 
-// out[n,d,ho,wo] = act(bias + sum_{kh,kw<k} Z[n,d,ho+sgn*kh,wo+sgn*kw,kh*8+kw])
+// out[n,d,ho,wo] = act(bias + sum_{kh,kw<k} Z[n,d,ho+sgn*kh+off,wo+sgn*kw+off,kh*8+kw])
+// One block = a band of output lines of one (n, d) plane.  Every Z line of the band is read from global memory ONCE
+// (coalesced 16-byte loads) into a padded shared-memory line (position pitch 33 words: conflict-free column reads);
+// thread wo then adds the line's k*k contributions to the <= 8 output lines that are still open, which it keeps in
+// registers (a statically rotated window of 8 partial sums).
 template <typename TZ, typename TO>
 __global__ void __launch_bounds__(256) shift_sum_kernel(const TZ* __restrict__ Z, TO* __restrict__ out, long long rows, int Hz,
                                                          int Wz, int Ho, int Wo, int k, int sgn, int off,
-                                                         const float* __restrict__ bias, int act, float slope) {
-  const long long total = rows * Ho * Wo;
+                                                         const float* __restrict__ bias, int act, float slope, int band) {
+  extern __shared__ uint32_t s_z[];                  // [Wz][33] words: 64 bf16 of one position + 1 pad word
   const float b = bias ? bias[0] : 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int wo = (int)(i % Wo);
-    const int ho = (int)((i / Wo) % Ho);
-    const long long r = i / ((long long)Wo * Ho);
-    float acc = 0.f;
-    for (int kh = 0; kh < k; ++kh) {
-      const int hz = ho + sgn * kh + off;
-      if (hz < 0 || hz >= Hz) continue;
-      for (int kw = 0; kw < k; ++kw) {
-        const int wz = wo + sgn * kw + off;
-        if (wz < 0 || wz >= Wz) continue;
-        acc += to_f(Z[((r * Hz + hz) * Wz + wz) * 64 + kh * 8 + kw]);
+  const int nbands = (Ho + band - 1) / band;
+  const long long nwork = rows * nbands;
+  for (long long wk = blockIdx.x; wk < nwork; wk += gridDim.x) {
+    const int bi = (int)(wk % nbands);
+    const long long r = wk / nbands;
+    const int ho0 = bi * band, ho1 = min(Ho, ho0 + band);
+    // Z lines that feed output lines [ho0, ho1): hz = ho + sgn*kh + off, kh in [0, k)
+    const int hz_lo = sgn > 0 ? ho0 + off : ho0 - (k - 1) + off;
+    const int hz_hi = sgn > 0 ? ho1 - 1 + (k - 1) + off : ho1 - 1 + off;       // inclusive
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    // process the lines in groups of 8 so that the rotating window index is static
+    for (int hz0 = hz_lo; hz0 <= hz_hi; hz0 += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int hz = hz0 + u;
+        if (hz > hz_hi) break;
+        __syncthreads();
+        const bool in_range = hz >= 0 && hz < Hz;
+        if (in_range) {
+          const uint4* gl = reinterpret_cast<const uint4*>(Z + ((r * Hz + hz) * (long long)Wz) * 64);
+          for (int i = threadIdx.x; i < Wz * 8; i += blockDim.x) {        // 8 x 16 B per position
+            const uint4 v = __ldg(gl + i);
+            uint32_t* d = s_z + (i >> 3) * 33 + (i & 7) * 4;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+          }
+        }
+        __syncthreads();
+        // contributions of line hz: to output line ho = hz - off - sgn*kh  for kh in [0, k)
+        const int wo = threadIdx.x;                                        // Wo <= blockDim.x (checked on host)
+        if (wo < Wo) {
+#pragma unroll
+          for (int kh = 0; kh < 8; ++kh) {
+            if (kh >= k) break;
+            // window slot of output line ho: lines are visited in increasing hz; slot = (u - sgn*kh) mod 8 is static
+            const int slot = ((u - sgn * kh) % 8 + 8) % 8;
+            float s = 0.f;
+            if (in_range) {
+#pragma unroll
+              for (int kw = 0; kw < 8; ++kw) {
+                if (kw >= k) break;
+                const int wz = wo + sgn * kw + off;
+                if (wz >= 0 && wz < Wz) {
+                  const uint32_t wrd = s_z[wz * 33 + ((kh * 8 + kw) >> 1)];
+                  s += __uint_as_float((kw & 1) ? (wrd & 0xffff0000u) : (wrd << 16));
+                }
+              }
+            }
+            acc[slot] += s;
+          }
+          // the output line completed by this Z line: for sgn > 0 it is ho = hz - off - (k-1) (its last contributor is
+          // kh = k-1); for sgn < 0 it is ho = hz - off (last contributor kh = 0)
+          const int ho_done = sgn > 0 ? hz - off - (k - 1) : hz - off;
+          const int slot_done = sgn > 0 ? ((u - (k - 1)) % 8 + 8) % 8 : u;
+          if (ho_done >= ho0 && ho_done < ho1)
+            out[(r * Ho + ho_done) * (long long)Wo + wo] = from_f<TO>(apply_act(acc[slot_done] + b, act, slope));
+          acc[slot_done] = 0.f;
+        }
       }
     }
-    out[i] = from_f<TO>(apply_act(acc + b, act, slope));
+    __syncthreads();
   }
 }
 
@@ -181,6 +240,30 @@ __global__ void im2col_dw_kernel(const float* __restrict__ dwe, float* __restric
   }
 }
 
+inline int launch_expand_hw(const bf16* src, bf16* out, long long rows, int Hs, int Ws, int Ho, int Wo, int k, int sgn, int off,
+                            cudaStream_t st) {
+  const long long nlines = rows * Ho;
+  long long grid = nlines < (long long)num_sms() * 8 ? nlines : (long long)num_sms() * 8;
+  if (grid < 1) grid = 1;
+  const size_t smem = (size_t)8 * (Wo + 8) * sizeof(bf16);
+  expand_hw_kernel<<<(unsigned)grid, 256, smem, st>>>(src, out, rows, Hs, Ws, Ho, Wo, k, sgn, off);
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+inline int launch_shift_sum(const bf16* Z, bf16* out, long long rows, int Hz, int Wz, int Ho, int Wo, int k, int sgn, int off,
+                            const float* bias, int act, float slope, cudaStream_t st) {
+  MRA_REQUIRE(Wo <= 256 && k <= 8, "shift_sum: line longer than a block (Wo = %d)", Wo);
+  const int band = 32;
+  const long long nwork = rows * ((Ho + band - 1) / band);
+  long long grid = nwork < (long long)num_sms() * 8 ? nwork : (long long)num_sms() * 8;
+  if (grid < 1) grid = 1;
+  const size_t smem = (size_t)Wz * 33 * sizeof(uint32_t);
+  MRA_REQUIRE(smem <= 48 * 1024, "shift_sum: Z line does not fit shared memory (Wz = %d)", Wz);
+  shift_sum_kernel<bf16, bf16><<<(unsigned)grid, 256, smem, st>>>(Z, out, rows, Hz, Wz, Ho, Wo, k, sgn, off, bias, act, slope, band);
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+
 struct Workspace {
   char* base; size_t size, off;
   void* take(size_t bytes) {
@@ -194,11 +277,11 @@ struct Workspace {
 
 inline bool stem_eligible(const mra_conv_desc& d) {
   return d.dtype == MRA_BF16 && !(d.flags & MRA_CONV_FORCE_NAIVE) && !d.transposed && d.stride == 1 && d.pad == 0 &&
-         d.cin == 1 && d.k >= 2 && d.k <= 8 && tc::pick_n_tile(d.cout) > 0;
+         d.cin == 1 && d.k >= 2 && d.k <= 8 && d.win <= 256 && tc::pick_n_tile(d.cout) > 0;
 }
 inline bool head_eligible(const mra_conv_desc& d) {
   return d.dtype == MRA_BF16 && !(d.flags & MRA_CONV_FORCE_NAIVE) && !d.transposed && d.stride == 1 && d.pad >= 0 &&
-         d.pad < d.k && d.cout == 1 && d.k >= 2 && d.k <= 8 && d.cin % 64 == 0;
+         d.pad < d.k && d.cout == 1 && d.k >= 2 && d.k <= 8 && d.win <= 256 && d.cin % 64 == 0;
 }
 
 inline bool im2col_eligible(const mra_conv_desc& d) {
@@ -291,8 +374,10 @@ inline int im2col_wgrad(const mra_conv_desc& d, const void* x, const void* dy, f
   const long long pos = (long long)d.n * d.dout * d.hout * d.wout;
   MRA_WS_TAKE(E, bf16, (size_t)pos * 64 * 2);
   MRA_WS_TAKE(dWe, float, (size_t)64 * d.cout * 4);
-  im2col1_kernel<<<sgrid(pos * 8), 256, 0, st>>>((const bf16*)x, E, d.n, d.din, d.hin, d.win, d.dout, d.hout, d.wout, d.k, d.stride, d.pad);
-  MRA_LAUNCH_CHECK();
+  if (!(d.flags & MRA_CONV_WS_REUSE)) {
+    im2col1_kernel<<<sgrid(pos * 8), 256, 0, st>>>((const bf16*)x, E, d.n, d.din, d.hin, d.win, d.dout, d.hout, d.wout, d.k, d.stride, d.pad);
+    MRA_LAUNCH_CHECK();
+  }
   MRA_CHECK_CUDA(cudaMemsetAsync(dWe, 0, (size_t)64 * d.cout * 4, st));
   WgradPlan plan;
   MRA_REQUIRE(build_wgrad_plan(im2col_geom(d), plan), "im2col wgrad plan");
@@ -324,8 +409,7 @@ inline int stem_fprop(const mra_conv_desc& d, const void* x, const void* w, cons
   const long long rows = (long long)d.n * d.din;
   MRA_WS_TAKE(E, bf16, (size_t)rows * d.hout * d.wout * 64 * 2);
   MRA_WS_TAKE(B, bf16, (size_t)d.k * d.cout * 64 * 2);
-  expand_hw_kernel<<<sgrid(rows * d.hout * d.wout * 8), 256, 0, st>>>((const bf16*)x, E, rows, d.hin, d.win, d.hout, d.wout, d.k, +1, 0);
-  MRA_LAUNCH_CHECK();
+  MRA_REQUIRE(launch_expand_hw((const bf16*)x, E, rows, d.hin, d.win, d.hout, d.wout, d.k, +1, 0, st) == 0, "expand_hw launch");
   wexp_kernel<<<sgrid((long long)d.k * d.cout * 64), 256, 0, st>>>((const bf16*)w, B, d.k, d.cout, 0);
   MRA_LAUNCH_CHECK();
   GatherPlan plan;
@@ -339,8 +423,8 @@ inline int stem_wgrad(const mra_conv_desc& d, const void* x, const void* dy, flo
   const long long rows = (long long)d.n * d.din;
   MRA_WS_TAKE(E, bf16, (size_t)rows * d.hout * d.wout * 64 * 2);
   MRA_WS_TAKE(dWe, float, (size_t)d.k * d.cout * 64 * 4);
-  expand_hw_kernel<<<sgrid(rows * d.hout * d.wout * 8), 256, 0, st>>>((const bf16*)x, E, rows, d.hin, d.win, d.hout, d.wout, d.k, +1, 0);
-  MRA_LAUNCH_CHECK();
+  if (!(d.flags & MRA_CONV_WS_REUSE))
+    MRA_REQUIRE(launch_expand_hw((const bf16*)x, E, rows, d.hin, d.win, d.hout, d.wout, d.k, +1, 0, st) == 0, "expand_hw launch");
   MRA_CHECK_CUDA(cudaMemsetAsync(dWe, 0, (size_t)d.k * d.cout * 64 * 4, st));
   WgradPlan plan;
   MRA_REQUIRE(build_wgrad_plan(stem_geom(d), plan), "stem wgrad plan");
@@ -361,9 +445,7 @@ inline int stem_dgrad(const mra_conv_desc& d, const void* dy, const void* wT, vo
   MRA_REQUIRE(build_gather_plan(stem_geom(d), 1, plan), "stem dgrad plan");
   tc::GatherRun R{dy, BT, d.k, nullptr, Z, 1, MRA_ACT_NONE, 0.f, nullptr};
   if (int rc = tc::run_gather_tc(plan, R, st)) return rc;
-  shift_sum_kernel<bf16, bf16><<<sgrid(rows * d.hin * d.win), 256, 0, st>>>(Z, (bf16*)dx, rows, d.hout, d.wout, d.hin, d.win, d.k, -1, 0,
-                                                                              nullptr, MRA_ACT_NONE, 0.f);
-  MRA_LAUNCH_CHECK();
+  if (int rc = launch_shift_sum(Z, (bf16*)dx, rows, d.hout, d.wout, d.hin, d.win, d.k, -1, 0, nullptr, MRA_ACT_NONE, 0.f, st)) return rc;
   return 0;
 }
 
@@ -381,9 +463,7 @@ inline int head_fprop(const mra_conv_desc& d, const void* x, const void* w, cons
   MRA_REQUIRE(build_gather_plan(head_geom(d), 0, plan), "head plan");
   tc::GatherRun R{x, B, d.k, nullptr, Z, 1, MRA_ACT_NONE, 0.f, nullptr};
   if (int rc = tc::run_gather_tc(plan, R, st)) return rc;
-  shift_sum_kernel<bf16, bf16><<<sgrid(rows * d.hout * d.wout), 256, 0, st>>>(Z, (bf16*)y, rows, d.hin, d.win, d.hout, d.wout, d.k, +1, -d.pad,
-                                                                                bias, d.act, d.slope);
-  MRA_LAUNCH_CHECK();
+  if (int rc = launch_shift_sum(Z, (bf16*)y, rows, d.hin, d.win, d.hout, d.wout, d.k, +1, -d.pad, bias, d.act, d.slope, st)) return rc;
   return 0;
 }
 
@@ -392,8 +472,8 @@ inline int head_dgrad(const mra_conv_desc& d, const void* dy, const void* wT, vo
   const long long rows = (long long)d.n * d.dout;
   MRA_WS_TAKE(E, bf16, (size_t)rows * d.hin * d.win * 64 * 2);
   MRA_WS_TAKE(BT, bf16, (size_t)d.k * d.cin * 64 * 2);
-  expand_hw_kernel<<<sgrid(rows * d.hin * d.win * 8), 256, 0, st>>>((const bf16*)dy, E, rows, d.hout, d.wout, d.hin, d.win, d.k, -1, d.pad);
-  MRA_LAUNCH_CHECK();
+  if (!(d.flags & MRA_CONV_WS_REUSE))
+    MRA_REQUIRE(launch_expand_hw((const bf16*)dy, E, rows, d.hout, d.wout, d.hin, d.win, d.k, -1, d.pad, st) == 0, "expand_hw launch");
   wexp_kernel<<<sgrid((long long)d.k * d.cin * 64), 256, 0, st>>>((const bf16*)wT, BT, d.k, d.cin, 0);      // [kd][ci][c]
   MRA_LAUNCH_CHECK();
   GatherPlan plan;
@@ -407,8 +487,7 @@ inline int head_wgrad(const mra_conv_desc& d, const void* x, const void* dy, flo
   const long long rows = (long long)d.n * d.dout;
   MRA_WS_TAKE(E, bf16, (size_t)rows * d.hin * d.win * 64 * 2);
   MRA_WS_TAKE(dWe, float, (size_t)d.k * d.cin * 64 * 4);
-  expand_hw_kernel<<<sgrid(rows * d.hin * d.win * 8), 256, 0, st>>>((const bf16*)dy, E, rows, d.hout, d.wout, d.hin, d.win, d.k, -1, d.pad);
-  MRA_LAUNCH_CHECK();
+  MRA_REQUIRE(launch_expand_hw((const bf16*)dy, E, rows, d.hout, d.wout, d.hin, d.win, d.k, -1, d.pad, st) == 0, "expand_hw launch");
   MRA_CHECK_CUDA(cudaMemsetAsync(dWe, 0, (size_t)d.k * d.cin * 64 * 4, st));
   WgradPlan plan;
   MRA_REQUIRE(build_wgrad_plan(head_geom(d), plan), "head wgrad plan");

@@ -66,6 +66,14 @@ size_t mra_conv3d_workspace_size(const mra_conv_desc* d, int which) {
   return d ? special::workspace_bytes(*d, which) : 0;
 }
 
+int mra_conv3d_lowering(const mra_conv_desc* d) {
+  if (!d) return 0;
+  if (special::im2col_eligible(*d)) return 3;
+  if (special::stem_eligible(*d)) return 1;
+  if (special::head_eligible(*d)) return 2;
+  return 0;
+}
+
 int mra_conv3d_uses_tensor_cores(const mra_conv_desc* d, int which) {
   if (!d) return 0;
   if (special::stem_eligible(*d) || special::head_eligible(*d) || special::im2col_eligible(*d)) return 1;

@@ -27,7 +27,17 @@ class ConvFn(torch.autograd.Function):
         I = ops.impl()
         g = mod.geom
         wc = mod.packed_weight(x.dtype)
-        y, stats = I.conv_fprop(x, wc, bias.detach() if bias is not None else None, g, act, slope, want_stats)
+        # channel-expanded lowerings (stem / head / PatchGAN layer 0): one workspace shared by the layer's calls so
+        # that the expanded operand is built once (fprop -> wgrad, or wgrad -> dgrad)
+        low, ws = 0, None
+        if x.dtype == torch.bfloat16 and min(g.cin, g.cout) == 1 and hasattr(I, "conv_shared_workspace"):
+            low, ws = I.conv_shared_workspace(g, x.shape[0], tuple(x.shape[1:4]), x.dtype, x.device)
+        keep = low in (1, 3) and ctx.needs_input_grad[1]
+        if keep:
+            y, stats = I.conv_fprop(x, wc, bias.detach() if bias is not None else None, g, act, slope, want_stats, ws=ws)
+        else:
+            y, stats = I.conv_fprop(x, wc, bias.detach() if bias is not None else None, g, act, slope, want_stats)
+        ctx.low, ctx.ws = low, (ws if keep else None)
         ctx.mod, ctx.act, ctx.slope, ctx.bias_grad = mod, act, slope, bias_grad
         ctx.in_dims = tuple(x.shape[1:4])
         ctx.save_for_backward(x, y if act != ACT_NONE else None)
@@ -46,13 +56,24 @@ class ConvFn(torch.autograd.Function):
             gy = I.act_bwd(gy, y, ctx.act, ctx.slope)
         dx = dw = db = None
         has_bias = mod.bias is not None
+        ws2 = None
         if ctx.needs_input_grad[1]:
-            dwp, dbv = I.conv_wgrad(x, gy, g, want_bias=has_bias and ctx.bias_grad)
+            if ctx.ws is not None:                       # lowerings 1 / 3: the forward pass left the expanded x in ctx.ws
+                dwp, dbv = I.conv_wgrad(x, gy, g, want_bias=has_bias and ctx.bias_grad, ws=ctx.ws, reuse=True)
+                ctx.ws = None
+            elif ctx.low == 2 and ctx.needs_input_grad[0]:   # head: wgrad expands dy, dgrad reuses it
+                _, ws2 = I.conv_shared_workspace(g, x.shape[0], ctx.in_dims, x.dtype, x.device)
+                dwp, dbv = I.conv_wgrad(x, gy, g, want_bias=has_bias and ctx.bias_grad, ws=ws2)
+            else:
+                dwp, dbv = I.conv_wgrad(x, gy, g, want_bias=has_bias and ctx.bias_grad)
             dw = weight_grad_view(dwp, g.k, g.transposed)
             if has_bias and ctx.needs_input_grad[2]:
                 db = dbv if dbv is not None else torch.zeros_like(mod.bias)
         if ctx.needs_input_grad[0]:
-            dx = I.conv_dgrad(gy, mod.packed_weight_t(gy.dtype), g, ctx.in_dims)
+            if ws2 is not None:
+                dx = I.conv_dgrad(gy, mod.packed_weight_t(gy.dtype), g, ctx.in_dims, ws=ws2, reuse=True)
+            else:
+                dx = I.conv_dgrad(gy, mod.packed_weight_t(gy.dtype), g, ctx.in_dims)
         return dx, dw, db, None, None, None, None, None
 
 

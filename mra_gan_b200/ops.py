@@ -86,14 +86,29 @@ class CudaImpl:
         d.flags = flags | (_lib.CONV_FORCE_NAIVE if self.force_naive else 0)
         return d
 
-    def _workspace(self, d, which, device):
+    def _workspace(self, d, which, device, ws=None):
         nbytes = int(self.L.mra_conv3d_workspace_size(C.byref(d), which))
         if nbytes == 0:
             return None, 0
+        if ws is not None:
+            if ws.numel() < nbytes:
+                raise RuntimeError("shared conv workspace too small")
+            return ws, ws.numel()
         return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
 
+    def conv_shared_workspace(self, g, n, in_dims, dtype, device):
+        """(lowering, workspace) for layers served by a channel-expanded lowering (conv_special.cuh): one buffer
+        big enough for all three calls, so that the expanded operand written by one call (fprop for lowerings
+        1 / 3, wgrad for lowering 2) can be reused by the next (``reuse=True``).  (0, None) for ordinary layers."""
+        d = self._conv_desc(g, n, tuple(in_dims), g.out_dims(tuple(in_dims)), MRA_BF16 if dtype == torch.bfloat16 else MRA_F32)
+        low = int(self.L.mra_conv3d_lowering(C.byref(d)))
+        if low == 0:
+            return 0, None
+        nbytes = max(int(self.L.mra_conv3d_workspace_size(C.byref(d), w)) for w in range(3))
+        return low, torch.empty(nbytes, dtype=torch.uint8, device=device)
+
     # -- convolution family -----------------------------------------------------------------
-    def conv_fprop(self, x, w, bias, g, act=ACT_NONE, slope=0.2, want_stats=False):
+    def conv_fprop(self, x, w, bias, g, act=ACT_NONE, slope=0.2, want_stats=False, ws=None):
         self._need(x, w, bias)
         n, in_dims = x.shape[0], tuple(x.shape[1:4])
         assert x.shape[4] == g.cin and w.shape == (g.taps, g.cout, g.cin) and w.dtype == x.dtype
@@ -101,29 +116,29 @@ class CudaImpl:
         y = torch.empty((n,) + out_dims + (g.cout,), dtype=x.dtype, device=x.device)
         stats = torch.empty((n, g.cout, 2), dtype=torch.float64, device=x.device) if want_stats else None
         d = self._conv_desc(g, n, in_dims, out_dims, _dt(x), act, slope)
-        ws, wsb = self._workspace(d, 0, x.device)
+        ws, wsb = self._workspace(d, 0, x.device, ws)
         _lib.check(self.L.mra_conv3d_fprop(C.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(y), _ptr(stats),
                                            _ptr(ws), wsb, self._stream()), "mra_conv3d_fprop")
         return y, stats
 
-    def conv_dgrad(self, dy, wT, g, in_dims):
+    def conv_dgrad(self, dy, wT, g, in_dims, ws=None, reuse=False):
         self._need(dy, wT)
         n, out_dims = dy.shape[0], tuple(dy.shape[1:4])
         assert dy.shape[4] == g.cout and wT.shape == (g.taps, g.cin, g.cout) and wT.dtype == dy.dtype
         dx = torch.empty((n,) + tuple(in_dims) + (g.cin,), dtype=dy.dtype, device=dy.device)
-        d = self._conv_desc(g, n, tuple(in_dims), out_dims, _dt(dy))
-        ws, wsb = self._workspace(d, 1, dy.device)
+        d = self._conv_desc(g, n, tuple(in_dims), out_dims, _dt(dy), flags=_lib.CONV_WS_REUSE if reuse else 0)
+        ws, wsb = self._workspace(d, 1, dy.device, ws)
         _lib.check(self.L.mra_conv3d_dgrad(C.byref(d), _ptr(dy), _ptr(wT), _ptr(dx), _ptr(ws), wsb, self._stream()),
                    "mra_conv3d_dgrad")
         return dx
 
-    def conv_wgrad(self, x, dy, g, want_bias=False):
+    def conv_wgrad(self, x, dy, g, want_bias=False, ws=None, reuse=False):
         self._need(x, dy)
         n, in_dims, out_dims = x.shape[0], tuple(x.shape[1:4]), tuple(dy.shape[1:4])
         dw = torch.empty((g.taps, g.cout, g.cin), dtype=torch.float32, device=x.device)
         db = torch.empty((g.cout,), dtype=torch.float32, device=x.device) if want_bias else None
-        d = self._conv_desc(g, n, in_dims, out_dims, _dt(x))
-        ws, wsb = self._workspace(d, 2, x.device)
+        d = self._conv_desc(g, n, in_dims, out_dims, _dt(x), flags=_lib.CONV_WS_REUSE if reuse else 0)
+        ws, wsb = self._workspace(d, 2, x.device, ws)
         _lib.check(self.L.mra_conv3d_wgrad(C.byref(d), _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), _ptr(ws), wsb,
                                            self._stream()), "mra_conv3d_wgrad")
         return dw, db
