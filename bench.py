@@ -189,6 +189,8 @@ def run_gpu(args):
     I = ops.impl()
     if world > 1:
         parallel.attach(model)
+    elif not args.no_graphs:
+        model.enable_cuda_graphs(warmup_steps=2)        # the step is replayed as two CUDA graphs after 2 eager steps
 
     g = torch.Generator().manual_seed(1234 + rank)
     shape = (per_gpu_batch, 1, PATCH, PATCH, PATCH)
@@ -225,7 +227,7 @@ def run_gpu(args):
         model.optimize_parameters()
         last_losses.update(model.get_current_losses())   # device -> host read of the 8 losses
 
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 3)):               # >= 3: two eager steps + the capture step of the graph replay
         step_resident()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -233,6 +235,9 @@ def run_gpu(args):
     launches0 = I.launch_count()
     ms_step = timed(step_resident, args.steps)
     launches = (I.launch_count() - launches0) // args.steps
+    graphs = getattr(model, "_graphs", None)
+    if graphs and graphs.get("launches"):
+        launches = graphs["launches"]                   # replayed from the captured graphs: count taken at capture
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if sampler else None
     err = I.tc_error()
@@ -241,6 +246,8 @@ def run_gpu(args):
     vox = global_batch * PATCH ** 3 / (ms_step * 1e-3)
     vox_e2e = global_batch * PATCH ** 3 / (ms_e2e * 1e-3)
     if rank != 0:
+        dist.barrier()
+        dist.destroy_process_group()
         return 0
 
     peaks, peak_src = load_peaks()
@@ -255,6 +262,7 @@ def run_gpu(args):
                                "optimize_parameters() on synthetic 128^3 patches",
                    "patch": PATCH, "per_gpu_batch": per_gpu_batch, "global_batch": global_batch,
                    "parallelism": "dp%d" % world, "l2": "per-step working set (tens of GB) >> 126 MB L2",
+                   "launch": "two CUDA graphs per step" if (world == 1 and not args.no_graphs) else "eager",
                    "model_tflop_per_sample_step": FLOP_PER_SAMPLE_STEP / 1e12},
         "e2e": {"value": vox_e2e, "unit": "voxels/s", "h2d_bytes_per_step": int(host_A.numel() * 4 * 2),
                 "d2h_bytes_per_step": 8 * 4, "ms_per_step": ms_e2e},
@@ -273,6 +281,9 @@ def run_gpu(args):
                                 "sample": "BASELINE config 1: 64^3 patch, batch 1, fp32, first optimize_parameters() "
                                           "(%.1f s) of the oracle port on the host cores" % sec}
     print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 
@@ -284,6 +295,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 2 on 1 GPU, 4 per GPU on N>1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="run the step eagerly (no CUDA-graph replay)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

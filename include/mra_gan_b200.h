@@ -145,6 +145,10 @@ typedef struct mra_adam_tensor {
 } mra_adam_tensor;
 int mra_adam_multi(const mra_adam_tensor* tensors, int count, float lr, float beta1, float beta2,
                    float eps, int step, mra_stream_t stream);
+/* Same sweep with the hyper-parameters read from DEVICE memory: hyper = {lr, beta1, beta2, eps, lr / (1 - beta1^t),
+ * sqrt(1 - beta2^t)} (6 floats).  Lets a captured CUDA graph of the training step be replayed while the host advances
+ * the step count and the learning-rate schedule. */
+int mra_adam_multi_dev(const mra_adam_tensor* tensors, int count, const float* hyper, mra_stream_t stream);
 
 /* Sliding-window inference helpers (test.py:147-178): window extraction with the (x-127.5)/127.5
  * scaling, and label += pred*127.5+127.5 ; weight += 1 accumulation; final label/weight + 0.01. */

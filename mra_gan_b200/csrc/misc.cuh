@@ -99,6 +99,8 @@ struct AdamBatch {
   long long numel[MRA_ADAM_MAX_TENSORS];
   int count;
   float lr, b1, b2, eps, step_size, bc2_sqrt;
+  const float* hyper;      // optional device copy of {lr, b1, b2, eps, step_size, bc2_sqrt}: read instead of the by-value
+                           // fields, so that a CUDA graph of the step can be replayed with new step counts / rates
 };
 #define MRA_ADAM_ELEMS_PER_BLOCK 4096
 
@@ -113,17 +115,19 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamBatch B) {
   float* __restrict__ v = B.v[ti];
   bf16* __restrict__ sh = B.shadow[ti];
   const long long n = B.numel[ti];
+  float b1 = B.b1, b2 = B.b2, eps = B.eps, step_size = B.step_size, bc2_sqrt = B.bc2_sqrt;
+  if (B.hyper) { b1 = B.hyper[1]; b2 = B.hyper[2]; eps = B.hyper[3]; step_size = B.hyper[4]; bc2_sqrt = B.hyper[5]; }
 #pragma unroll 4
   for (int k = 0; k < MRA_ADAM_ELEMS_PER_BLOCK / 256; ++k) {
     const long long i = base + k * 256 + threadIdx.x;
     if (i >= n) break;
     const float gi = g[i];
     // exp_avg.lerp_(grad, 1-b1) with ATen's two-branch lerp; exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
-    const float wl = 1.f - B.b1, diff = gi - m[i];
+    const float wl = 1.f - b1, diff = gi - m[i];
     const float mi = (wl < 0.5f) ? m[i] + wl * diff : gi - diff * (1.f - wl);
-    const float vi = B.b2 * v[i] + (1.f - B.b2) * gi * gi;
-    const float denom = sqrtf(vi) / B.bc2_sqrt + B.eps;
-    const float pi = p[i] - B.step_size * (mi / denom);
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    const float pi = p[i] - step_size * (mi / denom);
     m[i] = mi; v[i] = vi; p[i] = pi;
     if (sh) sh[i] = __float2bfloat16_rn(pi);
   }

@@ -295,17 +295,16 @@ int mra_corr_sums(const void* x, const void* y, int64_t numel, int dtype, double
   return 0;
 }
 
-int mra_adam_multi(const mra_adam_tensor* tensors, int count, float lr, float beta1, float beta2, float eps, int step,
-                   mra_stream_t stream) {
-  MRA_REQUIRE(count >= 0 && step >= 1, "bad adam arguments");
-  const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+static int adam_launch(const mra_adam_tensor* tensors, int count, float lr, float beta1, float beta2, float eps, float step_size,
+                       float bc2_sqrt, const float* hyper, cudaStream_t st) {
   int i = 0;
   while (i < count) {
     AdamBatch B;
     memset(&B, 0, sizeof(B));
     B.lr = lr; B.b1 = beta1; B.b2 = beta2; B.eps = eps;
-    B.step_size = (float)((double)lr / bc1);
-    B.bc2_sqrt = (float)sqrt(bc2);
+    B.step_size = step_size;
+    B.bc2_sqrt = bc2_sqrt;
+    B.hyper = hyper;
     long long blocks = 0;
     int c = 0;
     for (; c < MRA_ADAM_MAX_TENSORS && i < count; ++i) {
@@ -319,10 +318,23 @@ int mra_adam_multi(const mra_adam_tensor* tensors, int count, float lr, float be
     B.block_start[c] = blocks;
     B.count = c;
     if (c == 0) continue;
-    adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(B);
+    adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(B);
     MRA_LAUNCH_CHECK();
   }
   return 0;
+}
+
+int mra_adam_multi(const mra_adam_tensor* tensors, int count, float lr, float beta1, float beta2, float eps, int step,
+                   mra_stream_t stream) {
+  MRA_REQUIRE(count >= 0 && step >= 1, "bad adam arguments");
+  const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+  return adam_launch(tensors, count, lr, beta1, beta2, eps, (float)((double)lr / bc1), (float)sqrt(bc2), nullptr,
+                     (cudaStream_t)stream);
+}
+
+int mra_adam_multi_dev(const mra_adam_tensor* tensors, int count, const float* hyper, mra_stream_t stream) {
+  MRA_REQUIRE(count >= 0 && hyper != nullptr, "bad adam arguments");
+  return adam_launch(tensors, count, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, hyper, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------ sliding window helpers

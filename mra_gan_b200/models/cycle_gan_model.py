@@ -4,6 +4,7 @@ Per ``optimize_parameters()`` and sample: 6 generator forwards, 6 generator back
 forwards and 6 backwards (2 of them dgrad-only), two fused-Adam sweeps.  Loss names, visual names,
 the ImagePool policy and the host RNG call order follow the reference.
 """
+import gc
 import itertools
 import random
 
@@ -28,7 +29,7 @@ class ImagePool:
             return images
         picked = []
         for img in images:
-            img = img.detach().unsqueeze(0)
+            img = img.detach().unsqueeze(0).clone()      # own storage: the generator output may be a reused (graph) buffer
             if self.num_imgs < self.pool_size:
                 self.num_imgs += 1
                 self.images.append(img)
@@ -91,6 +92,7 @@ class CycleGANModel(BaseModel):
                 for m in net.conv_modules():
                     m.make_shadow(net.compute_dtype)
         self.grad_sync = None        # set by parallel.DataParallelTrainer
+        self._graphs = None          # CUDA-graph replay of the step (enable_cuda_graphs)
 
     def set_input(self, input):
         AtoB = self.opt.which_direction == "AtoB"
@@ -137,7 +139,85 @@ class CycleGANModel(BaseModel):
                        self.loss_idt_A + self.loss_idt_B)
         self.loss_G.backward()
 
+    # -- CUDA-graph replay of the step ----------------------------------------------------------------
+    def enable_cuda_graphs(self, warmup_steps=2):
+        """Replay the training step as two CUDA graphs (generator phase, discriminator phase) instead of ~2400
+        eager launches.  The image pools stay eager between the two (their control flow depends on the host RNG,
+        cycle_gan_model.py:8-35).  The next ``warmup_steps`` calls of optimize_parameters() still run eagerly (they
+        warm every kernel / allocation up), the one after is captured.  Single-process training only."""
+        if self.grad_sync is not None:
+            raise RuntimeError("CUDA-graph replay is not combined with data-parallel gradient sync yet")
+        self._graphs = {"warm": int(warmup_steps), "shape": None}
+
+    def _phase_G(self):
+        self.forward()
+        self.set_requires_grad([self.netD_A, self.netD_B], False)
+        self.optimizer_G.zero_grad(set_to_none=True)
+        self.backward_G()
+        self.optimizer_G.step()
+
+    def _phase_D(self, pooled_B, pooled_A):
+        self.set_requires_grad([self.netD_A, self.netD_B], True)
+        self.optimizer_D.zero_grad(set_to_none=True)
+        self.loss_D_A = self.backward_D_basic(self.netD_A, self.real_B, pooled_B)
+        self.loss_D_B = self.backward_D_basic(self.netD_B, self.real_A, pooled_A)
+        self.optimizer_D.step()
+
+    def _optimize_graphed(self):
+        G = self._graphs
+        A, B = self.real_A, self.real_B
+        shape = (tuple(A.shape), tuple(B.shape))
+        if G.get("gG") is None or G["shape"] != shape:
+            if G["warm"] > 0:
+                G["warm"] -= 1
+                return False
+            # capture: static inputs, both phases in one memory pool
+            G["shape"] = shape
+            G["sA"], G["sB"] = A.clone(), B.clone()
+            self.real_A, self.real_B = G["sA"], G["sB"]
+            # drop every reference to the eager steps' autograd graphs: their AccumulateGrad nodes live on the default
+            # stream and must not be reused inside the capture
+            for n in self.loss_names:
+                setattr(self, "loss_" + n, None)
+            self.loss_G = self.loss_cor_coe_GA = self.loss_cor_coe_GB = None
+            for n in ("fake_A", "fake_B", "rec_A", "rec_B", "idt_A", "idt_B"):
+                setattr(self, n, None)
+            self.optimizer_G.zero_grad(set_to_none=True)
+            self.optimizer_D.zero_grad(set_to_none=True)
+            gc.collect()
+            torch.cuda.synchronize()
+            # capture only records: each graph is replayed right after its capture to execute this step (the host
+            # side of optimizer.step() -- step counters, pinned hyper-parameters -- already ran during capture)
+            from .. import ops
+            n0 = ops.impl().launch_count() if hasattr(ops.impl(), "launch_count") else 0
+            G["gG"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(G["gG"]):
+                self._phase_G()
+            G["gG"].replay()
+            G["pB"] = torch.empty_like(self.fake_B)
+            G["pA"] = torch.empty_like(self.fake_A)
+            G["pB"].copy_(self.fake_B_pool.query(self.fake_B))
+            G["pA"].copy_(self.fake_A_pool.query(self.fake_A))
+            G["gD"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(G["gD"], pool=G["gG"].pool()):
+                self._phase_D(G["pB"], G["pA"])
+            G["gD"].replay()
+            G["launches"] = (ops.impl().launch_count() - n0) if hasattr(ops.impl(), "launch_count") else 0   # kernels per replayed step
+            return True
+        G["sA"].copy_(A, non_blocking=True)
+        G["sB"].copy_(B, non_blocking=True)
+        self.real_A, self.real_B = G["sA"], G["sB"]
+        self.optimizer_G.advance_host_state()
+        G["gG"].replay()
+        G["pB"].copy_(self.fake_B_pool.query(self.fake_B))
+        G["pA"].copy_(self.fake_A_pool.query(self.fake_A))
+        self.optimizer_D.advance_host_state()
+        G["gD"].replay()
+        return True
+
     def optimize_parameters(self):
+        if self._graphs is not None and self.grad_sync is None and self._optimize_graphed():
+            return
         sync = self.grad_sync
         self.forward()
         self.set_requires_grad([self.netD_A, self.netD_B], False)

@@ -273,6 +273,17 @@ class CudaImpl:
         _lib.check(self.L.mra_adam_multi(arr, len(params), lr, beta1, beta2, eps, step, self._stream()),
                    "mra_adam_multi")
 
+    def adam_step_dev(self, params, grads, exp_avgs, exp_avg_sqs, shadows, hyper):
+        """Same sweep, hyper-parameters {lr, b1, b2, eps, lr/(1-b1^t), sqrt(1-b2^t)} read from the device tensor ``hyper``."""
+        arr = (_lib.AdamTensor * len(params))()
+        for i, (p, g, m, v, s) in enumerate(zip(params, grads, exp_avgs, exp_avg_sqs, shadows)):
+            self._need_dense(p, g, m, v, s)
+            arr[i].p, arr[i].g, arr[i].m, arr[i].v = p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr()
+            arr[i].shadow = s.data_ptr() if s is not None else None
+            arr[i].numel = p.numel()
+        assert hyper.is_cuda and hyper.dtype == torch.float32 and hyper.numel() >= 6
+        _lib.check(self.L.mra_adam_multi_dev(arr, len(params), _ptr(hyper), self._stream()), "mra_adam_multi_dev")
+
     @staticmethod
     def _need_dense(p, g, m, v, s):
         for t in (p, g, m, v, s):

@@ -5,6 +5,8 @@ It is a regular ``torch.optim.Optimizer`` (param_groups / state_dict / LR schedu
 ``step()`` is one kernel sweep (``mra_adam_multi``) over every parameter that also refreshes the
 bf16 shadow copies the tensor-core convolutions read.
 """
+import math
+
 import torch
 
 from . import ops
@@ -17,12 +19,42 @@ class FusedAdam(torch.optim.Optimizer):
             raise NotImplementedError("the reference uses plain Adam (no weight decay, no amsgrad)")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
 
+    # -- device-resident hyper-parameters (CUDA-graph replay) -----------------------------------------
+    def _hyper_buffers(self, gi, device):
+        bufs = self.__dict__.setdefault("_hyper", {})
+        if gi not in bufs:
+            bufs[gi] = (torch.zeros(8, dtype=torch.float32).pin_memory(), torch.zeros(8, dtype=torch.float32, device=device))
+        return bufs[gi]
+
+    @staticmethod
+    def _fill_hyper(host, group, step_no):
+        b1, b2 = group["betas"]
+        lr = float(group["lr"])
+        host[0], host[1], host[2], host[3] = lr, b1, b2, group["eps"]
+        host[4] = lr / (1.0 - b1 ** step_no)
+        host[5] = math.sqrt(1.0 - b2 ** step_no)
+
+    def advance_host_state(self):
+        """Bookkeeping of one optimiser step WITHOUT launching anything: bump the step counters and refresh the
+        pinned hyper-parameter buffers (a captured graph of ``step()`` copies them to the device when replayed)."""
+        for gi, group in enumerate(self.param_groups):
+            step_no = None
+            for p in group["params"]:
+                st = self.state.get(p)
+                if st:
+                    st["step"] += 1
+                    step_no = st["step"]
+            if step_no is not None and gi in self.__dict__.get("_hyper", {}):
+                self._fill_hyper(self._hyper[gi][0], group, step_no)
+        _WeightsEpoch.value += 1
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         I = ops.impl()
         new_epoch = _WeightsEpoch.value + 1
-        for group in self.param_groups:
+        use_dev = hasattr(I, "adam_step_dev")
+        for gi, group in enumerate(self.param_groups):
             ps, gs, ms, vs, shs = [], [], [], [], []
             step_no = None
             for p in group["params"]:
@@ -45,8 +77,14 @@ class FusedAdam(torch.optim.Optimizer):
                 ps.append(p); gs.append(self._grad(p)); ms.append(st["exp_avg"]); vs.append(st["exp_avg_sq"])
                 shs.append(self._shadow(p))
             if ps:
-                I.adam_step(ps, gs, ms, vs, shs, group["lr"], group["betas"][0], group["betas"][1], group["eps"],
-                            step_no)
+                if use_dev:
+                    host, dev = self._hyper_buffers(gi, ps[0].device)
+                    self._fill_hyper(host, group, step_no)
+                    dev.copy_(host, non_blocking=True)        # a memcpy node when the step is being captured
+                    I.adam_step_dev(ps, gs, ms, vs, shs, dev)
+                else:
+                    I.adam_step(ps, gs, ms, vs, shs, group["lr"], group["betas"][0], group["betas"][1], group["eps"],
+                                step_no)
                 for p in ps:
                     self._mark(p, new_epoch)
         _WeightsEpoch.value = new_epoch
