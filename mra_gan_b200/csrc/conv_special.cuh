@@ -192,7 +192,9 @@ __global__ void __launch_bounds__(256) im2col1_kernel(const bf16* __restrict__ x
 }
 // dx[n,i] = sum over (o, k) with o*s - p + k == i of dE[n,o,(kd,kh,kw)]
 __global__ void __launch_bounds__(256) col2im1_kernel(const bf16* __restrict__ dE, bf16* __restrict__ dx, int N, int Di, int Hi, int Wi,
-                                                       int Do, int Ho, int Wo, int k, int s, int p) {
+                                                       int Do, int Ho, int Wo, int k, int s, int p,
+                                                       const float* __restrict__ bias, int act, float slope) {
+  const float bv = bias ? bias[0] : 0.f;
   const long long total = (long long)N * Di * Hi * Wi;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long q = i;
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(256) col2im1_kernel(const bf16* __restrict__ d
         }
       }
     }
-    dx[i] = __float2bfloat16_rn(acc);
+    dx[i] = __float2bfloat16_rn(apply_act(acc + bv, act, slope));
   }
 }
 // B[co][c] = w[c][co] (c < taps, else 0)  /  BT[c][co]  /  dw[t][co] += dWe[co][t]
@@ -288,6 +290,28 @@ inline bool im2col_eligible(const mra_conv_desc& d) {
   return d.dtype == MRA_BF16 && !(d.flags & MRA_CONV_FORCE_NAIVE) && !d.transposed && d.cin == 1 &&
          d.k * d.k * d.k <= 64 && tc::pick_n_tile(d.cout) > 0 && !(d.stride == 1 && d.pad == 0 && d.k >= 2);
 }
+// ConvTranspose3d(C -> 1, k, s, p) (the UNet's outermost up-convolution, networks3D.py:312-316) is, operand for operand,
+// the mirror Conv3d(1 -> C, k, s, p) with the roles of x and y swapped:
+//   convT fprop(x, w)  = mirror dgrad(dy := x)  (+ bias, activation)      convT dgrad(dy) = mirror fprop(x := dy)
+//   convT wgrad(x, dy) = mirror wgrad(x := dy, dy := x)
+// and the packed weights coincide byte for byte ([taps][1][C] vs [taps][C][1]).  So it rides the im2col lowering.
+inline mra_conv_desc convT1_mirror(const mra_conv_desc& d) {
+  mra_conv_desc m = d;
+  m.cin = 1; m.cout = d.cin;
+  m.din = d.dout; m.hin = d.hout; m.win = d.wout;
+  m.dout = d.din; m.hout = d.hin; m.wout = d.win;
+  m.transposed = 0; m.act = MRA_ACT_NONE;
+  return m;
+}
+inline bool convT1_eligible(const mra_conv_desc& d) {
+  if (!d.transposed || d.cout != 1 || d.dtype != MRA_BF16 || (d.flags & MRA_CONV_FORCE_NAIVE)) return false;
+  const mra_conv_desc m = convT1_mirror(d);
+  // the mirror must be a valid convolution (output_padding < stride guarantees it) that the im2col path accepts
+  if ((m.din + 2 * m.pad - m.k) / m.stride + 1 != m.dout || (m.hin + 2 * m.pad - m.k) / m.stride + 1 != m.hout ||
+      (m.win + 2 * m.pad - m.k) / m.stride + 1 != m.wout)
+    return false;
+  return im2col_eligible(m);
+}
 inline GeomEx im2col_geom(const mra_conv_desc& d) {    // E [N][Do][Ho][Wo][64] -> y [N][Do][Ho][Wo][Co], 1x1x1
   GeomEx g;
   g.n = d.n; g.cin = 64; g.cout = d.cout;
@@ -320,7 +344,10 @@ inline GeomEx head_geom(const mra_conv_desc& d) {      // x [N][Din][Hin][Win][C
 }
 
 inline size_t a256(size_t v) { return (v + 255) & ~size_t(255); }
+inline size_t workspace_bytes(const mra_conv_desc& d, int which);
+inline size_t workspace_bytes_convT1(const mra_conv_desc& d) { return workspace_bytes(convT1_mirror(d), 0); }
 inline size_t workspace_bytes(const mra_conv_desc& d, int which) {
+  if (convT1_eligible(d)) return workspace_bytes_convT1(d);
   const size_t wexp = a256((size_t)d.k * 64 * (d.cin == 1 ? d.cout : d.cin) * 2);
   const size_t dwe = a256((size_t)d.k * 64 * (d.cin == 1 ? d.cout : d.cin) * 4);
   if (im2col_eligible(d)) {
@@ -360,8 +387,10 @@ inline int im2col_fprop(const mra_conv_desc& d, const void* x, const void* w, co
   const long long pos = (long long)d.n * d.dout * d.hout * d.wout;
   MRA_WS_TAKE(E, bf16, (size_t)pos * 64 * 2);
   MRA_WS_TAKE(B, bf16, (size_t)64 * d.cout * 2);
-  im2col1_kernel<<<sgrid(pos * 8), 256, 0, st>>>((const bf16*)x, E, d.n, d.din, d.hin, d.win, d.dout, d.hout, d.wout, d.k, d.stride, d.pad);
-  MRA_LAUNCH_CHECK();
+  if (!(d.flags & MRA_CONV_WS_REUSE)) {
+    im2col1_kernel<<<sgrid(pos * 8), 256, 0, st>>>((const bf16*)x, E, d.n, d.din, d.hin, d.win, d.dout, d.hout, d.wout, d.k, d.stride, d.pad);
+    MRA_LAUNCH_CHECK();
+  }
   im2col_w_kernel<<<sgrid(64 * d.cout), 256, 0, st>>>((const bf16*)w, B, d.k * d.k * d.k, d.cout, 0);
   MRA_LAUNCH_CHECK();
   GatherPlan plan;
@@ -386,7 +415,8 @@ inline int im2col_wgrad(const mra_conv_desc& d, const void* x, const void* dy, f
   MRA_LAUNCH_CHECK();
   return 0;
 }
-inline int im2col_dgrad(const mra_conv_desc& d, const void* dy, const void* wT, void* dx, void* wsp, size_t wsb, cudaStream_t st) {
+inline int im2col_dgrad(const mra_conv_desc& d, const void* dy, const void* wT, void* dx, void* wsp, size_t wsb, cudaStream_t st,
+                        const float* bias = nullptr, int act = MRA_ACT_NONE, float slope = 0.f) {
   Workspace ws{(char*)wsp, wsb, 0};
   const long long pos = (long long)d.n * d.dout * d.hout * d.wout;
   MRA_WS_TAKE(dE, bf16, (size_t)pos * 64 * 2);
@@ -398,10 +428,11 @@ inline int im2col_dgrad(const mra_conv_desc& d, const void* dy, const void* wT, 
   tc::GatherRun R{dy, BT, 1, nullptr, dE, 1, MRA_ACT_NONE, 0.f, nullptr};
   if (int rc = tc::run_gather_tc(plan, R, st)) return rc;
   col2im1_kernel<<<sgrid((long long)d.n * d.din * d.hin * d.win), 256, 0, st>>>(dE, (bf16*)dx, d.n, d.din, d.hin, d.win, d.dout, d.hout,
-                                                                                  d.wout, d.k, d.stride, d.pad);
+                                                                                  d.wout, d.k, d.stride, d.pad, bias, act, slope);
   MRA_LAUNCH_CHECK();
   return 0;
 }
+
 
 inline int stem_fprop(const mra_conv_desc& d, const void* x, const void* w, const float* bias, void* y, double* stats,
                       void* wsp, size_t wsb, cudaStream_t st) {

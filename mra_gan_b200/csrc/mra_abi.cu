@@ -69,6 +69,7 @@ size_t mra_conv3d_workspace_size(const mra_conv_desc* d, int which) {
 int mra_conv3d_lowering(const mra_conv_desc* d) {
   if (!d) return 0;
   if (special::im2col_eligible(*d)) return 3;
+  if (special::convT1_eligible(*d)) return 2;      // wgrad builds im2col(dy), dgrad reuses it
   if (special::stem_eligible(*d)) return 1;
   if (special::head_eligible(*d)) return 2;
   return 0;
@@ -76,7 +77,8 @@ int mra_conv3d_lowering(const mra_conv_desc* d) {
 
 int mra_conv3d_uses_tensor_cores(const mra_conv_desc* d, int which) {
   if (!d) return 0;
-  if (special::stem_eligible(*d) || special::head_eligible(*d) || special::im2col_eligible(*d)) return 1;
+  if (special::stem_eligible(*d) || special::head_eligible(*d) || special::im2col_eligible(*d) || special::convT1_eligible(*d))
+    return 1;
   if (which == 2) return tc::wgrad_eligible(*d) ? 1 : 0;
   return tc::gather_eligible(*d, which) ? 1 : 0;
 }
@@ -87,6 +89,8 @@ int mra_conv3d_fprop(const mra_conv_desc* d, const void* x, const void* w, const
   cudaStream_t st = (cudaStream_t)stream;
   if (stats) MRA_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * d->n * d->cout, st));
   if (special::im2col_eligible(*d)) return special::im2col_fprop(*d, x, w, bias, y, stats, workspace, workspace_bytes, st);
+  if (special::convT1_eligible(*d) && !stats)
+    return special::im2col_dgrad(special::convT1_mirror(*d), x, w, y, workspace, workspace_bytes, st, bias, d->act, d->slope);
   if (special::stem_eligible(*d)) return special::stem_fprop(*d, x, w, bias, y, stats, workspace, workspace_bytes, st);
   if (special::head_eligible(*d) && !stats) return special::head_fprop(*d, x, w, bias, y, workspace, workspace_bytes, st);
   if (tc::gather_eligible(*d, 0)) return tc::run_gather_tc(*d, 0, x, w, bias, y, stats, st);
@@ -107,6 +111,8 @@ int mra_conv3d_dgrad(const mra_conv_desc* d, const void* dy, const void* wT, voi
   if (int rc = check_conv(d)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (special::im2col_eligible(*d)) return special::im2col_dgrad(*d, dy, wT, dx, workspace, workspace_bytes, st);
+  if (special::convT1_eligible(*d))
+    return special::im2col_fprop(special::convT1_mirror(*d), dy, wT, nullptr, dx, nullptr, workspace, workspace_bytes, st);
   if (special::stem_eligible(*d)) return special::stem_dgrad(*d, dy, wT, dx, workspace, workspace_bytes, st);
   if (special::head_eligible(*d)) return special::head_dgrad(*d, dy, wT, dx, workspace, workspace_bytes, st);
   if (tc::gather_eligible(*d, 1)) return tc::run_gather_tc(*d, 1, dy, wT, nullptr, dx, nullptr, st);
@@ -127,6 +133,8 @@ int mra_conv3d_wgrad(const mra_conv_desc* d, const void* x, const void* dy, floa
   if (dw) {
     if (special::im2col_eligible(*d)) {
       if (int rc = special::im2col_wgrad(*d, x, dy, dw, workspace, workspace_bytes, st)) return rc;
+    } else if (special::convT1_eligible(*d)) {
+      if (int rc = special::im2col_wgrad(special::convT1_mirror(*d), dy, x, dw, workspace, workspace_bytes, st)) return rc;
     } else if (special::stem_eligible(*d)) {
       if (int rc = special::stem_wgrad(*d, x, dy, dw, workspace, workspace_bytes, st)) return rc;
     } else if (special::head_eligible(*d)) {

@@ -35,6 +35,8 @@ TC_CONVS = [
     (ConvGeom(128, 1, 4, 1, 0), (7, 8, 9), 1),             # head-like, k4
     (ConvGeom(1, 64, 4, 2, 1), (12, 12, 12), 2),           # D.1: im2col lowering
     (ConvGeom(512, 1, 4, 1, 1), (7, 7, 7), 2),             # D.5: zero-padded head lowering
+    (ConvGeom(128, 1, 4, 2, 1, True, 0), (6, 6, 6), 2),    # UNet outermost up-conv: mirror of the im2col lowering
+    (ConvGeom(64, 1, 3, 2, 1, True, 1), (5, 6, 7), 1),     # ConvTranspose3d(C -> 1) with output padding
 ]
 
 
