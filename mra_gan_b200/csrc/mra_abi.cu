@@ -8,6 +8,7 @@
 #include "conv_special.cuh"
 #include "misc.cuh"
 #include "norm.cuh"
+#include "norm_stream.cuh"
 
 namespace mra {
 thread_local std::string g_last_error;
@@ -218,7 +219,7 @@ int mra_inorm_act_pad_fwd(const mra_norm_desc* d, const void* x, const double* s
               "InstanceNorm needs more than 1 spatial element per channel in training mode");
   MRA_REQUIRE((d->res_pad >= 0) == (residual != nullptr), "residual pointer / res_pad mismatch");
   MRA_REQUIRE(!d->use_running || (running_mean && running_var), "eval-mode norm needs running stats");
-  DISPATCH_NORM(d, return (norm_fwd_launch<T, VEC>(*d, x, stats, residual, y, mean, rstd, running_mean, running_var,
+  DISPATCH_NORM(d, return (ns::norm_fwd_launch_v2<T, VEC>(*d, x, stats, residual, y, mean, rstd, running_mean, running_var,
                                                    (cudaStream_t)stream)));
   return 0;
 }
@@ -227,7 +228,7 @@ int mra_inorm_act_pad_bwd(const mra_norm_desc* d, const void* gy, const void* x,
                           void* dx, void* dres, double* sums, mra_stream_t stream) {
   if (int rc = check_norm(d)) return rc;
   MRA_REQUIRE(!dres || d->res_pad >= 0, "dres requested without a residual");
-  DISPATCH_NORM(d, return (norm_bwd_launch<T, VEC>(*d, gy, x, mean, rstd, dx, dres, sums, (cudaStream_t)stream)));
+  DISPATCH_NORM(d, return (ns::norm_bwd_launch_v2<T, VEC>(*d, gy, x, mean, rstd, dx, dres, sums, (cudaStream_t)stream)));
   return 0;
 }
 

@@ -304,260 +304,12 @@ __global__ void __launch_bounds__(256) inorm_bwd_kernel(const T* __restrict__ gy
 }
 
 
-// =====================================================================================================
-// Fast paths (VEC == 8, channel groups G = C/8 a power of two <= 256): a block walks whole rows of the
-// (padded) position space, so all index arithmetic is 32-bit and hoisted out of the inner loop; a thread
-// always serves the same 8 channels (its mean / rstd live in registers) and keeps UNR independent 16-byte
-// loads in flight.
-// =====================================================================================================
-constexpr int kNormUnroll = 4;
 // the activations that follow a norm layer are piecewise linear: y = x > 0 ? x : x * nslope (none: 1, ReLU: 0)
 __device__ __forceinline__ float norm_neg_slope(const NormP& P) {
   return P.act == MRA_ACT_NONE ? 1.f : (P.act == MRA_ACT_RELU ? 0.f : P.slope);
 }
 
-// 8 consecutive elements kept in their storage format while the load is in flight (bf16: 4 registers)
-template <typename T> struct Raw8;
-template <> struct Raw8<bf16> {
-  uint4 r;
-  __device__ __forceinline__ void load(const bf16* p) { r = __ldg(reinterpret_cast<const uint4*>(p)); }
-  __device__ __forceinline__ void unpack(float (&v)[8]) const {
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
-  }
-};
-template <> struct Raw8<float> {
-  float4 a, b;
-  __device__ __forceinline__ void load(const float* p) {
-    a = __ldg(reinterpret_cast<const float4*>(p)); b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-  }
-  __device__ __forceinline__ void unpack(float (&v)[8]) const {
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-  }
-};
-
-template <typename T>
-__global__ void __launch_bounds__(256, 2) inorm_fwd_fast_kernel(const T* __restrict__ x, const float* __restrict__ mean,
-                                                                 const float* __restrict__ rstd, const T* __restrict__ res,
-                                                                 T* __restrict__ y, const NormP P, int lgG) {
-  const int n = blockIdx.y, t = threadIdx.x;
-  const int G = P.G, cg = t & (G - 1), wl = t >> lgG, wpp = 256 >> lgG;
-  float mu[8], rs[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { mu[j] = mean[n * P.C + cg * 8 + j]; rs[j] = rstd[n * P.C + cg * 8 + j]; }
-  const float nslope = norm_neg_slope(P);
-  const int p = P.pad, rp = P.res_pad;
-  const int Dp = P.D + 2 * p, Hp = P.H + 2 * p, Wp = P.W + 2 * p;
-  const int Hr = P.H + 2 * rp, Wr = P.W + 2 * rp, Dr = P.D + 2 * rp;
-  const T* xn = x + (long long)n * P.V * P.C + cg * 8;
-  T* yn = y + (long long)n * Dp * Hp * Wp * P.C + cg * 8;
-  const T* rn = (rp >= 0) ? res + (long long)n * Dr * Hr * Wr * P.C + cg * 8 : nullptr;
-  const int rows = Dp * Hp;
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int pd = row / Hp, ph = row - pd * Hp;
-    const int sd = min(max(pd - p, 0), P.D - 1), sh = min(max(ph - p, 0), P.H - 1);
-    const T* xr = xn + (long long)(sd * P.H + sh) * P.W * P.C;
-    T* yr = yn + (long long)row * Wp * P.C;
-    const T* rr = rn ? rn + (long long)((sd + rp) * Hr + sh + rp) * Wr * P.C + (long long)rp * P.C : nullptr;
-    for (int pw0 = wl; pw0 < Wp; pw0 += kNormUnroll * wpp) {
-      Raw8<T> xv[kNormUnroll], rv[kNormUnroll];
-#pragma unroll
-      for (int u = 0; u < kNormUnroll; ++u) {
-        const int pw = pw0 + u * wpp;
-        if (pw < Wp) {
-          const int sw = min(max(pw - p, 0), P.W - 1);
-          xv[u].load(xr + (long long)sw * P.C);
-          if (rr) rv[u].load(rr + (long long)sw * P.C);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < kNormUnroll; ++u) {
-        const int pw = pw0 + u * wpp;
-        if (pw < Wp) {
-          float v[8];
-          xv[u].unpack(v);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { const float xh = (v[j] - mu[j]) * rs[j]; v[j] = xh > 0.f ? xh : xh * nslope; }
-          if (rr) {
-            float r[8];
-            rv[u].unpack(r);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += r[j];
-          }
-          Vec8<T>::store(yr + (long long)pw * P.C, v);
-        }
-      }
-    }
-  }
-}
-
-// Padded gradient folded onto interior voxel (d,h,w): the interior case is ONE load (issued early, kept raw);
-// border voxels add the halo entries that clamp onto them.
-template <typename T>
-__device__ __forceinline__ void fold_edges(const T* __restrict__ gn_cg, int d, int h, int w, const NormP& P, int Hp, int Wp,
-                                           float (&g)[8]) {
-  const int p = P.pad;
-  const int d0 = (d == 0) ? 0 : d + p, d1 = (d == P.D - 1) ? d + 2 * p : d + p;
-  const int h0 = (h == 0) ? 0 : h + p, h1 = (h == P.H - 1) ? h + 2 * p : h + p;
-  const int w0 = (w == 0) ? 0 : w + p, w1 = (w == P.W - 1) ? w + 2 * p : w + p;
-  for (int a = d0; a <= d1; ++a)
-    for (int b = h0; b <= h1; ++b)
-      for (int c = w0; c <= w1; ++c) {
-        if (a == d + p && b == h + p && c == w + p) continue;        // the centre is already in g
-        float tv[8];
-        Vec8<T>::load(gn_cg + ((long long)(a * Hp + b) * Wp + c) * P.C, tv);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] += tv[j];
-      }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256, 2) inorm_bwd_stats_fast_kernel(const T* __restrict__ gy, const T* __restrict__ x,
-                                                                       const float* __restrict__ mean,
-                                                                       const float* __restrict__ rstd,
-                                                                       double* __restrict__ sums, const NormP P, int lgG) {
-  const int n = blockIdx.y, t = threadIdx.x;
-  const int G = P.G, cg = t & (G - 1), wl = t >> lgG, wpp = 256 >> lgG;
-  float mu[8], rs[8], s[8], ss[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    mu[j] = mean[n * P.C + cg * 8 + j]; rs[j] = rstd[n * P.C + cg * 8 + j];
-    s[j] = 0.f; ss[j] = 0.f;
-  }
-  const float nslope = norm_neg_slope(P);
-  const int p = P.pad;
-  const int Hp = P.H + 2 * p, Wp = P.W + 2 * p, Dp = P.D + 2 * p;
-  const T* xn = x + (long long)n * P.V * P.C + cg * 8;
-  const T* gn = gy + (long long)n * Dp * Hp * Wp * P.C + cg * 8;
-  const int rows = P.D * P.H;
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int d = row / P.H, h = row - d * P.H;
-    const T* xr = xn + (long long)row * P.W * P.C;
-    const T* gr = gn + ((long long)((d + p) * Hp + h + p) * Wp + p) * P.C;
-    const bool row_edge = p > 0 && (d == 0 || d == P.D - 1 || h == 0 || h == P.H - 1);
-    for (int w0 = wl; w0 < P.W; w0 += kNormUnroll * wpp) {
-      Raw8<T> xv[kNormUnroll], gv[kNormUnroll];
-#pragma unroll
-      for (int u = 0; u < kNormUnroll; ++u) {
-        const int w = w0 + u * wpp;
-        if (w < P.W) { xv[u].load(xr + (long long)w * P.C); gv[u].load(gr + (long long)w * P.C); }
-      }
-#pragma unroll
-      for (int u = 0; u < kNormUnroll; ++u) {
-        const int w = w0 + u * wpp;
-        if (w < P.W) {
-          float v[8], g[8];
-          xv[u].unpack(v); gv[u].unpack(g);
-          if (row_edge || (p > 0 && (w == 0 || w == P.W - 1))) fold_edges<T>(gn, d, h, w, P, Hp, Wp, g);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float xh = (v[j] - mu[j]) * rs[j];
-            const float dy = xh > 0.f ? g[j] : g[j] * nslope;
-            s[j] += dy;
-            ss[j] = fmaf(dy, xh, ss[j]);
-          }
-        }
-      }
-    }
-  }
-  // combine the wpp position lanes of every channel group: shared memory, then one fp64 atomic per channel
-  __shared__ float sm[2][256 * 8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { sm[0][t * 8 + j] = s[j]; sm[1][t * 8 + j] = ss[j]; }
-  __syncthreads();
-  for (int u = t; u < G * 8; u += 256) {
-    const int g = u >> 3, j = u & 7;
-    double a = 0.0, b = 0.0;
-    for (int r = 0; r < wpp; ++r) {
-      a += (double)sm[0][(r * G + g) * 8 + j];
-      b += (double)sm[1][(r * G + g) * 8 + j];
-    }
-    atomicAdd(sums + ((long long)n * P.C + u) * 2 + 0, a);
-    atomicAdd(sums + ((long long)n * P.C + u) * 2 + 1, b);
-  }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256, 2) inorm_bwd_fast_kernel(const T* __restrict__ gy, const T* __restrict__ x,
-                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                                 const double* __restrict__ sums, T* __restrict__ dx,
-                                                                 T* __restrict__ dres, const NormP P, int lgG) {
-  const int n = blockIdx.y, t = threadIdx.x;
-  const int G = P.G, cg = t & (G - 1), wl = t >> lgG, wpp = 256 >> lgG;
-  float mu[8], rs[8], m1[8], m2[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = cg * 8 + j;
-    mu[j] = mean[n * P.C + c]; rs[j] = rstd[n * P.C + c];
-    if (P.use_running) { m1[j] = 0.f; m2[j] = 0.f; }
-    else {
-      m1[j] = (float)(sums[((long long)n * P.C + c) * 2 + 0] / (double)P.V);
-      m2[j] = (float)(sums[((long long)n * P.C + c) * 2 + 1] / (double)P.V);
-    }
-  }
-  const float nslope = norm_neg_slope(P);
-  const int p = P.pad;
-  const int Hp = P.H + 2 * p, Wp = P.W + 2 * p, Dp = P.D + 2 * p;
-  const int rp = dres ? P.res_pad : 0;
-  const int Dr = P.D + 2 * rp, Hr = P.H + 2 * rp, Wr = P.W + 2 * rp;
-  const T* xn = x + (long long)n * P.V * P.C + cg * 8;
-  const T* gn = gy + (long long)n * Dp * Hp * Wp * P.C + cg * 8;
-  T* dxn = dx + (long long)n * P.V * P.C + cg * 8;
-  T* drn = dres ? dres + (long long)n * Dr * Hr * Wr * P.C + cg * 8 : nullptr;
-  const int rows = Dr * Hr;
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int rd = row / Hr, rh = row - rd * Hr;
-    const int d = rd - rp, h = rh - rp;
-    T* drr = drn ? drn + (long long)row * Wr * P.C : nullptr;
-    if (d < 0 || d >= P.D || h < 0 || h >= P.H) {          // halo row of the residual gradient: zeros
-      float z[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) z[j] = 0.f;
-      for (int rw = wl; rw < Wr; rw += wpp) Vec8<T>::store(drr + (long long)rw * P.C, z);
-      continue;
-    }
-    const T* xr = xn + (long long)(d * P.H + h) * P.W * P.C;
-    const T* gr = gn + ((long long)((d + p) * Hp + h + p) * Wp + p) * P.C;
-    T* dxr = dxn + (long long)(d * P.H + h) * P.W * P.C;
-    const bool row_edge = p > 0 && (d == 0 || d == P.D - 1 || h == 0 || h == P.H - 1);
-    if (drr && rp > 0) {
-      float z[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) z[j] = 0.f;
-      for (int rw = wl; rw < rp; rw += wpp) {
-        Vec8<T>::store(drr + (long long)rw * P.C, z);
-        Vec8<T>::store(drr + (long long)(Wr - 1 - rw) * P.C, z);
-      }
-    }
-    for (int w0 = wl; w0 < P.W; w0 += kNormUnroll * wpp) {
-      Raw8<T> xv[kNormUnroll], gv[kNormUnroll];
-#pragma unroll
-      for (int u = 0; u < kNormUnroll; ++u) {
-        const int w = w0 + u * wpp;
-        if (w < P.W) { xv[u].load(xr + (long long)w * P.C); gv[u].load(gr + (long long)w * P.C); }
-      }
-#pragma unroll
-      for (int u = 0; u < kNormUnroll; ++u) {
-        const int w = w0 + u * wpp;
-        if (w < P.W) {
-          float v[8], g[8], o[8];
-          xv[u].unpack(v); gv[u].unpack(g);
-          if (row_edge || (p > 0 && (w == 0 || w == P.W - 1))) fold_edges<T>(gn, d, h, w, P, Hp, Wp, g);
-          if (drr) Vec8<T>::store(drr + (long long)(w + rp) * P.C, g);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float xh = (v[j] - mu[j]) * rs[j];
-            const float dy = xh > 0.f ? g[j] : g[j] * nslope;
-            o[j] = rs[j] * (dy - m1[j] - xh * m2[j]);
-          }
-          Vec8<T>::store(dxr + (long long)w * P.C, o);
-        }
-      }
-    }
-  }
-}
-
+// eligibility of the row-streaming kernels (norm_stream.cuh): 16-byte items, power-of-two channel groups
 inline int norm_fast_lg(const NormP& P, int vec) {
   if (vec != 8 || P.G > 256 || (P.G & (P.G - 1)) != 0) return -1;
   if (P.act != MRA_ACT_NONE && P.act != MRA_ACT_RELU && P.act != MRA_ACT_LRELU) return -1;
@@ -565,13 +317,6 @@ inline int norm_fast_lg(const NormP& P, int vec) {
   while ((1 << lg) < P.G) ++lg;
   return lg;
 }
-inline unsigned norm_row_grid(long long rows, int n) {
-  long long b = ((long long)num_sms() * 4 + n - 1) / n;     // two rounds of 2 resident blocks per SM across the batch
-  if (b > rows) b = rows;
-  if (b < 1) b = 1;
-  return (unsigned)b;
-}
-
 // ---- stand-alone replication pad fwd / bwd and activations ----
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) reppad_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, const NormP P) {
@@ -669,14 +414,6 @@ int norm_fwd_launch(const mra_norm_desc& d, const void* x, const double* stats, 
   NormP P = make_norm_params(d, VEC);
   inorm_finalize_kernel<<<(d.c + 127) / 128, 128, 0, st>>>(stats, mean, rstd, rm, rv, P);
   MRA_LAUNCH_CHECK();
-  const int lg = norm_fast_lg(P, VEC);
-  if (lg >= 0) {
-    dim3 grid(norm_row_grid((long long)(d.d + 2 * d.pad) * (d.h + 2 * d.pad), d.n), d.n);
-    inorm_fwd_fast_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(x), mean, rstd, reinterpret_cast<const T*>(res),
-                                                   reinterpret_cast<T*>(y), P, lg);
-    MRA_LAUNCH_CHECK();
-    return 0;
-  }
   const long long items = (long long)(d.d + 2 * d.pad) * (d.h + 2 * d.pad) * (d.w + 2 * d.pad) * P.G;
   dim3 grid(grid_for(items, 256 * 4, (16 + d.n - 1) / d.n), d.n);
   inorm_fwd_kernel<T, VEC><<<grid, 256, 2 * d.c * sizeof(float), st>>>(
@@ -689,22 +426,6 @@ template <typename T, int VEC>
 int norm_bwd_launch(const mra_norm_desc& d, const void* gy, const void* x, const float* mean,
                     const float* rstd, void* dx, void* dres, double* sums, cudaStream_t st) {
   NormP P = make_norm_params(d, VEC);
-  const int lg = norm_fast_lg(P, VEC);
-  if (lg >= 0) {
-    if (!d.use_running) {
-      MRA_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * d.n * d.c, st));
-      dim3 grid(norm_row_grid((long long)d.d * d.h, d.n), d.n);
-      inorm_bwd_stats_fast_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(gy), reinterpret_cast<const T*>(x), mean,
-                                                           rstd, sums, P, lg);
-      MRA_LAUNCH_CHECK();
-    }
-    const int rpf = dres ? d.res_pad : 0;
-    dim3 grid(norm_row_grid((long long)(d.d + 2 * rpf) * (d.h + 2 * rpf), d.n), d.n);
-    inorm_bwd_fast_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(gy), reinterpret_cast<const T*>(x), mean, rstd, sums,
-                                                   reinterpret_cast<T*>(dx), reinterpret_cast<T*>(dres), P, lg);
-    MRA_LAUNCH_CHECK();
-    return 0;
-  }
   if (!d.use_running) {
     MRA_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * d.n * d.c, st));
     long long bx = ((long long)num_sms() * 4 + d.n - 1) / d.n;

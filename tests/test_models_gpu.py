@@ -202,7 +202,7 @@ def test_cuda_graph_step_matches_eager(tmp_path):
         if use_graphs:
             m.enable_cuda_graphs(warmup_steps=1)
         losses = []
-        for step in range(5):
+        for step in range(3):                               # eager warm-up, capture (+ replay), pure replay
             A, B = OF.synthetic_patches(1, 32, seed=200 + step)
             m.set_input([A, B])
             m.optimize_parameters()
@@ -212,12 +212,13 @@ def test_cuda_graph_step_matches_eager(tmp_path):
         with torch.no_grad():
             out = m.netG_A(A.cuda()).cpu()
         runs.append((losses, out))
-    # the eager warm-up step is bit-identical; afterwards the runs drift apart like two eager runs do (fp64/fp32
-    # atomics order differs run to run and Adam's first updates amplify it: tools/graph_compare.py prints
-    # eager vs eager vs graphs side by side)
+    # the eager warm-up step is bit-identical; afterwards the runs drift apart like two eager runs can (the order of
+    # the fp32 atomics of the CUDA-core wgrad depends on kernel timing, which differs between eager launches and a
+    # graph replay; Adam's first lr*sign(g) updates amplify it step by step: tools/graph_compare.py and
+    # tools/graph_debug.py print eager vs eager vs graphs side by side)
     for i, (le, lg) in enumerate(zip(runs[0][0], runs[1][0])):
         for k in le:
-            rel, ab = (1e-5, 1e-6) if i == 0 else (1e-1, 3e-2)
+            rel, ab = (1e-5, 1e-6) if i == 0 else ((2e-3, 1e-4) if i == 1 else (3e-2, 1e-2))
             assert lg[k] == pytest.approx(le[k], rel=rel, abs=ab), (i, k)
     assert OF.rel_l2(runs[1][1], runs[0][1]) < 1e-1
     assert ops.impl().tc_error() == 0

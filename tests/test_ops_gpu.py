@@ -113,6 +113,14 @@ NORMS = [
     (1, 3, 4, 5, 4, 1, R.ACT_RELU, -1),        # scalar (C % 8 != 0) path
     (1, 2, 2, 2, 512, 0, R.ACT_LRELU, -1),     # tiny reduction, many channels
     (2, 4, 4, 4, 8, 0, R.ACT_NONE, 0),
+    # row-streaming kernels (norm_stream.cuh): wide rows, deep pad folds, residual halo, re-cut rows, degenerate dims
+    (1, 9, 7, 40, 64, 3, R.ACT_RELU, -1),
+    (2, 10, 12, 33, 256, 1, R.ACT_NONE, 1),
+    (1, 15, 15, 15, 512, 0, R.ACT_LRELU, -1),
+    (2, 1, 1, 8, 16, 2, R.ACT_RELU, -1),
+    (1, 3, 3, 1, 8, 1, R.ACT_RELU, -1),
+    (3, 16, 16, 16, 128, 0, R.ACT_LRELU, -1),
+    (1, 12, 12, 12, 256, 1, R.ACT_RELU, -1),
 ]
 
 
