@@ -140,7 +140,7 @@ def run_reference(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def time_dominant_kernel(torch, I, batch, reps=20):
-    """The dominant kernel: the 256->256 k3 conv on the padded 34^3 tensor (G.rb fprop = gather_tc_kernel,
+    """The dominant kernel: the 256->256 k3 conv on the padded 34^3 tensor (G.rb fprop = gather_halo_kernel,
     79.7 % of generator FLOPs).  Timed alone with CUDA events on the launching stream."""
     from mra_gan_b200.ops import ConvGeom
     g = ConvGeom(256, 256, 3, 1, 0)
@@ -161,6 +161,51 @@ def time_dominant_kernel(torch, I, batch, reps=20):
     ms = total / reps
     flops = 2.0 * batch * 32 ** 3 * 256 * 256 * 27
     return ms, flops
+
+
+def time_norm_kernels(torch, I, batch, hbm_peak, reps=10):
+    """HBM-bound companions of the conv kernel: the fused InstanceNorm+ReLU(+pad) forward and backward on the
+    largest activation of the generator (64 channels x 128^3, G.c1 / G.u2 norms).  Algorithmic bytes
+    (SURVEY.md 8d): fwd = read x + write y, bwd = read gy + read x + write dx; the tensors (0.5 GB each at batch 2)
+    are far larger than L2, so no flush is needed between launches."""
+    from mra_gan_b200.ops import ACT_RELU
+    x = torch.randn((batch, 128, 128, 128, 64), device="cuda").to(torch.bfloat16)
+    stats = I.inorm_stats(x)
+    y, mean, rstd = I.inorm_fwd(x, stats, None, 0, ACT_RELU, 0.0, -1)
+    gy = torch.randn_like(y)
+    e = x.numel() * 2
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    t_f = timed(lambda: I.inorm_fwd(x, stats, None, 0, ACT_RELU, 0.0, -1))
+    t_b = timed(lambda: I.inorm_bwd(gy, x, mean, rstd, 0, ACT_RELU, 0.0, -1))
+    out = []
+    for name, ms, nbytes, launches in (("inorm_fwd_stream_kernel (IN+ReLU fwd, 64ch x 128^3)", t_f, 2 * e, 2),
+                                       ("inorm_bwd_stats_stream_kernel + inorm_bwd_stream_kernel (IN+ReLU bwd, 64ch x 128^3)",
+                                        t_b, 3 * e, 2)):
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out.append({"bound": "hbm", "kernel": name, "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": gbs / hbm_peak, "ms_per_call": ms, "algorithmic_bytes": nbytes, "launches_per_call": launches})
+    return out
+
+
+def load_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel, from the committed
+    `ncu --set full` capture (profiles/roofline_traffic.json); None when no capture of this kernel exists."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f).get(kernel, {}).get("dram_bytes")
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def run_gpu(args):
@@ -252,6 +297,7 @@ def run_gpu(args):
 
     peaks, peak_src = load_peaks()
     k_ms, k_flops = time_dominant_kernel(torch, I, per_gpu_batch)
+    norm_roof = time_norm_kernels(torch, I, per_gpu_batch, float(peaks.get("hbm_gbs", 6650.0)))
     achieved = k_flops / (k_ms * 1e-3) / 1e12
     peak = float(peaks.get("bf16_tflops", 1590.0))
     line = {
@@ -269,10 +315,12 @@ def run_gpu(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "model_tflops": global_batch * FLOP_PER_SAMPLE_STEP / (ms_step * 1e-3) / 1e12,
-        "roofline": {"bound": "tensor", "kernel": "gather_tc_kernel (Conv3d 256->256 k3, 34^3->32^3, batch %d)" % per_gpu_batch,
+        "roofline": {"bound": "tensor", "kernel": "gather_halo_kernel (Conv3d 256->256 k3 fprop, 34^3->32^3, batch %d)" % per_gpu_batch,
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "peak_source": peak_src + " bf16_tflops (burst: kernel timed alone)", "ms_per_launch": k_ms,
-                     "traffic": None},
+                     "algorithmic_flop": k_flops,
+                     "traffic": load_traffic("gather_halo_kernel_fprop_b%d" % per_gpu_batch)},
+        "roofline_hbm": norm_roof,
         "tc_error_flag": err,
     }
     if world == 1 and not args.no_cpu_baseline:
