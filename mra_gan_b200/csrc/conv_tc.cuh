@@ -31,7 +31,15 @@
 namespace mra {
 namespace tc {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;                    // wgrad kernel: producer, MMA, 4 epilogue warps
+// Gather kernels: warps 0..7 = epilogue (two per TMEM lane quadrant, quadrant = warp % 4), then the TMA producer(s),
+// and the MMA issuer LAST: the warp scheduler of an SM sub-partition favours the highest warp id among eligible
+// warps, so the single thread that feeds the tensor pipe must not sit below the epilogue warps it shares a
+// scheduler with.
+constexpr int kEpiWarps = 8;
+constexpr int kProdWarp = kEpiWarps;             // TMA producer (A and B boxes / weight ring)
+constexpr int kMmaWarp = kEpiWarps + 1;          // gather_tc / gather_col: TMEM allocator + MMA issuer
+constexpr int kThreadsGather = 32 * (kEpiWarps + 2);
 constexpr int kMaxTaps = 64;
 constexpr uint32_t kABytes = 128 * 128;          // 128 rows x 64 bf16
 
@@ -196,20 +204,30 @@ struct EpiArgs {
 __device__ __noinline__ float act_slow(float v, int act) {
   return act == MRA_ACT_TANH ? tanhf(v) : 1.f / (1.f + expf(-v));
 }
-// One accumulator tile (this warp's 32 TMEM lanes x nchunks * 32 columns) -> bias / stats / activation / store.
-// `release` is called once all TMEM reads of the tile are done.
+// One accumulator tile -> bias / stats / activation / store.  A warp owns the 32 TMEM lanes of its quadrant and the
+// 32-column chunks c = c_begin, c_begin + c_step, ... < nchunks (two warps share a quadrant and take alternate
+// chunks).  `release` is called once this warp's TMEM reads of the tile are done (also when it owns no chunk).
+//
+// InstanceNorm statistics, two flavours:
+//   * defer (the warp owns at most ONE chunk, i.e. n_tile <= 64): every thread adds its row's 32 values and
+//     squares into fp32 registers d1 / d2 across all tiles of the CTA; the 32-lane transpose-reduce happens once
+//     per flush instead of once per tile (it is ~2/3 of the epilogue's instructions, and with N = 64 the epilogue,
+//     not the tensor pipe, bounds the small-K launches);
+//   * otherwise per tile: warp transpose-reduce, fp64 per-lane partials st_s / st_q.
 template <typename Release>
-__device__ __forceinline__ void epilogue_tile(const EpiArgs& E, uint32_t t_addr, int nchunks, bool valid, long long obase, int n0,
-                                              int lane, double* st_s, double* st_q, Release release) {
+__device__ __forceinline__ void epilogue_tile(const EpiArgs& E, uint32_t t_addr, int c_begin, int c_step, int nchunks, bool valid,
+                                              long long obase, int n0, int lane, double* st_s, double* st_q, bool defer,
+                                              float (&d1)[32], float (&d2)[32], Release release) {
   const bool lin_act = E.act == MRA_ACT_RELU || E.act == MRA_ACT_LRELU;
   const float nslope = E.act == MRA_ACT_RELU ? 0.f : E.slope;
+  if (c_begin >= nchunks) { release(); return; }
 #pragma unroll 1
-  for (int c = 0; c < nchunks; ++c) {
+  for (int c = c_begin; c < nchunks; c += c_step) {
     const int c0 = c * 32;
     uint32_t r[32];
     tmem_ld32(t_addr + (uint32_t)c0, r);
     tmem_wait_ld();
-    if (c == nchunks - 1) release();
+    if (c + c_step >= nchunks) release();
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
@@ -222,11 +240,18 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, uint32_t t_addr,
       }
     }
     if (E.stats) {
-      float s1[32], s2[32];
+      if (defer) {
+        if (valid) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) { s1[i] = valid ? v[i] : 0.f; s2[i] = s1[i] * s1[i]; }
-      st_s[c] += (double)warp_colsum32(s1, lane);
-      st_q[c] += (double)warp_colsum32(s2, lane);
+          for (int i = 0; i < 32; ++i) { d1[i] += v[i]; d2[i] = fmaf(v[i], v[i], d2[i]); }
+        }
+      } else {
+        float s1[32], s2[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { s1[i] = valid ? v[i] : 0.f; s2[i] = s1[i] * s1[i]; }
+        st_s[c] += (double)warp_colsum32(s1, lane);
+        st_q[c] += (double)warp_colsum32(s2, lane);
+      }
     }
     if (lin_act) {
 #pragma unroll
@@ -258,18 +283,44 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, uint32_t t_addr,
     }
   }
 }
-// add this warp's per-chunk partial sums to stats[n][Cn][2] (lane = column inside the chunk) and clear them
-__device__ __forceinline__ void epilogue_flush_stats(double* stats, int n, int Cn, int n0, int nchunks, int lane, double* st_s,
-                                                     double* st_q) {
+// Add the CTA's per-chunk partial sums to stats[n][Cn][2] and clear them.  The four quadrant warps that own a chunk
+// first combine their per-lane partials through shared memory, so a flush costs ONE fp64 atomic per channel and CTA:
+// all CTAs flush at the same moment (kernel end), and same-address atomics are serialised by the L2 at ~50 ns each
+// -- with one atomic per WARP (592 per address) that tail was 30 us per launch.
+// Called by all epilogue warps at the same points of the tile sequence (named barrier 1 + group, 128 threads).
+typedef double EpiRed[2][4][32][2];              // [chunk group][quadrant][lane][sum, sum of squares]
+constexpr size_t kEpiRedBytes = sizeof(EpiRed);  // static shared memory of the gather kernels
+__device__ __forceinline__ void epilogue_flush_stats(double* stats, int n, int Cn, int n0, int q, int c_begin, int c_step,
+                                                     int nchunks, int lane, double* st_s, double* st_q, bool defer,
+                                                     float (&d1)[32], float (&d2)[32], EpiRed& red) {
   if (n < 0) return;
+  if (defer && c_begin < nchunks) {
+    st_s[c_begin] += (double)warp_colsum32(d1, lane);
+    st_q[c_begin] += (double)warp_colsum32(d2, lane);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { d1[i] = 0.f; d2[i] = 0.f; }
+  }
 #pragma unroll 1
-  for (int c = 0; c < nchunks; ++c) {
-    double* st = stats + ((long long)n * Cn + n0 + c * 32 + lane) * 2;
-    atomicAdd(st, st_s[c]);
-    atomicAdd(st + 1, st_q[c]);
+  for (int c = c_begin; c < nchunks; c += c_step) {
+    red[c_begin][q][lane][0] = st_s[c];
+    red[c_begin][q][lane][1] = st_q[c];
     st_s[c] = 0.0; st_q[c] = 0.0;
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + c_begin) : "memory");
+    if (q == 0) {
+      const double a = red[c_begin][0][lane][0] + red[c_begin][1][lane][0] + red[c_begin][2][lane][0] + red[c_begin][3][lane][0];
+      const double b = red[c_begin][0][lane][1] + red[c_begin][1][lane][1] + red[c_begin][2][lane][1] + red[c_begin][3][lane][1];
+      double* st = stats + ((long long)n * Cn + n0 + c * 32 + lane) * 2;
+      atomicAdd(st, a);
+      atomicAdd(st + 1, b);
+    }
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + c_begin) : "memory");
   }
 }
+// per-warp epilogue state shared by the three gather kernels
+struct EpiWarp {
+  int q, c_begin;                  // TMEM lane quadrant (warp % 4), first chunk of this warp
+  __device__ __forceinline__ EpiWarp(int warp) : q(warp & 3), c_begin(warp >> 2) {}
+};
 
 // ------------------------------------------------------------------ gather (fprop / dgrad) kernel
 struct GatherP {
@@ -294,15 +345,27 @@ struct GatherP {
   int16_t twi[kMaxTaps];
   int debug;                        // bit 1: cycle counters into dbg (see tc_dbg_counters)
   unsigned long long* dbg;
+  // Merged parity phases (stride-2 dgrad-form plans): ONE launch walks (spatial tile, phase) work items, so the 8
+  // phases of a tile run back to back on neighbouring SMs and re-read the input tile from L2 instead of HBM.
+  int nph;                          // 1 (plain launch) or 8
+  int16_t ph_tap0[9];               // phase p uses taps [ph_tap0[p], ph_tap0[p + 1])
+  int8_t ph_od[8], ph_oh[8], ph_ow[8];   // output coordinate offsets of phase p
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-struct TileCoord { int n, lw0, lh0, ld0, n0; };
+struct TileCoord { int n, lw0, lh0, ld0, n0, ph; };
+// phase of work item `tile` of a merged launch: rotated with the spatial index so that every CTA of the persistent
+// schedule sees all phases (they carry 1..8 taps) equally often
+__device__ __forceinline__ int tile_phase(const GatherP& P, int tile) {
+  return P.nph == 8 ? ((tile & 7) + (tile >> 3)) & 7 : 0;
+}
 __device__ __forceinline__ TileCoord decode_tile(const GatherP& P, int tile) {
   TileCoord t;
+  t.ph = tile_phase(P, tile);
+  if (P.nph == 8) tile >>= 3;
   const int nt = tile % P.n_tiles; tile /= P.n_tiles;
   const int tw = tile % P.tilesW; tile /= P.tilesW;
   const int th = tile % P.tilesH; tile /= P.tilesH;
@@ -316,7 +379,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GatherP& P, int tile) {
 // double-buffered in TMEM so the epilogue of tile j overlaps the MMAs of tile j+1; InstanceNorm
 // statistics are accumulated per CTA in registers and flushed with one fp64 atomic per channel when the
 // sample index changes (instead of per tile).
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsGather, 1)
 gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ GatherP P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -329,23 +392,23 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* acc_empty = acc_full + 2;             // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
+  __shared__ EpiRed epi_red;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int iters = P.ntaps * P.kchunks;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kEpiWarps); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, P.tmem_cols);
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, P.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == kProdWarp) {
     if (elect_one()) {
       uint32_t git = 0;                                    // global k-iteration counter (stage ring position)
       bool ok = true;
@@ -356,7 +419,8 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       (void)git;
       for (int tile = blockIdx.x; tile < P.total_tiles && ok; tile += gridDim.x) {
         const TileCoord t = decode_tile(P, tile);
-        int tap = 0, kc = 0;
+        int tap = P.ph_tap0[t.ph], kc = 0;
+        const int iters = (P.ph_tap0[t.ph + 1] - tap) * P.kchunks;
         for (int it = 0; it < iters; ++it) {
           const long long tw0 = prof ? clock64() : 0;
           if (!mbar_wait(&empty_bar[s], ph ^ 1u, P.err, 1)) { ok = false; break; }
@@ -372,7 +436,7 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       if (prof) { atomicAdd(P.dbg + 0, (unsigned long long)t_wait); atomicAdd(P.dbg + 1, (unsigned long long)(clock64() - t_begin)); }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     if (elect_one()) {
       const uint32_t idesc = make_idesc(P.n_tile, 0, 0);
       const uint64_t desc0 = desc_kmajor_sw128(0);
@@ -392,6 +456,8 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * P.n_tile);
         // single issuing thread: no divisions, descriptors advance by constants (16-byte units)
+        const int tph = tile_phase(P, tile);
+        const int iters = (P.ph_tap0[tph + 1] - P.ph_tap0[tph]) * P.kchunks;
         for (int it = 0; it < iters; ++it) {
           const long long tw0 = prof ? clock64() : 0;
           if (!mbar_wait(&full_bar[s], ph, P.err, 2)) { ok = false; break; }
@@ -415,14 +481,19 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    // epilogue warps 2..5 -> TMEM lane quadrant (warp % 4)
-    const int q = warp & 3;
+    // epilogue warps 0..7 -> TMEM lane quadrant (warp % 4), alternate 32-column chunks
+    const EpiWarp W(warp);
+    const int q = W.q;
     const int row = q * 32 + lane;
     const int rw = row % P.bw, rh = (row / P.bw) % P.bh, rd = row / (P.bw * P.bh);
     const int nchunks = P.n_tile / 32;
+    const bool defer = P.stats != nullptr && nchunks <= 2;
     double st_s[8], st_q[8];                 // per-lane running sums for column (chunk*32 + lane)
 #pragma unroll
     for (int c = 0; c < 8; ++c) { st_s[c] = 0.0; st_q[c] = 0.0; }
+    float d1[32], d2[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { d1[i] = 0.f; d2[i] = 0.f; }
     int st_n = -1, st_n0 = 0;
     const EpiArgs E{P.out, P.out_bf16, P.bias, P.act, P.slope, P.stats != nullptr};
     int j = 0;
@@ -433,10 +504,11 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t aph = ((uint32_t)j >> 1) & 1u;
       const int lw = t.lw0 + rw, lh = t.lh0 + rh, ld = t.ld0 + rd;
       const bool valid = lw < P.Wl && lh < P.Hl && ld < P.Dl;
-      const long long obase = (long long)t.n * P.osn + (long long)(ld * P.ostep + P.od0) * P.osd +
-                              (long long)(lh * P.ostep + P.oh0) * P.osh + (long long)(lw * P.ostep + P.ow0) * P.osw + t.n0;
+      const long long obase = (long long)t.n * P.osn + (long long)(ld * P.ostep + P.ph_od[t.ph]) * P.osd +
+                              (long long)(lh * P.ostep + P.ph_oh[t.ph]) * P.osh +
+                              (long long)(lw * P.ostep + P.ph_ow[t.ph]) * P.osw + t.n0;
       if (P.stats && (t.n != st_n || t.n0 != st_n0)) {
-        epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, nchunks, lane, st_s, st_q);
+        epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, W.q, W.c_begin, 2, nchunks, lane, st_s, st_q, defer, d1, d2, epi_red);
         st_n = t.n; st_n0 = t.n0;
       }
       ok = mbar_wait(&acc_full[buf], aph, P.err, 3);
@@ -445,18 +517,18 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const long long te0 = (P.debug & 2) ? clock64() : 0;
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * P.n_tile);
       uint64_t* rel_bar = &acc_empty[buf];
-      epilogue_tile(E, t_addr, nchunks, valid, obase, t.n0, lane, st_s, st_q, [&]() {
+      epilogue_tile(E, t_addr, W.c_begin, 2, nchunks, valid, obase, t.n0, lane, st_s, st_q, defer, d1, d2, [&]() {
         tc_fence_before();                      // accumulator fully read: hand the buffer back to the MMA warp
         __syncwarp();
         if (lane == 0) mbar_arrive(rel_bar);
       });
-      if ((P.debug & 2) && threadIdx.x == 64) atomicAdd(P.dbg + 4, (unsigned long long)(clock64() - te0));
+      if ((P.debug & 2) && threadIdx.x == 0) atomicAdd(P.dbg + 4, (unsigned long long)(clock64() - te0));
     }
-    if (P.stats) epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, nchunks, lane, st_s, st_q);
+    if (P.stats) epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, W.q, W.c_begin, 2, nchunks, lane, st_s, st_q, defer, d1, d2, epi_red);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, P.tmem_cols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, P.tmem_cols);
 }
 
 // ------------------------------------------------------------------ wgrad kernel
@@ -884,23 +956,40 @@ struct GatherRun {
   double* stats;
 };
 
-// One launch of a gather plan on gather_tc_kernel (one TMA box per filter tap).
-inline int run_gather_v1_launch(const GatherPlan& plan, const GatherLaunch& L, const GatherRun& R, const CUtensorMap& tmB,
+// Can the launches of a plan run as ONE merged launch?  8 parity phases over the same launch space (the stride-2
+// dgrad-form plans of conv_plan.h), unit A step, one tile box, <= kMaxTaps taps in total.
+inline bool gather_mergeable(const GatherPlan& plan) {
+  if (plan.launches.size() != 8 || getenv("MRA_GATHER_NOMERGE")) return false;
+  const GatherLaunch& L0 = plan.launches[0];
+  size_t taps = 0;
+  for (const GatherLaunch& L : plan.launches) {
+    if (L.astep != 1 || L.ostep != L0.ostep) return false;
+    for (int i = 0; i < 3; ++i)
+      if (L.dims[i] != L0.dims[i] || L.box[i] != L0.box[i] || L.o0[i] < -128 || L.o0[i] > 127) return false;
+    taps += L.taps.size();
+  }
+  return taps <= (size_t)kMaxTaps;
+}
+
+// One launch of gather_tc_kernel (one TMA box per filter tap): a single GatherLaunch of the plan, or all 8 parity
+// phases merged (`nl` = 8 consecutive launches starting at `Ls`).
+inline int run_gather_v1_launch(const GatherPlan& plan, const GatherLaunch* Ls, int nl, const GatherRun& R, const CUtensorMap& tmB,
                                 int n_tile, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
     attr_set = true;
   }
-  MRA_REQUIRE((int)L.taps.size() <= kMaxTaps, "too many taps for the tensor-core path");
+  const GatherLaunch& L = Ls[0];
+  MRA_REQUIRE(nl == 1 || nl == 8, "gather launch: 1 or 8 phases");
   GatherP P;
   memset(&P, 0, sizeof(P));
   P.bd = L.box[0]; P.bh = L.box[1]; P.bw = L.box[2];
   P.Dl = L.dims[0]; P.Hl = L.dims[1]; P.Wl = L.dims[2];
   P.tilesD = (P.Dl + P.bd - 1) / P.bd; P.tilesH = (P.Hl + P.bh - 1) / P.bh; P.tilesW = (P.Wl + P.bw - 1) / P.bw;
   P.astep = L.astep;
-  P.Cn = plan.cn; P.n_tile = n_tile; P.n_tiles = plan.cn / n_tile; P.kchunks = plan.ck / 64; P.ntaps = (int)L.taps.size();
-  const long long total_tiles = (long long)plan.n * P.tilesD * P.tilesH * P.tilesW * P.n_tiles;
+  P.Cn = plan.cn; P.n_tile = n_tile; P.n_tiles = plan.cn / n_tile; P.kchunks = plan.ck / 64;
+  const long long total_tiles = (long long)plan.n * P.tilesD * P.tilesH * P.tilesW * P.n_tiles * nl;
   MRA_REQUIRE(total_tiles < (1ll << 31), "too many tiles");
   P.total_tiles = (int)total_tiles;
   P.ostep = L.ostep; P.od0 = L.o0[0]; P.oh0 = L.o0[1]; P.ow0 = L.o0[2];
@@ -913,13 +1002,24 @@ inline int run_gather_v1_launch(const GatherPlan& plan, const GatherLaunch& L, c
   P.stats = R.stats; P.err = tc_err_flag();
   { const char* e = getenv("MRA_GATHER_DEBUG"); P.debug = e ? atoi(e) : 0; }
   P.dbg = tc_dbg_counters();
-  for (int i = 0; i < P.ntaps; ++i) {
-    MRA_REQUIRE(L.taps[i].dd >= -128 && L.taps[i].dd < 128 && L.taps[i].widx < R.slabs, "tap out of range");
-    P.tdd[i] = (int8_t)L.taps[i].dd; P.tdh[i] = (int8_t)L.taps[i].dh; P.tdw[i] = (int8_t)L.taps[i].dw;
-    P.twi[i] = (int16_t)L.taps[i].widx;
+  P.nph = nl;
+  int nt = 0;
+  for (int p = 0; p < nl; ++p) {
+    const GatherLaunch& Lp = Ls[p];
+    P.ph_tap0[p] = (int16_t)nt;
+    P.ph_od[p] = (int8_t)Lp.o0[0]; P.ph_oh[p] = (int8_t)Lp.o0[1]; P.ph_ow[p] = (int8_t)Lp.o0[2];
+    for (const Tap& t : Lp.taps) {
+      MRA_REQUIRE(nt < kMaxTaps, "too many taps for the tensor-core path");
+      MRA_REQUIRE(t.dd >= -128 && t.dd < 128 && t.widx < R.slabs, "tap out of range");
+      P.tdd[nt] = (int8_t)t.dd; P.tdh[nt] = (int8_t)t.dh; P.tdw[nt] = (int8_t)t.dw;
+      P.twi[nt] = (int16_t)t.widx;
+      ++nt;
+    }
   }
+  P.ph_tap0[nl] = (int16_t)nt;
+  P.ntaps = nt;
   const size_t stage_bytes = kABytes + (size_t)n_tile * 128;
-  int stages = (int)((kSmemLimit - 2048) / stage_bytes);
+  int stages = (int)((kSmemLimit - 2048 - kEpiRedBytes) / stage_bytes);
   if (stages > 6) stages = 6;
   P.stages = stages;
   P.tmem_cols = pow2_cols(2 * n_tile);
@@ -929,7 +1029,7 @@ inline int run_gather_v1_launch(const GatherPlan& plan, const GatherLaunch& L, c
                             P.astep))
     return rc;
   const int ctas = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
-  gather_tc_kernel<<<ctas, kThreads, smem, st>>>(tmA, tmB, P);
+  gather_tc_kernel<<<ctas, kThreadsGather, smem, st>>>(tmA, tmB, P);
   MRA_LAUNCH_CHECK();
   return 0;
 }

@@ -7,7 +7,7 @@
 //   * a ring of input planes (one 16 x 8 position tile of one d-plane, 64 channels = 16 KB): stepping to the next
 //     output plane loads ONE new plane instead of kd, and costs ONE barrier wait for 4 * kd back-to-back MMAs.
 // Columns are cut into segments along d so that the persistent CTAs get a balanced number of work units.
-// Warp roles as in conv_tc.cuh: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue.
+// Warp roles as in conv_tc.cuh: 0..7 = epilogue, 8 = TMA producer, 9 = TMEM allocator + MMA issuer.
 #pragma once
 #include "conv_tc.cuh"
 
@@ -37,7 +37,7 @@ struct ColP {
   unsigned long long* dbg;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsGather, 1)
 gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ ColP P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -53,6 +53,7 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* acc_full = w_bar + 1;                // [2]
   uint64_t* acc_empty = acc_full + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  __shared__ EpiRed epi_red;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -60,10 +61,10 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     prefetch_tmap(&tmB);
     for (int s = 0; s < P.NPR; ++s) { mbar_init(&p_full[s], 1); mbar_init(&p_empty[s], 1); }
     mbar_init(w_bar, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kEpiWarps); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, P.tmem_cols);
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, P.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -79,7 +80,7 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     len = min(P.seg_len, P.Dl - d0);
   };
 
-  if (warp == 0) {
+  if (warp == kProdWarp) {
     if (elect_one()) {
       // resident weights: every (tap, chunk) slab once
       mbar_expect_tx(w_bar, w_bytes);
@@ -103,7 +104,7 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     if (elect_one()) {
       const uint32_t idesc = make_idesc(P.n_tile, 0, 0);
       const uint64_t desc0 = desc_kmajor_sw128(0);
@@ -168,12 +169,17 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    const int q = warp & 3;
+    const EpiWarp W(warp);
+    const int q = W.q;
     const int row = q * 32 + lane;
     const int nchunks = P.n_tile / 32;
+    const bool defer = P.stats != nullptr && nchunks <= 2;
     double st_s[8], st_q[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) { st_s[c] = 0.0; st_q[c] = 0.0; }
+    float d1[32], d2[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { d1[i] = 0.f; d2[i] = 0.f; }
     int st_n = -1;
     const EpiArgs E{P.out, P.out_bf16, P.bias, P.act, P.slope, P.stats != nullptr};
     int jt = 0;
@@ -183,7 +189,10 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       unit_coords(u, n, h0, w0, d0, len);
       const int lh = h0 + (row >> 3), lw = w0 + (row & 7);
       const bool valid = lw < P.Wl && lh < P.Hl;
-      if (P.stats && n != st_n) { epilogue_flush_stats(P.stats, st_n, P.Cn, 0, nchunks, lane, st_s, st_q); st_n = n; }
+      if (P.stats && n != st_n) {
+        epilogue_flush_stats(P.stats, st_n, P.Cn, 0, W.q, W.c_begin, 2, nchunks, lane, st_s, st_q, defer, d1, d2, epi_red);
+        st_n = n;
+      }
       for (int j = 0; j < len && ok; ++j, ++jt) {
         const int buf = jt & 1;
         const uint32_t aph = ((uint32_t)jt >> 1) & 1u;
@@ -194,18 +203,18 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * P.n_tile);
         uint64_t* rel_bar = &acc_empty[buf];
-        epilogue_tile(E, t_addr, nchunks, valid, obase, 0, lane, st_s, st_q, [&]() {
+        epilogue_tile(E, t_addr, W.c_begin, 2, nchunks, valid, obase, 0, lane, st_s, st_q, defer, d1, d2, [&]() {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(rel_bar);
         });
       }
     }
-    if (P.stats) epilogue_flush_stats(P.stats, st_n, P.Cn, 0, nchunks, lane, st_s, st_q);
+    if (P.stats) epilogue_flush_stats(P.stats, st_n, P.Cn, 0, W.q, W.c_begin, 2, nchunks, lane, st_s, st_q, defer, d1, d2, epi_red);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, P.tmem_cols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, P.tmem_cols);
 }
 
 // Eligibility + geometry: unit A step, taps along d only forming a contiguous range, one output-channel tile,
@@ -231,7 +240,7 @@ inline bool col_setup(const GatherLaunch& L, int n, int ck, int cn, ColP& P) {
   P.Dl = L.dims[0]; P.Hl = L.dims[1]; P.Wl = L.dims[2]; P.N = n;
   P.Cn = cn; P.n_tile = n_tile; P.kchunks = ck / 64;
   P.tiles_w = (P.Wl + 7) / 8; P.tiles_hw = ((P.Hl + 15) / 16) * P.tiles_w;
-  const size_t budget = kSmemLimit - 2048;
+  const size_t budget = kSmemLimit - 2048 - kEpiRedBytes;
   const size_t w_bytes = (size_t)kd * P.kchunks * n_tile * 128;
   const size_t slot = (size_t)kABytes * P.kchunks;
   if (w_bytes + (size_t)(kd + 1) * slot > budget) return false;
@@ -256,7 +265,7 @@ inline int run_gather_col(const GatherPlan& plan, const GatherLaunch& L, ColP& P
                           cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
     attr_set = true;
   }
   P.ostep = L.ostep; P.od0 = L.o0[0]; P.oh0 = L.o0[1]; P.ow0 = L.o0[2];
@@ -274,7 +283,7 @@ inline int run_gather_col(const GatherPlan& plan, const GatherLaunch& L, ColP& P
   if (int rc = make_act_map(&tmA, R.a, plan.n, plan.adims[0], plan.adims[1], plan.adims[2], plan.ck, 8, 16, 1, 1)) return rc;
   const size_t smem = (size_t)P.kd * P.kchunks * P.n_tile * 128 + (size_t)P.NPR * kABytes * P.kchunks + 1024 + 512;
   const int ctas = P.total_units < num_sms() ? P.total_units : num_sms();
-  gather_col_kernel<<<ctas, kThreads, smem, st>>>(tmA, tmB, P);
+  gather_col_kernel<<<ctas, kThreadsGather, smem, st>>>(tmA, tmB, P);
   MRA_LAUNCH_CHECK();
   return 0;
 }

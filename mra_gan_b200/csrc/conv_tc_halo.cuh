@@ -16,8 +16,8 @@
 //          dense tile); the kw - 1 positions per line that wrap around are computed and discarded.  Used when
 //          the 2D shape would waste more (e.g. the 34^3 dgrad of the residual blocks: 90 % vs 60 % useful rows).
 //
-// Warp roles: 0 = TMA producer of the weight ring, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue,
-// 6 = TMA producer of the plane ring.  Persistent over tiles, accumulators double-buffered in TMEM.
+// Warp roles: 0..7 = epilogue (two per TMEM lane quadrant, alternate 32-column chunks), 8 = TMA producer of the weight
+// ring, 9 = TMA producer of the plane ring, 10 = TMEM allocator + MMA issuer (highest warp id: scheduler priority).  Persistent over tiles, accumulators double-buffered in TMEM.
 #pragma once
 #include "conv_tc.cuh"
 #include "conv_tc_col.cuh"
@@ -25,7 +25,9 @@
 namespace mra {
 namespace tc {
 
-constexpr int kThreadsHalo = 224;
+constexpr int kHaloPlaneWarp = kEpiWarps + 1;
+constexpr int kHaloMmaWarp = kEpiWarps + 2;
+constexpr int kThreadsHalo = 32 * (kEpiWarps + 3);
 
 struct HaloP {
   int Dl, Hl, Wl;                   // launch-space (output) dims
@@ -180,6 +182,7 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* acc_empty = acc_full + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
+  __shared__ EpiRed epi_red;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = kPair ? (int)cluster_ctarank() : 0;
   const bool leader = rank == 0;
@@ -201,10 +204,10 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     prefetch_tmap(&tmB);
     for (int s = 0; s < P.NP; ++s) { mbar_init(&p_full[s], 1); mbar_init(&p_empty[s], 1); }
     for (int s = 0; s < P.NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4 * kCtas); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kEpiWarps * kCtas); }
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == kHaloMmaWarp) {
     if constexpr (kPair) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(P.tmem_cols)
                    : "memory");
@@ -219,7 +222,7 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   const bool dbg_nob = (P.debug & 4) != 0, dbg_nop = (P.debug & 8) != 0;     // timing experiments: no weight / plane traffic
-  if (warp == 6) {
+  if (warp == kHaloPlaneWarp) {
     // ---- plane producer: one halo plane per (work item, channel chunk, td); each CTA loads its own tile's planes
     if (elect_one() && !dbg_nop) {
       int s = 0;
@@ -238,7 +241,7 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
       }
     }
-  } else if (warp == 0) {
+  } else if (warp == kProdWarp) {
     // ---- weight producer: one (64 x n_tile) slab per (work item, channel chunk, tap); pair: each CTA its half
     if (elect_one() && !dbg_nob) {
       int s = 0;
@@ -266,7 +269,7 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
       if (prof) { atomicAdd(P.dbg + 0, (unsigned long long)t_wait); atomicAdd(P.dbg + 1, (unsigned long long)(clock64() - t_begin)); }
     }
-  } else if (warp == 1) {
+  } else if (warp == kHaloMmaWarp) {
     if (elect_one() && leader) {
       // The issue loop is a single thread: keep it to a few dozen instructions per stage (no divisions, the
       // descriptors advance by adding constants to their 16-byte-unit address field).
@@ -338,13 +341,18 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
   } else {
-    // ---- epilogue warps 2..5 -> TMEM lane quadrant (warp % 4)
-    const int q = warp & 3;
+    // ---- epilogue warps 0..7 -> TMEM lane quadrant (warp % 4), alternate 32-column chunks
+    const EpiWarp W(warp);
+    const int q = W.q;
     const int row = q * 32 + lane;
     int nchunks = P.n_tile / 32;
+    const bool defer = P.stats != nullptr && nchunks <= 2;
     double st_s[8], st_q[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) { st_s[c] = 0.0; st_q[c] = 0.0; }
+    float d1[32], d2[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { d1[i] = 0.f; d2[i] = 0.f; }
     int st_n = -1, st_n0 = 0;
     const EpiArgs E{P.out, P.out_bf16, P.bias, P.act, P.slope, P.stats != nullptr};
     int j = 0;
@@ -360,7 +368,7 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const long long obase = (long long)t.n * P.osn + (long long)(t.d * P.ostep + P.od0) * P.osd +
                               (long long)(lh * P.ostep + P.oh0) * P.osh + (long long)(lw * P.ostep + P.ow0) * P.osw + t.n0;
       if (P.stats && (t.n != st_n || t.n0 != st_n0)) {
-        epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, nchunks, lane, st_s, st_q);
+        epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, W.q, W.c_begin, 2, nchunks, lane, st_s, st_q, defer, d1, d2, epi_red);
         st_n = t.n; st_n0 = t.n0;
       }
       nchunks = t.width / 32;
@@ -370,18 +378,18 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const long long te0 = prof ? clock64() : 0;
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * P.n_tile);
       uint64_t* rel_bar = &acc_empty[buf];
-      epilogue_tile(E, t_addr, nchunks, valid, obase, t.n0, lane, st_s, st_q, [&]() {
+      epilogue_tile(E, t_addr, W.c_begin, 2, nchunks, valid, obase, t.n0, lane, st_s, st_q, defer, d1, d2, [&]() {
         tc_fence_before();                      // accumulator fully read: hand the buffer back to the MMA warp
         __syncwarp();
         if (lane == 0) { if constexpr (kPair) mbar_arrive_leader(rel_bar); else mbar_arrive(rel_bar); }
       });
-      if (prof && threadIdx.x == 64) atomicAdd(P.dbg + 4, (unsigned long long)(clock64() - te0));
+      if (prof && threadIdx.x == 0) atomicAdd(P.dbg + 4, (unsigned long long)(clock64() - te0));
     }
-    if (P.stats) epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, nchunks, lane, st_s, st_q);
+    if (P.stats) epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, W.q, W.c_begin, 2, nchunks, lane, st_s, st_q, defer, d1, d2, epi_red);
   }
   tc_fence_before();
   if constexpr (kPair) cluster_sync_all(); else __syncthreads();
-  if (warp == 1) {
+  if (warp == kHaloMmaWarp) {
     if constexpr (kPair)
       asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols) : "memory");
     else
@@ -422,7 +430,7 @@ inline bool halo_setup(const GatherLaunch& L, int n, int ck, int cn, bool pair, 
   const int tf = (int)((flat_len + 127) / 128);
   const int Hbf = (Wbf - 1 + 128 + (kh - 1) * Wbf + (kw - 1) + Wbf - 1) / Wbf;   // lines covering any 128-run + halo
   const long long rowsf = (long long)tf * 128;
-  const size_t budget = kSmemLimit - 2048;
+  const size_t budget = kSmemLimit - 2048 - kEpiRedBytes;
   auto fits = [&](int Wb, int Hb) {
     if (Wb > 256 || Hb > 256) return false;
     const size_t slot = ((size_t)Wb * Hb * 128 + 1023) / 1024 * 1024;
@@ -481,8 +489,8 @@ inline int run_gather_halo(const GatherPlan& plan, const GatherLaunch& L, HaloP&
     } }
   static bool attr_set = false;
   if (!attr_set) {
-    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
     attr_set = true;
   }
   P.ostep = L.ostep; P.od0 = L.o0[0]; P.oh0 = L.o0[1]; P.ow0 = L.o0[2];
@@ -534,6 +542,12 @@ inline int run_gather_tc(const GatherPlan& plan, const GatherRun& R, cudaStream_
   const bool force_v1 = gm && !strcmp(gm, "v1");
   const bool no_pair = gm && !strcmp(gm, "single");
   const bool no_col = gm && !strcmp(gm, "nocol");
+  if (!force_v1 && gather_mergeable(plan)) {
+    bool slabs_ok = true;
+    for (const GatherLaunch& L : plan.launches)
+      for (const Tap& t : L.taps) if (t.widx >= R.slabs) slabs_ok = false;
+    if (slabs_ok) return run_gather_v1_launch(plan, plan.launches.data(), 8, R, tmB, n_tile, st);
+  }
   for (const GatherLaunch& L : plan.launches) {
     bool slabs_ok = true;
     for (const Tap& t : L.taps) if (t.widx >= R.slabs) slabs_ok = false;
@@ -555,7 +569,7 @@ inline int run_gather_tc(const GatherPlan& plan, const GatherRun& R, cudaStream_
     bool halo = !force_v1 && reuse && halo_setup(L, plan.n, plan.ck, plan.cn, !no_pair, P);
     if (halo) for (const Tap& t : L.taps) if (t.widx >= R.slabs) halo = false;
     if (halo) { if (int rc = run_gather_halo(plan, L, P, R, tmB, st)) return rc; }
-    else      { if (int rc = run_gather_v1_launch(plan, L, R, tmB, n_tile, st)) return rc; }
+    else      { if (int rc = run_gather_v1_launch(plan, &L, 1, R, tmB, n_tile, st)) return rc; }
   }
   return 0;
 }

@@ -20,7 +20,7 @@ def timeit(fn, reps=10):
     for _ in range(reps): fn()
     e1.record(); e1.synchronize()
     return e0.elapsed_time(e1) / reps
-for name, fn in (("fprop", lambda: I.conv_fprop(x, w, None, g, want_stats=g.cout > 1)), ("dgrad", lambda: I.conv_dgrad(dy, wT, g, dims)),
+for name, fn in (("fprop", lambda: I.conv_fprop(x, w, None, g, want_stats=(g.cout > 1 and os.environ.get("STATS", "1") == "1"))), ("dgrad", lambda: I.conv_dgrad(dy, wT, g, dims)),
                  ("wgrad", lambda: I.conv_wgrad(x, dy, g))):
     if os.environ.get("ONLY") and os.environ["ONLY"] != name: continue
     I.debug_counters()
@@ -34,7 +34,7 @@ for name, fn in (("fprop", lambda: I.conv_fprop(x, w, None, g, want_stats=g.cout
     print("%s %.4f ms  %.1f TFLOP/s  (flag %d)" % (name, t, 2 * macs / t / 1e9, I.tc_error()), flush=True)
 if os.environ.get("KERNELS"):
     from torch.profiler import ProfilerActivity, profile
-    for name, fn in (("fprop", lambda: I.conv_fprop(x, w, None, g, want_stats=g.cout > 1)), ("dgrad", lambda: I.conv_dgrad(dy, wT, g, dims)),
+    for name, fn in (("fprop", lambda: I.conv_fprop(x, w, None, g, want_stats=(g.cout > 1 and os.environ.get("STATS", "1") == "1"))), ("dgrad", lambda: I.conv_dgrad(dy, wT, g, dims)),
                      ("wgrad", lambda: I.conv_wgrad(x, dy, g))):
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
             fn(); torch.cuda.synchronize()
