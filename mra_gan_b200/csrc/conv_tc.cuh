@@ -340,7 +340,9 @@ struct GatherP {
   double* stats;                    // [N][Cn][2] or null
   int* err;
   int stages;
-  uint32_t tmem_cols;               // 2 accumulator buffers of n_tile columns (power of two >= 32)
+  int nbuf;                         // accumulator buffers in TMEM: 512 / n_tile, at most 8 (small tiles: the buffer
+                                    // turnaround MMA -> commit -> epilogue -> release is ~1 us, far more than their MMAs)
+  uint32_t tmem_cols;               // nbuf accumulator buffers of n_tile columns (power of two >= 32)
   int8_t tdd[kMaxTaps], tdh[kMaxTaps], tdw[kMaxTaps];
   int16_t twi[kMaxTaps];
   int debug;                        // bit 1: cycle counters into dbg (see tc_dbg_counters)
@@ -388,9 +390,9 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t stage_bytes = kABytes + b_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + P.stages;
-  uint64_t* acc_full = empty_bar + P.stages;      // [2]
-  uint64_t* acc_empty = acc_full + 2;             // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* acc_full = empty_bar + P.stages;      // [nbuf]
+  uint64_t* acc_empty = acc_full + P.nbuf;        // [nbuf]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + P.nbuf);
 
   __shared__ EpiRed epi_red;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -399,7 +401,7 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kEpiWarps); }
+    for (int b = 0; b < P.nbuf; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, P.tmem_cols);
@@ -447,9 +449,9 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int j = 0;
       const bool prof = (P.debug & 2) != 0;
       long long t_wait = 0, t_wacc = 0, t_begin = prof ? clock64() : 0;
+      int buf = 0;
+      uint32_t aph = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles && ok; tile += gridDim.x, ++j) {
-        const int buf = j & 1;
-        const uint32_t aph = ((uint32_t)j >> 1) & 1u;
         const long long ta0 = prof ? clock64() : 0;
         if (!mbar_wait(&acc_empty[buf], aph ^ 1u, P.err, 4)) { ok = false; break; }   // epilogue drained this buffer
         if (prof) t_wacc += clock64() - ta0;
@@ -474,6 +476,7 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (++s == P.stages) { s = 0; ph ^= 1u; }
         }
         if (ok) umma_commit(&acc_full[buf]);
+        if (++buf == P.nbuf) { buf = 0; aph ^= 1u; }
       }
       if (prof) {
         atomicAdd(P.dbg + 2, (unsigned long long)t_wait); atomicAdd(P.dbg + 3, (unsigned long long)(clock64() - t_begin));
@@ -496,12 +499,11 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int i = 0; i < 32; ++i) { d1[i] = 0.f; d2[i] = 0.f; }
     int st_n = -1, st_n0 = 0;
     const EpiArgs E{P.out, P.out_bf16, P.bias, P.act, P.slope, P.stats != nullptr};
-    int j = 0;
+    int buf = 0;
+    uint32_t aph = 0;
     bool ok = true;
-    for (int tile = blockIdx.x; tile < P.total_tiles && ok; tile += gridDim.x, ++j) {
+    for (int tile = blockIdx.x; tile < P.total_tiles && ok; tile += gridDim.x) {
       const TileCoord t = decode_tile(P, tile);
-      const int buf = j & 1;
-      const uint32_t aph = ((uint32_t)j >> 1) & 1u;
       const int lw = t.lw0 + rw, lh = t.lh0 + rh, ld = t.ld0 + rd;
       const bool valid = lw < P.Wl && lh < P.Hl && ld < P.Dl;
       const long long obase = (long long)t.n * P.osn + (long long)(ld * P.ostep + P.ph_od[t.ph]) * P.osd +
@@ -523,6 +525,7 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) mbar_arrive(rel_bar);
       });
       if ((P.debug & 2) && threadIdx.x == 0) atomicAdd(P.dbg + 4, (unsigned long long)(clock64() - te0));
+      if (++buf == P.nbuf) { buf = 0; aph ^= 1u; }
     }
     if (P.stats) epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, W.q, W.c_begin, 2, nchunks, lane, st_s, st_q, defer, d1, d2, epi_red);
   }
@@ -1022,7 +1025,9 @@ inline int run_gather_v1_launch(const GatherPlan& plan, const GatherLaunch* Ls, 
   int stages = (int)((kSmemLimit - 2048 - kEpiRedBytes) / stage_bytes);
   if (stages > 6) stages = 6;
   P.stages = stages;
-  P.tmem_cols = pow2_cols(2 * n_tile);
+  P.nbuf = 512 / n_tile > 8 ? 8 : 512 / n_tile;
+  { const char* e = getenv("MRA_GATHER_NBUF"); if (e && atoi(e) >= 2 && atoi(e) <= P.nbuf) P.nbuf = atoi(e); }
+  P.tmem_cols = pow2_cols(P.nbuf * n_tile);
   const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
   CUtensorMap tmA;
   if (int rc = make_act_map(&tmA, R.a, plan.n, plan.adims[0], plan.adims[1], plan.adims[2], plan.ck, P.bw, P.bh, P.bd,

@@ -31,6 +31,7 @@ struct ColP {
   float slope;
   double* stats;
   int* err;
+  int nbuf;                         // accumulator buffers in TMEM (512 / n_tile, at most 8)
   uint32_t tmem_cols;
   int16_t twi[kMaxTaps];            // weight slab of tap td
   int debug;
@@ -50,9 +51,9 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* p_full = reinterpret_cast<uint64_t*>(ring + (size_t)P.NPR * slot_bytes);
   uint64_t* p_empty = p_full + P.NPR;
   uint64_t* w_bar = p_empty + P.NPR;
-  uint64_t* acc_full = w_bar + 1;                // [2]
-  uint64_t* acc_empty = acc_full + 2;            // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* acc_full = w_bar + 1;                // [nbuf]
+  uint64_t* acc_empty = acc_full + P.nbuf;       // [nbuf]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + P.nbuf);
   __shared__ EpiRed epi_red;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -61,7 +62,7 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     prefetch_tmap(&tmB);
     for (int s = 0; s < P.NPR; ++s) { mbar_init(&p_full[s], 1); mbar_init(&p_empty[s], 1); }
     mbar_init(w_bar, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kEpiWarps); }
+    for (int b = 0; b < P.nbuf; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, P.tmem_cols);
@@ -116,7 +117,9 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int s_old = 0;                 // ring slot of the oldest plane of the current tile
       int s_new = 0;                 // ring slot (and phase) of the next plane to wait for
       uint32_t ph_new = 0;
-      int jt = 0;                    // tiles issued by this CTA (accumulator buffer / phase)
+      int jt = 0;                    // tiles issued by this CTA
+      int buf = 0;                   // accumulator buffer / phase of the next tile
+      uint32_t aph = 0;
       const bool prof = (P.debug & 2) != 0;
       long long t_wacc = 0, t_wp = 0, t_begin = prof ? clock64() : 0;
       for (int u = blockIdx.x; u < P.total_units && ok; u += gridDim.x) {
@@ -124,8 +127,6 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         unit_coords(u, n, h0, w0, d0, len);
         int have = 0;                // planes of this unit already waited for
         for (int j = 0; j < len && ok; ++j, ++jt) {
-          const int buf = jt & 1;
-          const uint32_t aph = ((uint32_t)jt >> 1) & 1u;
           const long long t0 = prof ? clock64() : 0;
           if (!mbar_wait(&acc_empty[buf], aph ^ 1u, P.err, 34)) { ok = false; break; }
           const long long t1 = prof ? clock64() : 0;
@@ -155,6 +156,7 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (++s == NPR) s = 0;
           }
           umma_commit(&acc_full[buf]);
+          if (++buf == P.nbuf) { buf = 0; aph ^= 1u; }
           // the oldest plane is dead after this tile; after the unit's last tile so are the other kd - 1
           const int nrel = (j == len - 1) ? kd : 1;
           for (int r = 0; r < nrel; ++r) {
@@ -182,7 +184,8 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int i = 0; i < 32; ++i) { d1[i] = 0.f; d2[i] = 0.f; }
     int st_n = -1;
     const EpiArgs E{P.out, P.out_bf16, P.bias, P.act, P.slope, P.stats != nullptr};
-    int jt = 0;
+    int buf = 0;
+    uint32_t aph = 0;
     bool ok = true;
     for (int u = blockIdx.x; u < P.total_units && ok; u += gridDim.x) {
       int n, h0, w0, d0, len;
@@ -193,9 +196,7 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         epilogue_flush_stats(P.stats, st_n, P.Cn, 0, W.q, W.c_begin, 2, nchunks, lane, st_s, st_q, defer, d1, d2, epi_red);
         st_n = n;
       }
-      for (int j = 0; j < len && ok; ++j, ++jt) {
-        const int buf = jt & 1;
-        const uint32_t aph = ((uint32_t)jt >> 1) & 1u;
+      for (int j = 0; j < len && ok; ++j) {
         const long long obase = (long long)n * P.osn + (long long)((d0 + j) * P.ostep + P.od0) * P.osd +
                                 (long long)(lh * P.ostep + P.oh0) * P.osh + (long long)(lw * P.ostep + P.ow0) * P.osw;
         ok = mbar_wait(&acc_full[buf], aph, P.err, 33);
@@ -208,6 +209,7 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           __syncwarp();
           if (lane == 0) mbar_arrive(rel_bar);
         });
+        if (++buf == P.nbuf) { buf = 0; aph ^= 1u; }
       }
     }
     if (P.stats) epilogue_flush_stats(P.stats, st_n, P.Cn, 0, W.q, W.c_begin, 2, nchunks, lane, st_s, st_q, defer, d1, d2, epi_red);
@@ -278,7 +280,8 @@ inline int run_gather_col(const GatherPlan& plan, const GatherLaunch& L, ColP& P
   P.stats = R.stats; P.err = tc_err_flag();
   { const char* e = getenv("MRA_GATHER_DEBUG"); P.debug = e ? atoi(e) : 0; }
   P.dbg = tc_dbg_counters();
-  P.tmem_cols = pow2_cols(2 * P.n_tile);
+  P.nbuf = 512 / P.n_tile > 8 ? 8 : 512 / P.n_tile;
+  P.tmem_cols = pow2_cols(P.nbuf * P.n_tile);
   CUtensorMap tmA;
   if (int rc = make_act_map(&tmA, R.a, plan.n, plan.adims[0], plan.adims[1], plan.adims[2], plan.ck, 8, 16, 1, 1)) return rc;
   const size_t smem = (size_t)P.kd * P.kchunks * P.n_tile * 128 + (size_t)P.NPR * kABytes * P.kchunks + 1024 + 512;

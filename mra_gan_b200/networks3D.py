@@ -42,9 +42,11 @@ def get_default_compute_dtype():
     return _default_compute_dtype
 
 
-# bumped by the fused optimiser after every step so cached compute-dtype weight copies refresh
+# The fused optimiser updates weights through raw pointers (no torch in-place op, so ``_version`` does not move):
+# it bumps ``p._mra_epoch`` of every parameter it touched so cached compute-dtype copies refresh.  The counter is
+# per parameter on purpose: a step of the discriminators' optimiser must not invalidate the generators' caches.
 class _WeightsEpoch:
-    value = 0
+    value = 0          # total optimiser steps (diagnostics only)
 
 
 ###############################################################################
@@ -92,7 +94,7 @@ class _ConvNd(nn.Module):
         return self._packed_view(self.weight.detach())
 
     def _tag(self):
-        return (self.weight._version, _WeightsEpoch.value, self.weight.data_ptr())
+        return (self.weight._version, getattr(self.weight, "_mra_epoch", 0), self.weight.data_ptr())
 
     def packed_weight(self, dtype):
         """[taps][Cout][Cin] in the compute dtype (the master itself for fp32)."""

@@ -44,6 +44,7 @@ class FusedAdam(torch.optim.Optimizer):
                 if st:
                     st["step"] += 1
                     step_no = st["step"]
+                    self._mark(p)                      # the replayed Adam kernel rewrites weight and shadow
             if step_no is not None and gi in self.__dict__.get("_hyper", {}):
                 self._fill_hyper(self._hyper[gi][0], group, step_no)
         _WeightsEpoch.value += 1
@@ -52,7 +53,6 @@ class FusedAdam(torch.optim.Optimizer):
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         I = ops.impl()
-        new_epoch = _WeightsEpoch.value + 1
         use_dev = hasattr(I, "adam_step_dev")
         for gi, group in enumerate(self.param_groups):
             ps, gs, ms, vs, shs = [], [], [], [], []
@@ -72,7 +72,7 @@ class FusedAdam(torch.optim.Optimizer):
                     # parameters that joined late get their own sweep below
                     I.adam_step([p], [self._grad(p)], [st["exp_avg"]], [st["exp_avg_sq"]], [self._shadow(p)],
                                 group["lr"], group["betas"][0], group["betas"][1], group["eps"], st["step"])
-                    self._mark(p, new_epoch)
+                    self._mark(p)
                     continue
                 ps.append(p); gs.append(self._grad(p)); ms.append(st["exp_avg"]); vs.append(st["exp_avg_sq"])
                 shs.append(self._shadow(p))
@@ -86,8 +86,8 @@ class FusedAdam(torch.optim.Optimizer):
                     I.adam_step(ps, gs, ms, vs, shs, group["lr"], group["betas"][0], group["betas"][1], group["eps"],
                                 step_no)
                 for p in ps:
-                    self._mark(p, new_epoch)
-        _WeightsEpoch.value = new_epoch
+                    self._mark(p)
+        _WeightsEpoch.value += 1
         return loss
 
     @staticmethod
@@ -102,7 +102,9 @@ class FusedAdam(torch.optim.Optimizer):
         return getattr(p, "_mra_shadow", None)
 
     @staticmethod
-    def _mark(p, epoch):
+    def _mark(p):
+        """The weight behind ``p`` changed (and its bf16 shadow with it): bump the parameter's epoch and stamp the
+        shadow with the tag _ConvNd._tag() computes from now on."""
+        p._mra_epoch = getattr(p, "_mra_epoch", 0) + 1
         if getattr(p, "_mra_shadow", None) is not None:
-            # tag = (version, epoch, data_ptr) as computed by _ConvNd._tag() after this step
-            p._mra_shadow_tag = (p._version, epoch, p.data_ptr())
+            p._mra_shadow_tag = (p._version, p._mra_epoch, p.data_ptr())
