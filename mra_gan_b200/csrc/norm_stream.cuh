@@ -164,8 +164,9 @@ struct RowWalk {
 
 // ------------------------------------------------------------------------------------------------ forward
 template <typename T, int CONS>
-__global__ void __launch_bounds__(CONS + 32, 1) inorm_fwd_stream_kernel(const T* __restrict__ x, const float* __restrict__ mean,
-                                                                         const float* __restrict__ rstd,
+__global__ void __launch_bounds__(CONS + 32, 1) inorm_fwd_stream_kernel(const T* __restrict__ x, const double* __restrict__ stats,
+                                                                         float* __restrict__ mean, float* __restrict__ rstd,
+                                                                         float* running_mean, float* running_var,
                                                                          const T* __restrict__ res, T* __restrict__ y,
                                                                          const StreamP S) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -191,9 +192,41 @@ __global__ void __launch_bounds__(CONS + 32, 1) inorm_fwd_stream_kernel(const T*
     return;
   }
   const int G = P.G, cg = t & (G - 1), wl = t >> S.lgG, wpp = CONS >> S.lgG, lane = t & 31;
+  // mean / rstd of this thread's 8 channels straight from the conv epilogue's {sum, sum of squares} (the former
+  // finalize kernel, same arithmetic); the first CTA of every sample also publishes them for the backward pass and
+  // CTA (0, 0) applies the running-statistics EMA (torch: buffers averaged over the batch, unbiased variance)
   F8 nmu, rs;
-  load_pairs(mean + n * P.C + cg * 8, nmu, -1.f);
-  load_pairs(rstd + n * P.C + cg * 8, rs, 1.f);
+  {
+    float m8[8], r8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cg * 8 + j;
+      if (P.use_running) { m8[j] = running_mean[c]; r8[j] = 1.0f / sqrtf(running_var[c] + P.eps); }
+      else mean_rstd_from_stats(stats + ((long long)n * P.C + c) * 2, P.V, P.eps, m8[j], r8[j]);
+    }
+    if (blockIdx.x == 0 && wl == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { mean[n * P.C + cg * 8 + j] = m8[j]; rstd[n * P.C + cg * 8 + j] = r8[j]; }
+      if (n == 0 && !P.use_running && running_mean) {
+        for (int j = 0; j < 8; ++j) {
+          const int c = cg * 8 + j;
+          double msum = 0.0, vsum = 0.0;
+          for (int nn = 0; nn < P.N; ++nn) {
+            const double* st = stats + ((long long)nn * P.C + c) * 2;
+            const double mu = st[0] / (double)P.V;
+            double var = st[1] / (double)P.V - mu * mu;
+            if (var < 0.0) var = 0.0;
+            msum += mu;
+            vsum += var * ((double)P.V / (double)(P.V - 1));
+          }
+          running_mean[c] = (1.f - P.momentum) * running_mean[c] + P.momentum * (float)(msum / P.N);
+          running_var[c] = (1.f - P.momentum) * running_var[c] + P.momentum * (float)(vsum / P.N);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { nmu[i] = make_float2(-m8[2 * i], -m8[2 * i + 1]); rs[i] = make_float2(r8[2 * i], r8[2 * i + 1]); }
+  }
   const float2 nsl = bc2(norm_neg_slope(P));
   T* yn = y + (long long)n * Dp * Hp * Wp * P.C + cg * 8;
   const uint32_t esz = sizeof(T), cb = (uint32_t)P.C * esz, cgoff = (uint32_t)cg * 8 * esz;
@@ -519,12 +552,12 @@ template <typename K> inline int stream_attr(K kernel) {
 }
 
 template <typename T, int CONS>
-int norm_fwd_stream_launch(const StreamP& S, const void* x, const void* res, void* y, const float* mean, const float* rstd,
-                           cudaStream_t st) {
+int norm_fwd_stream_launch(const StreamP& S, const void* x, const double* stats, const void* res, void* y, float* mean,
+                           float* rstd, float* rm, float* rv, cudaStream_t st) {
   static bool attr = false;
   if (!attr) { if (int rc = stream_attr(inorm_fwd_stream_kernel<T, CONS>)) return rc; attr = true; }
   inorm_fwd_stream_kernel<T, CONS><<<stream_grid(S), CONS + 32, stream_smem(S), st>>>(
-      reinterpret_cast<const T*>(x), mean, rstd, reinterpret_cast<const T*>(res), reinterpret_cast<T*>(y), S);
+      reinterpret_cast<const T*>(x), stats, mean, rstd, rm, rv, reinterpret_cast<const T*>(res), reinterpret_cast<T*>(y), S);
   MRA_LAUNCH_CHECK();
   return 0;
 }
@@ -535,10 +568,7 @@ int norm_fwd_launch_v2(const mra_norm_desc& d, const void* x, const double* stat
   StreamP S;
   if (VEC != 8 || !stream_plan<T>(d, VEC, false, res != nullptr, S))
     return norm_fwd_launch<T, VEC>(d, x, stats, res, y, mean, rstd, rm, rv, st);
-  NormP P0 = make_norm_params(d, VEC);
-  inorm_finalize_kernel<<<(d.c + 127) / 128, 128, 0, st>>>(stats, mean, rstd, rm, rv, P0);
-  MRA_LAUNCH_CHECK();
-  return norm_fwd_stream_launch<T, kConsumers>(S, x, res, y, mean, rstd, st);
+  return norm_fwd_stream_launch<T, kConsumers>(S, x, stats, res, y, mean, rstd, rm, rv, st);
 }
 
 template <typename T, int CONS, int U>

@@ -58,17 +58,37 @@ class ConvFn(torch.autograd.Function):
         has_bias = mod.bias is not None
         ws2 = None
         if ctx.needs_input_grad[1]:
+            want_b = has_bias and ctx.bias_grad
+            # Fused gradient accumulation (single-process training).  A weight used by several passes of a step (each
+            # generator runs three times) would get one fresh gradient buffer + memset per use, summed by autograd
+            # with add_ kernels before AccumulateGrad runs once.  Instead this function owns ``weight.grad``: the
+            # first use of a step adopts the fresh buffer, every later use lets the wgrad kernel ADD into it
+            # (MRA_CONV_ACCUMULATE), and autograd is handed no gradient for the parameters at all.
+            fuse = bool(getattr(mod, "fuse_wgrad", False))
+            acc = {}
+            if fuse:
+                wg = mod.weight.grad
+                if (wg is not None and wg.dtype == torch.float32 and wg.stride() == mod.weight.stride()
+                        and (not want_b or mod.bias.grad is not None)):
+                    acc = dict(acc_dw=mod._packed_view(wg), acc_db=mod.bias.grad if want_b else None)
+                elif wg is not None:
+                    fuse = False                         # foreign gradient layout: leave this one to autograd
             if ctx.ws is not None:                       # lowerings 1 / 3: the forward pass left the expanded x in ctx.ws
-                dwp, dbv = I.conv_wgrad(x, gy, g, want_bias=has_bias and ctx.bias_grad, ws=ctx.ws, reuse=True)
+                dwp, dbv = I.conv_wgrad(x, gy, g, want_bias=want_b, ws=ctx.ws, reuse=True, **acc)
                 ctx.ws = None
             elif ctx.low == 2 and ctx.needs_input_grad[0]:   # head: wgrad expands dy, dgrad reuses it
                 _, ws2 = I.conv_shared_workspace(g, x.shape[0], ctx.in_dims, x.dtype, x.device)
-                dwp, dbv = I.conv_wgrad(x, gy, g, want_bias=has_bias and ctx.bias_grad, ws=ws2)
+                dwp, dbv = I.conv_wgrad(x, gy, g, want_bias=want_b, ws=ws2, **acc)
             else:
-                dwp, dbv = I.conv_wgrad(x, gy, g, want_bias=has_bias and ctx.bias_grad)
-            dw = weight_grad_view(dwp, g.k, g.transposed)
-            if has_bias and ctx.needs_input_grad[2]:
-                db = dbv if dbv is not None else torch.zeros_like(mod.bias)
+                dwp, dbv = I.conv_wgrad(x, gy, g, want_bias=want_b, **acc)
+            if not fuse:
+                dw = weight_grad_view(dwp, g.k, g.transposed)
+                if has_bias and ctx.needs_input_grad[2]:
+                    db = dbv if dbv is not None else torch.zeros_like(mod.bias)
+            elif not acc:                                # first use of the step: adopt the fresh buffers
+                mod.weight.grad = weight_grad_view(dwp, g.k, g.transposed)
+                if has_bias and mod.bias.requires_grad and mod.bias.grad is None:
+                    mod.bias.grad = dbv if dbv is not None else torch.zeros_like(mod.bias)
         if ctx.needs_input_grad[0]:
             if ws2 is not None:
                 dx = I.conv_dgrad(gy, mod.packed_weight_t(gy.dtype), g, ctx.in_dims, ws=ws2, reuse=True)

@@ -49,6 +49,16 @@ class _WeightsEpoch:
     value = 0          # total optimiser steps (diagnostics only)
 
 
+def set_fused_wgrad(net, flag=True):
+    """Let the wgrad kernels of ``net`` accumulate straight into ``weight.grad`` when a weight is used several times
+    per step (functional.ConvFn.backward).  Off under data parallelism: the gradient-bucket hooks need autograd's
+    AccumulateGrad to fire for every parameter."""
+    for m in net.modules():
+        if isinstance(m, _ConvNd):
+            m.fuse_wgrad = bool(flag)
+    return net
+
+
 ###############################################################################
 # Layers (parameter containers + plan tokens; arithmetic lives in the kernels)
 ###############################################################################
@@ -83,6 +93,8 @@ class _ConvNd(nn.Module):
                 init.uniform_(self.bias, -bound, bound)
 
     # -- packed views / compute-dtype copies -------------------------------------------------
+    fuse_wgrad = False       # set per instance by set_fused_wgrad(): wgrad kernels add into weight.grad (functional.ConvFn)
+
     def _packed_view(self, t):
         perm = (2, 3, 4, 1, 0) if self.transposed else (2, 3, 4, 0, 1)
         p = t.permute(*perm)

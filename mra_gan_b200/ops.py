@@ -132,12 +132,22 @@ class CudaImpl:
                    "mra_conv3d_dgrad")
         return dx
 
-    def conv_wgrad(self, x, dy, g, want_bias=False, ws=None, reuse=False):
+    def conv_wgrad(self, x, dy, g, want_bias=False, ws=None, reuse=False, acc_dw=None, acc_db=None):
+        """dw [taps][Cout][Cin] fp32 (+ db).  With ``acc_dw`` (and ``acc_db`` when a bias gradient is wanted) the
+        kernels ADD into those buffers (MRA_CONV_ACCUMULATE) instead of writing fresh ones."""
         self._need(x, dy)
         n, in_dims, out_dims = x.shape[0], tuple(x.shape[1:4]), tuple(dy.shape[1:4])
-        dw = torch.empty((g.taps, g.cout, g.cin), dtype=torch.float32, device=x.device)
-        db = torch.empty((g.cout,), dtype=torch.float32, device=x.device) if want_bias else None
-        d = self._conv_desc(g, n, in_dims, out_dims, _dt(x), flags=_lib.CONV_WS_REUSE if reuse else 0)
+        flags = _lib.CONV_WS_REUSE if reuse else 0
+        if acc_dw is not None:
+            if want_bias and acc_db is None:
+                raise ValueError("conv_wgrad: accumulate mode needs a bias-gradient buffer too")
+            self._need(acc_dw)
+            dw, db = acc_dw, (acc_db if want_bias else None)
+            flags |= _lib.CONV_ACCUMULATE
+        else:
+            dw = torch.empty((g.taps, g.cout, g.cin), dtype=torch.float32, device=x.device)
+            db = torch.empty((g.cout,), dtype=torch.float32, device=x.device) if want_bias else None
+        d = self._conv_desc(g, n, in_dims, out_dims, _dt(x), flags=flags)
         ws, wsb = self._workspace(d, 2, x.device, ws)
         _lib.check(self.L.mra_conv3d_wgrad(C.byref(d), _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), _ptr(ws), wsb,
                                            self._stream()), "mra_conv3d_wgrad")

@@ -148,6 +148,9 @@ def attach(model, bucket_mb=32.0):
             net = getattr(model, "net" + name)
             for t in list(net.parameters()) + list(net.buffers()):
                 dist.broadcast(_dense_view(t.data), src=0)
+    from . import networks3D
+    for name in model.model_names:
+        networks3D.set_fused_wgrad(getattr(model, "net" + name), False)     # every gradient must pass AccumulateGrad
     model.grad_sync = GradSync({"G": [model.netG_A, model.netG_B], "D": [model.netD_A, model.netD_B]},
                                bucket_mb=bucket_mb)
     return model.grad_sync

@@ -109,13 +109,18 @@ class RefImpl:
             (dx,) = torch.autograd.grad(y, x, to_ncdhw(self._c(dy)))
         return to_ndhwc(dx).to(dy.dtype)
 
-    def conv_wgrad(self, x, dy, g, want_bias=False):
+    def conv_wgrad(self, x, dy, g, want_bias=False, acc_dw=None, acc_db=None):
         with torch.enable_grad():
             wp = torch.zeros((g.taps, g.cout, g.cin), dtype=self.cd, requires_grad=True)
             y = self._conv(to_ncdhw(self._c(x)).detach(), wp, None, g)
             (dw,) = torch.autograd.grad(y, wp, to_ncdhw(self._c(dy)))
         db = self._c(dy).sum((0, 1, 2, 3)).float() if want_bias else None
-        return dw.float(), db
+        if acc_dw is not None:                       # MRA_CONV_ACCUMULATE: add into the caller's buffers
+            acc_dw += dw.float()
+            if want_bias:
+                acc_db += db
+            return acc_dw, (acc_db if want_bias else None)
+        return dw.float().contiguous(), db
 
     def conv_uses_tensor_cores(self, g, n, in_dims, dtype, which):
         return False

@@ -86,6 +86,11 @@ def _check_conv(g, dims, n, dtype, expect_tc):
     assert I.tc_error() == 0
     assert rel_l2(dw.cpu(), dw_ref) < tol, "wgrad"
     assert rel_l2(db.cpu(), db_ref) < tol, "dbias"
+    # MRA_CONV_ACCUMULATE: the kernels add into the caller's buffers (fused gradient accumulation)
+    acc_w, acc_b = dw.clone(), db.clone()
+    dw2, db2 = I.conv_wgrad(xd, dyd, g, want_bias=True, acc_dw=acc_w, acc_db=acc_b)
+    assert dw2.data_ptr() == acc_w.data_ptr() and db2.data_ptr() == acc_b.data_ptr()
+    assert rel_l2(acc_w.cpu(), 2 * dw_ref) < tol and rel_l2(acc_b.cpu(), 2 * db_ref) < tol, "wgrad accumulate"
 
 
 @pytest.mark.parametrize("case", CONVS, ids=gid)
