@@ -214,20 +214,29 @@ __device__ __noinline__ float act_slow(float v, int act) {
 //     per flush instead of once per tile (it is ~2/3 of the epilogue's instructions, and with N = 64 the epilogue,
 //     not the tensor pipe, bounds the small-K launches);
 //   * otherwise per tile: warp transpose-reduce, fp64 per-lane partials st_s / st_q.
+//
+// Dual-plane tiles (gather_col_kernel with 64 output channels): the accumulator is 128 columns wide, columns
+// [0, 64) belong to output plane p and [64, 128) to plane p + 1 (`dual_stride` elements further, validity
+// `valid_hi`); TMEM chunk c then maps to channel chunk c & 1 of plane c >> 1.
 template <typename Release>
 __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, uint32_t t_addr, int c_begin, int c_step, int nchunks, bool valid,
                                               long long obase, int n0, int lane, double* st_s, double* st_q, bool defer,
-                                              float (&d1)[32], float (&d2)[32], Release release) {
+                                              float (&d1)[32], float (&d2)[32], Release release, bool dual = false,
+                                              long long dual_stride = 0, bool valid_hi = false) {
   const bool lin_act = E.act == MRA_ACT_RELU || E.act == MRA_ACT_LRELU;
   const float nslope = E.act == MRA_ACT_RELU ? 0.f : E.slope;
   if (c_begin >= nchunks) { release(); return; }
+  const bool valid_lo = valid;
 #pragma unroll 1
-  for (int c = c_begin; c < nchunks; c += c_step) {
+  for (int ct = c_begin; ct < nchunks; ct += c_step) {
+    const int c = dual ? (ct & 1) : ct;                 // channel chunk
     const int c0 = c * 32;
+    if (dual) valid = (ct >> 1) ? valid_hi : valid_lo;
+    const long long obase_c = obase + ((dual && (ct >> 1)) ? dual_stride : 0);
     uint32_t r[32];
-    tmem_ld32(t_addr + (uint32_t)c0, r);
+    tmem_ld32(t_addr + (uint32_t)(ct * 32), r);
     tmem_wait_ld();
-    if (c + c_step >= nchunks) release();
+    if (ct + c_step >= nchunks) release();
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
@@ -270,13 +279,13 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, uint32_t t_addr,
     }
     if (valid) {
       if (E.out_bf16) {
-        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(E.out) + obase + c0);
+        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(E.out) + obase_c + c0);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           o[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
                             pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
       } else {
-        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(E.out) + obase + c0);
+        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(E.out) + obase_c + c0);
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
       }

@@ -7,6 +7,12 @@
 //   * a ring of input planes (one 16 x 8 position tile of one d-plane, 64 channels = 16 KB): stepping to the next
 //     output plane loads ONE new plane instead of kd, and costs ONE barrier wait for 4 * kd back-to-back MMAs.
 // Columns are cut into segments along d so that the persistent CTAs get a balanced number of work units.
+//
+// Dual-plane mode (64 output channels): tcgen05.mma runs N = 64 at 54.5 clk per 128x64x16 instruction where 32 would
+// be ideal (tools/mma_probe.cu: the A-operand read bounds it), N = 128 at the ideal 64.  So a tile covers TWO output
+// planes p, p + 1 side by side in a 128-column accumulator: input plane p + dmin + t (t = 0..kd) meets the weight rows
+// [W[t] ; W[t-1]] -- with the resident slabs stored in REVERSE tap order these are simply two consecutive slabs, one
+// N = 128 descriptor.  Only the first and the last plane of a pair (one tap each) issue N = 64 MMAs.
 // Warp roles as in conv_tc.cuh: 0..7 = epilogue, 8 = TMA producer, 9 = TMEM allocator + MMA issuer.
 #pragma once
 #include "conv_tc.cuh"
@@ -31,7 +37,8 @@ struct ColP {
   float slope;
   double* stats;
   int* err;
-  int nbuf;                         // accumulator buffers in TMEM (512 / n_tile, at most 8)
+  int nbuf;                         // accumulator buffers in TMEM (512 / accumulator width, at most 8)
+  int dual;                         // 1: dual-plane tiles (accumulator 2 * n_tile = 128 columns)
   uint32_t tmem_cols;
   int16_t twi[kMaxTaps];            // weight slab of tap td
   int debug;
@@ -87,14 +94,15 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_expect_tx(w_bar, w_bytes);
       for (int td = 0; td < P.kd; ++td)
         for (int kc = 0; kc < P.kchunks; ++kc)
-          tma_load_2d(wres + (size_t)(td * P.kchunks + kc) * slab_bytes, &tmB, w_bar, kc * 64, (int)P.twi[td] * P.Cn);
+          tma_load_2d(wres + (size_t)(P.dual ? kc * P.kd + (P.kd - 1 - td) : td * P.kchunks + kc) * slab_bytes, &tmB, w_bar,
+                      kc * 64, (int)P.twi[td] * P.Cn);
       int s = 0;
       uint32_t ph = 0;
       bool ok = true;
       for (int u = blockIdx.x; u < P.total_units && ok; u += gridDim.x) {
         int n, h0, w0, d0, len;
         unit_coords(u, n, h0, w0, d0, len);
-        const int nplanes = len + P.kd - 1;
+        const int nplanes = (P.dual ? 2 * ((len + 1) / 2) : len) + P.kd - 1;
         for (int p = 0; p < nplanes; ++p) {
           if (!mbar_wait(&p_empty[s], ph ^ 1u, P.err, 31)) { ok = false; break; }
           mbar_expect_tx(&p_full[s], slot_bytes);
@@ -126,6 +134,67 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         int n, h0, w0, d0, len;
         unit_coords(u, n, h0, w0, d0, len);
         int have = 0;                // planes of this unit already waited for
+        if (P.dual) {
+          const uint32_t idesc64 = make_idesc(64, 0, 0), idesc128 = make_idesc(128, 0, 0);
+          const int npairs = (len + 1) / 2;
+          for (int jp = 0; jp < npairs && ok; ++jp, ++jt) {
+            const long long t0 = prof ? clock64() : 0;
+            if (!mbar_wait(&acc_empty[buf], aph ^ 1u, P.err, 34)) { ok = false; break; }
+            const long long t1 = prof ? clock64() : 0;
+            while (have < 2 * jp + kd + 1) {    // a pair reads kd + 1 planes; two of them are new after the first pair
+              if (!mbar_wait(&p_full[s_new], ph_new, P.err, 35)) { ok = false; break; }
+              if (++s_new == NPR) { s_new = 0; ph_new ^= 1u; }
+              ++have;
+            }
+            if (prof) { t_wacc += t1 - t0; t_wp += clock64() - t1; }
+            if (!ok) break;
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
+            int s_last = s_old + kd;
+            if (s_last >= NPR) s_last -= NPR;
+            // the two end planes first (one tap each, N = 64, they initialise their half of the accumulator) ...
+            for (int kc = 0; kc < kchunks; ++kc) {
+              const uint32_t a0 = ring_u + (uint32_t)s_old * slot_u + (uint32_t)kc * chunk_u;
+              const uint32_t a1 = ring_u + (uint32_t)s_last * slot_u + (uint32_t)kc * chunk_u;
+              const uint32_t b0 = wres_u + (uint32_t)(kc * kd + (kd - 1)) * slab_u;      // W[0]      -> plane p, columns [0, 64)
+              const uint32_t b1 = wres_u + (uint32_t)(kc * kd) * slab_u;                 // W[kd - 1] -> plane p + 1, columns [64, 128)
+              const uint64_t ad0 = desc0 | (uint64_t)(a0 & 0x3FFFu), bd0 = desc0 | (uint64_t)(b0 & 0x3FFFu);
+              const uint64_t ad1 = desc0 | (uint64_t)(a1 & 0x3FFFu), bd1 = desc0 | (uint64_t)(b1 & 0x3FFFu);
+              umma_f16(d_tmem, ad0, bd0, idesc64, (uint32_t)(kc != 0));
+              umma_f16(d_tmem, ad0 + 2, bd0 + 2, idesc64, 1u);
+              umma_f16(d_tmem, ad0 + 4, bd0 + 4, idesc64, 1u);
+              umma_f16(d_tmem, ad0 + 6, bd0 + 6, idesc64, 1u);
+              umma_f16(d_tmem + 64, ad1, bd1, idesc64, (uint32_t)(kc != 0));
+              umma_f16(d_tmem + 64, ad1 + 2, bd1 + 2, idesc64, 1u);
+              umma_f16(d_tmem + 64, ad1 + 4, bd1 + 4, idesc64, 1u);
+              umma_f16(d_tmem + 64, ad1 + 6, bd1 + 6, idesc64, 1u);
+            }
+            // ... then the kd - 1 inner planes: rows [W[t] ; W[t - 1]] = two consecutive reversed slabs, N = 128
+            int s = s_old;
+            for (int t = 1; t < kd; ++t) {
+              if (++s == NPR) s = 0;
+              for (int kc = 0; kc < kchunks; ++kc) {
+                const uint32_t a_u = ring_u + (uint32_t)s * slot_u + (uint32_t)kc * chunk_u;
+                const uint32_t b_u = wres_u + (uint32_t)(kc * kd + (kd - 1 - t)) * slab_u;
+                const uint64_t ad = desc0 | (uint64_t)(a_u & 0x3FFFu);
+                const uint64_t bd = desc0 | (uint64_t)(b_u & 0x3FFFu);
+                umma_f16(d_tmem, ad, bd, idesc128, 1u);
+                umma_f16(d_tmem, ad + 2, bd + 2, idesc128, 1u);
+                umma_f16(d_tmem, ad + 4, bd + 4, idesc128, 1u);
+                umma_f16(d_tmem, ad + 6, bd + 6, idesc128, 1u);
+              }
+            }
+            umma_commit(&acc_full[buf]);
+            if (++buf == P.nbuf) { buf = 0; aph ^= 1u; }
+            // the two oldest planes are dead after this pair; after the unit's last pair so are the other kd - 1
+            const int nrel = (jp == npairs - 1) ? kd + 1 : 2;
+            for (int r = 0; r < nrel; ++r) {
+              umma_commit(&p_empty[s_old]);
+              if (++s_old == NPR) s_old = 0;
+            }
+          }
+          continue;
+        }
         for (int j = 0; j < len && ok; ++j, ++jt) {
           const long long t0 = prof ? clock64() : 0;
           if (!mbar_wait(&acc_empty[buf], aph ^ 1u, P.err, 34)) { ok = false; break; }
@@ -174,7 +243,8 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const EpiWarp W(warp);
     const int q = W.q;
     const int row = q * 32 + lane;
-    const int nchunks = P.n_tile / 32;
+    const int nchunks = P.n_tile / 32;                    // CHANNEL chunks (dual tiles hold each of them twice)
+    const int acc_cols = P.dual ? 2 * P.n_tile : P.n_tile;
     const bool defer = P.stats != nullptr && nchunks <= 2;
     double st_s[8], st_q[8];
 #pragma unroll
@@ -196,19 +266,21 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         epilogue_flush_stats(P.stats, st_n, P.Cn, 0, W.q, W.c_begin, 2, nchunks, lane, st_s, st_q, defer, d1, d2, epi_red);
         st_n = n;
       }
-      for (int j = 0; j < len && ok; ++j) {
-        const long long obase = (long long)n * P.osn + (long long)((d0 + j) * P.ostep + P.od0) * P.osd +
+      const int ntiles = P.dual ? (len + 1) / 2 : len;
+      for (int j = 0; j < ntiles && ok; ++j) {
+        const int pl = P.dual ? 2 * j : j;                 // (first) output plane of the tile, relative to d0
+        const long long obase = (long long)n * P.osn + (long long)((d0 + pl) * P.ostep + P.od0) * P.osd +
                                 (long long)(lh * P.ostep + P.oh0) * P.osh + (long long)(lw * P.ostep + P.ow0) * P.osw;
         ok = mbar_wait(&acc_full[buf], aph, P.err, 33);
         if (!ok) break;
         tc_fence_after();
-        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * P.n_tile);
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
         uint64_t* rel_bar = &acc_empty[buf];
-        epilogue_tile(E, t_addr, W.c_begin, 2, nchunks, valid, obase, 0, lane, st_s, st_q, defer, d1, d2, [&]() {
+        epilogue_tile(E, t_addr, W.c_begin, 2, acc_cols / 32, valid, obase, 0, lane, st_s, st_q, defer, d1, d2, [&]() {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(rel_bar);
-        });
+        }, P.dual != 0, (long long)P.ostep * P.osd, valid && pl + 1 < len);
         if (++buf == P.nbuf) { buf = 0; aph ^= 1u; }
       }
     }
@@ -249,6 +321,8 @@ inline bool col_setup(const GatherLaunch& L, int n, int ck, int cn, ColP& P) {
   int npr = (int)((budget - w_bytes) / slot);
   if (npr > kd + 6) npr = kd + 6;
   P.NPR = npr;
+  // dual-plane tiles: two output planes per 128-column accumulator (needs kd + 1 resident planes + 2 in flight)
+  P.dual = (n_tile == 64 && P.Dl >= 2 && npr >= kd + 3 && getenv("MRA_COL_NODUAL") == nullptr) ? 1 : 0;
   // segments: aim at >= 6 units per SM, but keep them long enough to amortise the kd - 1 warm-up planes
   const long long cols = (long long)n * P.tiles_hw;
   long long nseg = ((long long)num_sms() * 6 + cols - 1) / cols;
@@ -256,6 +330,7 @@ inline bool col_setup(const GatherLaunch& L, int n, int ck, int cn, ColP& P) {
   if (nseg > max_seg) nseg = max_seg;
   if (nseg < 1) nseg = 1;
   P.seg_len = (int)((P.Dl + nseg - 1) / nseg);
+  if (P.dual && (P.seg_len & 1)) ++P.seg_len;           // whole pairs per segment
   P.nseg = (P.Dl + P.seg_len - 1) / P.seg_len;
   const long long units = cols * P.nseg;
   if (units >= (1ll << 31)) return false;
@@ -280,8 +355,9 @@ inline int run_gather_col(const GatherPlan& plan, const GatherLaunch& L, ColP& P
   P.stats = R.stats; P.err = tc_err_flag();
   { const char* e = getenv("MRA_GATHER_DEBUG"); P.debug = e ? atoi(e) : 0; }
   P.dbg = tc_dbg_counters();
-  P.nbuf = 512 / P.n_tile > 8 ? 8 : 512 / P.n_tile;
-  P.tmem_cols = pow2_cols(P.nbuf * P.n_tile);
+  const int acc_cols = P.dual ? 2 * P.n_tile : P.n_tile;
+  P.nbuf = 512 / acc_cols > 8 ? 8 : 512 / acc_cols;
+  P.tmem_cols = pow2_cols(P.nbuf * acc_cols);
   CUtensorMap tmA;
   if (int rc = make_act_map(&tmA, R.a, plan.n, plan.adims[0], plan.adims[1], plan.adims[2], plan.ck, 8, 16, 1, 1)) return rc;
   const size_t smem = (size_t)P.kd * P.kchunks * P.n_tile * 128 + (size_t)P.NPR * kABytes * P.kchunks + 1024 + 512;

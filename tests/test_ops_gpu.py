@@ -37,6 +37,9 @@ TC_CONVS = [
     (ConvGeom(512, 1, 4, 1, 1), (7, 7, 7), 2),             # D.5: zero-padded head lowering
     (ConvGeom(128, 1, 4, 2, 1, True, 0), (6, 6, 6), 2),    # UNet outermost up-conv: mirror of the im2col lowering
     (ConvGeom(64, 1, 3, 2, 1, True, 1), (5, 6, 7), 1),     # ConvTranspose3d(C -> 1) with output padding
+    (ConvGeom(128, 64, 3, 2, 1, True, 1), (12, 12, 12), 2),  # G.u2: 8 merged parity phases, several work items per CTA,
+                                                             # deferred statistics across a sample boundary
+    (ConvGeom(64, 128, 3, 2, 1), (15, 16, 17), 1),         # odd dims: the dgrad phases differ in extent -> unmerged launches
 ]
 
 
