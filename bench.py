@@ -234,7 +234,10 @@ def run_gpu(args):
     I = ops.impl()
     if world > 1:
         parallel.attach(model)
-    elif not args.no_graphs:
+    # Data-parallel graph replay (NCCL all-reduces captured) measured +2 % at N = 2 but the process group did not shut
+    # down cleanly afterwards, so it stays opt-in (MRA_DP_GRAPHS=1) until that is understood.
+    use_graphs = not args.no_graphs and (world == 1 or os.environ.get("MRA_DP_GRAPHS", "0") == "1")
+    if use_graphs:
         model.enable_cuda_graphs(warmup_steps=2)        # the step is replayed as two CUDA graphs after 2 eager steps
 
     g = torch.Generator().manual_seed(1234 + rank)
@@ -291,6 +294,7 @@ def run_gpu(args):
     vox = global_batch * PATCH ** 3 / (ms_step * 1e-3)
     vox_e2e = global_batch * PATCH ** 3 / (ms_e2e * 1e-3)
     if rank != 0:
+        model._graphs = None
         dist.barrier()
         dist.destroy_process_group()
         return 0
@@ -308,7 +312,7 @@ def run_gpu(args):
                                "optimize_parameters() on synthetic 128^3 patches",
                    "patch": PATCH, "per_gpu_batch": per_gpu_batch, "global_batch": global_batch,
                    "parallelism": "dp%d" % world, "l2": "per-step working set (tens of GB) >> 126 MB L2",
-                   "launch": "two CUDA graphs per step" if (world == 1 and not args.no_graphs) else "eager",
+                   "launch": "two CUDA graphs per step" if use_graphs else "eager",
                    "model_tflop_per_sample_step": FLOP_PER_SAMPLE_STEP / 1e12},
         "e2e": {"value": vox_e2e, "unit": "voxels/s", "h2d_bytes_per_step": int(host_A.numel() * 4 * 2),
                 "d2h_bytes_per_step": 8 * 4, "ms_per_step": ms_e2e},
@@ -328,8 +332,9 @@ def run_gpu(args):
         line["cpu_baseline"] = {"value": 64 ** 3 / sec, "unit": "voxels/s", "cores": threads, "kind": "port",
                                 "sample": "BASELINE config 1: 64^3 patch, batch 1, fp32, first optimize_parameters() "
                                           "(%.1f s) of the oracle port on the host cores" % sec}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
+        model._graphs = None                       # graphs holding NCCL nodes must go before the communicator
         dist.barrier()
         dist.destroy_process_group()
     return 0

@@ -145,23 +145,38 @@ class CycleGANModel(BaseModel):
         """Replay the training step as two CUDA graphs (generator phase, discriminator phase) instead of ~2400
         eager launches.  The image pools stay eager between the two (their control flow depends on the host RNG,
         cycle_gan_model.py:8-35).  The next ``warmup_steps`` calls of optimize_parameters() still run eagerly (they
-        warm every kernel / allocation up), the one after is captured.  Single-process training only."""
-        if self.grad_sync is not None:
-            raise RuntimeError("CUDA-graph replay is not combined with data-parallel gradient sync yet")
+        warm every kernel / allocation up), the one after is captured.
+        Under data parallelism (parallel.attach) the bucketed NCCL all-reduces are issued from the gradient hooks
+        while the backward pass is being captured, so they become nodes of the same graphs (the capture runs in
+        thread-local error mode: NCCL's watchdog thread must not trip it)."""
         self._graphs = {"warm": int(warmup_steps), "shape": None}
 
     def _phase_G(self):
+        sync = self.grad_sync
         self.forward()
         self.set_requires_grad([self.netD_A, self.netD_B], False)
-        self.optimizer_G.zero_grad(set_to_none=True)
+        if sync:
+            sync.zero("G")                         # gradients are views into the flat buckets: one fill per bucket
+            sync.begin("G")
+        else:
+            self.optimizer_G.zero_grad(set_to_none=True)
         self.backward_G()
+        if sync:
+            sync.finish("G")
         self.optimizer_G.step()
 
     def _phase_D(self, pooled_B, pooled_A):
+        sync = self.grad_sync
         self.set_requires_grad([self.netD_A, self.netD_B], True)
-        self.optimizer_D.zero_grad(set_to_none=True)
+        if sync:
+            sync.zero("D")
+            sync.begin("D")
+        else:
+            self.optimizer_D.zero_grad(set_to_none=True)
         self.loss_D_A = self.backward_D_basic(self.netD_A, self.real_B, pooled_B)
         self.loss_D_B = self.backward_D_basic(self.netD_B, self.real_A, pooled_A)
+        if sync:
+            sync.finish("D")
         self.optimizer_D.step()
 
     def _optimize_graphed(self):
@@ -183,16 +198,18 @@ class CycleGANModel(BaseModel):
             self.loss_G = self.loss_cor_coe_GA = self.loss_cor_coe_GB = None
             for n in ("fake_A", "fake_B", "rec_A", "rec_B", "idt_A", "idt_B"):
                 setattr(self, n, None)
-            self.optimizer_G.zero_grad(set_to_none=True)
-            self.optimizer_D.zero_grad(set_to_none=True)
+            if self.grad_sync is None:
+                self.optimizer_G.zero_grad(set_to_none=True)
+                self.optimizer_D.zero_grad(set_to_none=True)
             gc.collect()
             torch.cuda.synchronize()
             # capture only records: each graph is replayed right after its capture to execute this step (the host
             # side of optimizer.step() -- step counters, pinned hyper-parameters -- already ran during capture)
             from .. import ops
             n0 = ops.impl().launch_count() if hasattr(ops.impl(), "launch_count") else 0
+            mode = dict(capture_error_mode="thread_local") if self.grad_sync is not None else {}
             G["gG"] = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(G["gG"]):
+            with torch.cuda.graph(G["gG"], **mode):
                 self._phase_G()
             G["gG"].replay()
             G["pB"] = torch.empty_like(self.fake_B)
@@ -200,7 +217,7 @@ class CycleGANModel(BaseModel):
             G["pB"].copy_(self.fake_B_pool.query(self.fake_B))
             G["pA"].copy_(self.fake_A_pool.query(self.fake_A))
             G["gD"] = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(G["gD"], pool=G["gG"].pool()):
+            with torch.cuda.graph(G["gD"], pool=G["gG"].pool(), **mode):
                 self._phase_D(G["pB"], G["pA"])
             G["gD"].replay()
             G["launches"] = (ops.impl().launch_count() - n0) if hasattr(ops.impl(), "launch_count") else 0   # kernels per replayed step
@@ -217,7 +234,7 @@ class CycleGANModel(BaseModel):
         return True
 
     def optimize_parameters(self):
-        if self._graphs is not None and self.grad_sync is None and self._optimize_graphed():
+        if self._graphs is not None and self._optimize_graphed():
             return
         sync = self.grad_sync
         self.forward()

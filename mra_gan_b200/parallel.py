@@ -107,6 +107,11 @@ class GradSync:
             bucket.work = dist.all_reduce(bucket.flat, op=op, group=self.group, async_op=True)
             self.stats["allreduce_calls"] += 1
 
+    def zero(self, phase):
+        """zero_grad for a phase: one fill per flat bucket (every ``p.grad`` is a view into it)."""
+        for b in self.phases[phase]:
+            b.flat.zero_()
+
     def begin(self, phase):
         """Call after zero_grad(set_to_none=False) and before the phase's backward pass(es)."""
         self.active = phase
