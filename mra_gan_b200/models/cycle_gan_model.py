@@ -239,17 +239,21 @@ class CycleGANModel(BaseModel):
         sync = self.grad_sync
         self.forward()
         self.set_requires_grad([self.netD_A, self.netD_B], False)
-        self.optimizer_G.zero_grad(set_to_none=sync is None)
         if sync:
+            sync.zero("G")
             sync.begin("G")
+        else:
+            self.optimizer_G.zero_grad(set_to_none=True)
         self.backward_G()
         if sync:
             sync.finish("G")
         self.optimizer_G.step()
         self.set_requires_grad([self.netD_A, self.netD_B], True)
-        self.optimizer_D.zero_grad(set_to_none=sync is None)
         if sync:
+            sync.zero("D")
             sync.begin("D")
+        else:
+            self.optimizer_D.zero_grad(set_to_none=True)
         self.backward_D_A()
         self.backward_D_B()
         if sync:
