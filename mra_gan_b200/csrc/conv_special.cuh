@@ -164,61 +164,63 @@ __global__ void wunexp_kernel(const float* __restrict__ dwe, float* __restrict__
 // PatchGAN layer 0 (networks3D.py:392): Conv3d(1 -> Co, k4, s2, p1).  With Cin = 1 and k^3 <= 64 the whole
 // receptive field fits one 64-wide channel axis: E[n,o,(kd,kh,kw)] = x[n, o*s - p + k] (im2col), after which
 // the layer is a 1x1x1 convolution (one GEMM tap) on the tensor cores; dgrad is the GEMM followed by col2im.
+// (Index arithmetic is 32-bit with one tap decode per thread: the first version spent ~250 instructions per 16-byte
+// store on 64-bit divisions and ran at 0.5 TB/s; positions are checked to fit 31 bits on the host.)
 __global__ void __launch_bounds__(256) im2col1_kernel(const bf16* __restrict__ x, bf16* __restrict__ E, int N, int Di, int Hi, int Wi,
                                                        int Do, int Ho, int Wo, int k, int s, int p) {
-  const long long total = (long long)N * Do * Ho * Wo * 8;       // one thread = 8 consecutive channels
+  const unsigned total = (unsigned)N * Do * Ho * Wo * 8u;         // one thread = 8 consecutive channels
   const int taps = k * k * k;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i & 7) * 8;
-    long long q = i >> 3;
-    const int ow = (int)(q % Wo); q /= Wo;
-    const int oh = (int)(q % Ho); q /= Ho;
-    const int od = (int)(q % Do);
-    const int n = (int)(q / Do);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c0 = (int)(i & 7u) * 8;
+    unsigned q = i >> 3;
+    const int ow = (int)(q % (unsigned)Wo); q /= (unsigned)Wo;
+    const int oh = (int)(q % (unsigned)Ho); q /= (unsigned)Ho;
+    const int od = (int)(q % (unsigned)Do);
+    const int n = (int)(q / (unsigned)Do);
+    int kw = c0 % k, kh = (c0 / k) % k, kd = c0 / (k * k);        // taps c0 .. c0 + 7 walk (kd, kh, kw) incrementally
+    const bf16* xn = x + (long long)n * Di * Hi * Wi;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int t = c0 + j;
       v[j] = 0.f;
-      if (t < taps) {
-        const int kw = t % k, kh = (t / k) % k, kd = t / (k * k);
+      if (c0 + j < taps) {
         const int d = od * s - p + kd, h = oh * s - p + kh, w = ow * s - p + kw;
-        if (d >= 0 && d < Di && h >= 0 && h < Hi && w >= 0 && w < Wi)
-          v[j] = __bfloat162float(x[(((long long)n * Di + d) * Hi + h) * Wi + w]);
+        if ((unsigned)d < (unsigned)Di && (unsigned)h < (unsigned)Hi && (unsigned)w < (unsigned)Wi)
+          v[j] = __bfloat162float(xn[(d * Hi + h) * Wi + w]);
       }
+      if (++kw == k) { kw = 0; if (++kh == k) { kh = 0; ++kd; } }
     }
-    Vec8<bf16>::store(E + (i >> 3) * 64 + c0, v);
+    Vec8<bf16>::store(E + (long long)(i >> 3) * 64 + c0, v);
   }
 }
-// dx[n,i] = sum over (o, k) with o*s - p + k == i of dE[n,o,(kd,kh,kw)]
+// dx[n,i] = sum over (o, k) with o*s - p + k == i of dE[n,o,(kd,kh,kw)].  Per dim only ceil(k/s) output coordinates can
+// reach an input voxel: o = (i + p) / s - j, tap = (i + p) - o*s.
 __global__ void __launch_bounds__(256) col2im1_kernel(const bf16* __restrict__ dE, bf16* __restrict__ dx, int N, int Di, int Hi, int Wi,
                                                        int Do, int Ho, int Wo, int k, int s, int p,
                                                        const float* __restrict__ bias, int act, float slope) {
   const float bv = bias ? bias[0] : 0.f;
-  const long long total = (long long)N * Di * Hi * Wi;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long q = i;
-    const int w = (int)(q % Wi); q /= Wi;
-    const int h = (int)(q % Hi); q /= Hi;
-    const int d = (int)(q % Di);
-    const int n = (int)(q / Di);
+  const unsigned total = (unsigned)N * Di * Hi * Wi;
+  const int R = (k + s - 1) / s;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    unsigned q = i;
+    const int w = (int)(q % (unsigned)Wi); q /= (unsigned)Wi;
+    const int h = (int)(q % (unsigned)Hi); q /= (unsigned)Hi;
+    const int d = (int)(q % (unsigned)Di);
+    const int n = (int)(q / (unsigned)Di);
+    const bf16* En = dE + (long long)n * Do * Ho * Wo * 64;
+    const int od0 = (d + p) / s, oh0 = (h + p) / s, ow0 = (w + p) / s;
     float acc = 0.f;
-    for (int kd = 0; kd < k; ++kd) {
-      const int a = d + p - kd;
-      if (a < 0 || a % s) continue;
-      const int od = a / s;
-      if (od >= Do) continue;
-      for (int kh = 0; kh < k; ++kh) {
-        const int b = h + p - kh;
-        if (b < 0 || b % s) continue;
-        const int oh = b / s;
-        if (oh >= Ho) continue;
-        for (int kw = 0; kw < k; ++kw) {
-          const int c = w + p - kw;
-          if (c < 0 || c % s) continue;
-          const int ow = c / s;
-          if (ow >= Wo) continue;
-          acc += __bfloat162float(dE[((((long long)n * Do + od) * Ho + oh) * Wo + ow) * 64 + (kd * k + kh) * k + kw]);
+    for (int jd = 0; jd < R; ++jd) {
+      const int od = od0 - jd, kd = d + p - od * s;
+      if (od < 0 || od >= Do || kd >= k) continue;
+      for (int jh = 0; jh < R; ++jh) {
+        const int oh = oh0 - jh, kh = h + p - oh * s;
+        if (oh < 0 || oh >= Ho || kh >= k) continue;
+        const bf16* Er = En + ((long long)(od * Ho + oh) * Wo) * 64 + (kd * k + kh) * k;
+        for (int jw = 0; jw < R; ++jw) {
+          const int ow = ow0 - jw, kw = w + p - ow * s;
+          if (ow < 0 || ow >= Wo || kw >= k) continue;
+          acc += __bfloat162float(Er[ow * 64 + kw]);
         }
       }
     }
@@ -287,6 +289,9 @@ inline bool head_eligible(const mra_conv_desc& d) {
 }
 
 inline bool im2col_eligible(const mra_conv_desc& d) {
+  // (the im2col / col2im helpers index with 32 bits)
+  if ((long long)d.n * d.dout * d.hout * d.wout * 8 >= (1ll << 32) || (long long)d.n * d.din * d.hin * d.win >= (1ll << 31))
+    return false;
   return d.dtype == MRA_BF16 && !(d.flags & MRA_CONV_FORCE_NAIVE) && !d.transposed && d.cin == 1 &&
          d.k * d.k * d.k <= 64 && tc::pick_n_tile(d.cout) > 0 && !(d.stride == 1 && d.pad == 0 && d.k >= 2);
 }
