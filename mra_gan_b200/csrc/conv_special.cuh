@@ -25,36 +25,70 @@ namespace mra {
 namespace special {
 
 // out[n,d,ho,wo,kh*8+kw] = src[n,d,ho+sgn*kh+off,wo+sgn*kw+off] (0 out of range / kh,kw >= k).
-// One block = one output line (n*d row r, ho): the <= 8 source lines it touches are staged in shared memory
-// (zero outside the volume), then one thread per (wo, kh) writes 8 channels = 16 B; a warp writes 512 contiguous bytes.
+// One block = a band of kExpandBand output lines of one (n, d) plane: the band + 7 source lines it touches are staged
+// in shared memory once (zero outside the volume; line l holds source columns j + base, base = off - (sgn < 0 ? 7 : 0)),
+// then one thread per (wo, kh) writes 8 channels = 16 B; a warp writes 512 contiguous bytes.  The 8 source values of an
+// item are consecutive in the staged line (ascending for sgn > 0, descending for sgn < 0): they are fetched as five
+// aligned 32-bit words and cut out with one funnel shift / byte permute per output word (the first version read them
+// as 8 scalar bf16 and was bound by instruction issue at 2.7 TB/s of stores).
+constexpr int kExpandBand = 16;
 __global__ void __launch_bounds__(256) expand_hw_kernel(const bf16* __restrict__ src, bf16* __restrict__ out, long long rows /*N*D*/,
-                                                         int Hs, int Ws, int Ho, int Wo, int k, int sgn, int off) {
-  extern __shared__ bf16 s_lines[];                 // [8][Wo + 8]  (line kh holds source columns wo + sgn*kw + off for all wo, kw)
-  const int pitch = Wo + 8;
-  const long long nlines = rows * Ho;
-  for (long long line = blockIdx.x; line < nlines; line += gridDim.x) {
-    const int ho = (int)(line % Ho);
-    const long long r = line / Ho;
-    // stage: s_lines[kh][j] = src[r][ho + sgn*kh + off][j + base], base = off - (sgn < 0 ? 7 : 0), j in [0, Wo + 8)
-    const int base = off - (sgn < 0 ? 7 : 0);
-    for (int i = threadIdx.x; i < 8 * pitch; i += blockDim.x) {
-      const int kh = i / pitch, j = i - kh * pitch;
-      const int hs = ho + sgn * kh + off, ws = j + base;
-      bf16 v = __float2bfloat16_rn(0.f);
-      if (kh < k && hs >= 0 && hs < Hs && ws >= 0 && ws < Ws) v = src[(r * Hs + hs) * Ws + ws];
-      s_lines[i] = v;
-    }
-    __syncthreads();
-    bf16* oline = out + line * Wo * 64;
-    for (int i = threadIdx.x; i < Wo * 8; i += blockDim.x) {
-      const int kh = i & 7, wo = i >> 3;
-      const bf16* sl = s_lines + kh * pitch + wo - base + off;      // + sgn*kw walks the line
-      float v[8];
+                                                         int Hs, int Ws, int Ho, int Wo, int k, int sgn, int off, int pitch) {
+  extern __shared__ uint32_t s_words[];              // [kExpandBand + 7][pitch / 2]
+  const int pw = pitch >> 1;                         // words per staged line
+  const int nbands = (Ho + kExpandBand - 1) / kExpandBand;
+  const long long nwork = rows * nbands;
+  const int base = off - (sgn < 0 ? 7 : 0);
+  // zero masks for kw >= k inside output word i (kw = 2i, 2i + 1)
+  uint32_t wmask[4];
 #pragma unroll
-      for (int kw = 0; kw < 8; ++kw) v[kw] = (kw < k && kh < k) ? __bfloat162float(sl[sgn * kw]) : 0.f;
-      Vec8<bf16>::store(oline + (long long)wo * 64 + kh * 8, v);
+  for (int i = 0; i < 4; ++i) wmask[i] = (2 * i < k ? 0x0000ffffu : 0u) | (2 * i + 1 < k ? 0xffff0000u : 0u);
+  for (long long wk = blockIdx.x; wk < nwork; wk += gridDim.x) {
+    const int bi = (int)(wk % nbands);
+    const long long r = wk / nbands;
+    const int ho0 = bi * kExpandBand, nlo = min(kExpandBand, Ho - ho0);
+    // staged line l <-> source line hs = hs0 + l;  output line ho uses line (ho - ho0) + (sgn > 0 ? kh : 7 - kh)
+    const int hs0 = ho0 + off - (sgn < 0 ? 7 : 0);
+    const int nl = nlo + 7;
+    __syncthreads();                                 // previous band fully written out
+    bf16* sl = reinterpret_cast<bf16*>(s_words);
+    for (int l = 0; l < nl; ++l) {
+      const int hs = hs0 + l;
+      const bf16* gl = src + (r * Hs + hs) * (long long)Ws;
+      for (int j = threadIdx.x; j < pitch; j += blockDim.x) {
+        const int ws = j + base;
+        bf16 v = __float2bfloat16_rn(0.f);
+        if (hs >= 0 && hs < Hs && ws >= 0 && ws < Ws) v = gl[ws];
+        sl[l * pitch + j] = v;
+      }
     }
     __syncthreads();
+    for (int lo = 0; lo < nlo; ++lo) {
+      uint4* oline = reinterpret_cast<uint4*>(out + ((r * Ho + ho0 + lo) * (long long)Wo) * 64);
+      for (int i = threadIdx.x; i < Wo * 8; i += blockDim.x) {
+        const int kh = i & 7, wo = i >> 3;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (kh < k) {
+          const int l = lo + (sgn > 0 ? kh : 7 - kh);
+          const int e0 = wo;                         // lowest staged column of the item (columns e0 .. e0 + 7)
+          const uint32_t* w = s_words + l * pw + (e0 >> 1);
+          const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+          if (sgn > 0) {
+            const uint32_t sh = (uint32_t)(e0 & 1) * 16u;
+            o.x = __funnelshift_r(w0, w1, sh); o.y = __funnelshift_r(w1, w2, sh);
+            o.z = __funnelshift_r(w2, w3, sh); o.w = __funnelshift_r(w3, w4, sh);
+          } else if (e0 & 1) {                       // descending from column e0 + 7: (lo of w[4-i], hi of w[3-i])
+            o.x = __byte_perm(w4, w3, 0x7610); o.y = __byte_perm(w3, w2, 0x7610);
+            o.z = __byte_perm(w2, w1, 0x7610); o.w = __byte_perm(w1, w0, 0x7610);
+          } else {                                   // descending, even start: halves of w[3-i] swapped
+            o.x = __byte_perm(w3, 0u, 0x1032); o.y = __byte_perm(w2, 0u, 0x1032);
+            o.z = __byte_perm(w1, 0u, 0x1032); o.w = __byte_perm(w0, 0u, 0x1032);
+          }
+          o.x &= wmask[0]; o.y &= wmask[1]; o.z &= wmask[2]; o.w &= wmask[3];
+        }
+        oline[i] = o;
+      }
+    }
   }
 }
 
@@ -246,11 +280,16 @@ __global__ void im2col_dw_kernel(const float* __restrict__ dwe, float* __restric
 
 inline int launch_expand_hw(const bf16* src, bf16* out, long long rows, int Hs, int Ws, int Ho, int Wo, int k, int sgn, int off,
                             cudaStream_t st) {
-  const long long nlines = rows * Ho;
-  long long grid = nlines < (long long)num_sms() * 8 ? nlines : (long long)num_sms() * 8;
+  const long long nwork = rows * ((Ho + kExpandBand - 1) / kExpandBand);
+  long long grid = nwork < (long long)num_sms() * 8 ? nwork : (long long)num_sms() * 8;
   if (grid < 1) grid = 1;
-  const size_t smem = (size_t)8 * (Wo + 8) * sizeof(bf16);
-  expand_hw_kernel<<<(unsigned)grid, 256, smem, st>>>(src, out, rows, Hs, Ws, Ho, Wo, k, sgn, off);
+  // staged line: Wo + 8 columns + 2 of slack for the fifth word; an odd number of words per line spreads the 8 lines
+  // a warp reads (one per kh) over the banks
+  int pitch = (Wo + 10 + 1) & ~1;
+  if (((pitch >> 1) & 1) == 0) pitch += 2;
+  const size_t smem = (size_t)(kExpandBand + 7) * pitch * sizeof(bf16);
+  MRA_REQUIRE(smem <= 48 * 1024, "expand_hw: line too long (Wo = %d)", Wo);
+  expand_hw_kernel<<<(unsigned)grid, 256, smem, st>>>(src, out, rows, Hs, Ws, Ho, Wo, k, sgn, off, pitch);
   MRA_LAUNCH_CHECK();
   return 0;
 }
