@@ -358,9 +358,16 @@ struct GatherP {
   unsigned long long* dbg;
   // Merged parity phases (stride-2 dgrad-form plans): ONE launch walks (spatial tile, phase) work items, so the 8
   // phases of a tile run back to back on neighbouring SMs and re-read the input tile from L2 instead of HBM.
-  int nph;                          // 1 (plain launch) or 8
-  int16_t ph_tap0[9];               // phase p uses taps [ph_tap0[p], ph_tap0[p + 1])
-  int8_t ph_od[8], ph_oh[8], ph_ow[8];   // output coordinate offsets of phase p
+  int nph;                          // work items per spatial tile: 1 (plain launch), 8 (phases) or 4 (phase pairs)
+  int16_t ph_tap0[9];               // item p uses entries [ph_tap0[p], ph_tap0[p + 1]) of the tap arrays
+  int8_t ph_od[8], ph_oh[8], ph_ow[8];   // output coordinate offsets of item p
+  // Phase pairs (n_tile = 64 only: an N = 64 MMA costs 54.5 clk where 32 would be ideal, N = 128 the ideal 64): the two
+  // phases that differ in the parity of w share a 128-column accumulator (columns [0, 64) = even w, [64, 128) = odd w,
+  // adjacent output positions).  A tap entry is then one A offset with the weight slab of either phase or of both:
+  // both -> one N = 128 MMA over the two slabs stacked in the stage, one -> N = 64 into its half.
+  int pair;
+  int16_t twi2[kMaxTaps];           // second phase's slab of the entry (-1: none; then twi may be -1 instead)
+  uint8_t eacc[kMaxTaps];           // 1: the entry's columns were already written by an earlier entry (accumulate)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -371,12 +378,12 @@ struct TileCoord { int n, lw0, lh0, ld0, n0, ph; };
 // phase of work item `tile` of a merged launch: rotated with the spatial index so that every CTA of the persistent
 // schedule sees all phases (they carry 1..8 taps) equally often
 __device__ __forceinline__ int tile_phase(const GatherP& P, int tile) {
-  return P.nph == 8 ? ((tile & 7) + (tile >> 3)) & 7 : 0;
+  return P.nph == 8 ? ((tile & 7) + (tile >> 3)) & 7 : (P.nph == 4 ? ((tile & 3) + (tile >> 2)) & 3 : 0);
 }
 __device__ __forceinline__ TileCoord decode_tile(const GatherP& P, int tile) {
   TileCoord t;
   t.ph = tile_phase(P, tile);
-  if (P.nph == 8) tile >>= 3;
+  if (P.nph == 8) tile >>= 3; else if (P.nph == 4) tile >>= 2;
   const int nt = tile % P.n_tiles; tile /= P.n_tiles;
   const int tw = tile % P.tilesW; tile /= P.tilesW;
   const int th = tile % P.tilesH; tile /= P.tilesH;
@@ -395,8 +402,10 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ GatherP P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t b_bytes = (uint32_t)P.n_tile * 128u;
+  const uint32_t slab_bytes = (uint32_t)P.n_tile * 128u;
+  const uint32_t b_bytes = P.pair ? 2u * slab_bytes : slab_bytes;
   const uint32_t stage_bytes = kABytes + b_bytes;
+  const int acc_cols = P.pair ? 2 * P.n_tile : P.n_tile;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + P.stages;
   uint64_t* acc_full = empty_bar + P.stages;      // [nbuf]
@@ -437,10 +446,12 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (!mbar_wait(&empty_bar[s], ph ^ 1u, P.err, 1)) { ok = false; break; }
           if (prof) t_wait += clock64() - tw0;
           uint8_t* sa = smem + (size_t)s * stage_bytes;
-          mbar_expect_tx(&full_bar[s], stage_bytes);
+          const int w1 = P.twi[tap], w2 = P.pair ? P.twi2[tap] : -1;
+          mbar_expect_tx(&full_bar[s], kABytes + ((w1 >= 0 && w2 >= 0) ? 2u * slab_bytes : slab_bytes));
           tma_load_5d(sa, &tmA, &full_bar[s], kc * 64, t.lw0 * P.astep + P.tdw[tap], t.lh0 * P.astep + P.tdh[tap],
                       t.ld0 * P.astep + P.tdd[tap], t.n);
-          tma_load_2d(sa + kABytes, &tmB, &full_bar[s], kc * 64, (int)P.twi[tap] * P.Cn + t.n0);
+          tma_load_2d(sa + kABytes, &tmB, &full_bar[s], kc * 64, (w1 >= 0 ? w1 : w2) * P.Cn + t.n0);
+          if (w1 >= 0 && w2 >= 0) tma_load_2d(sa + kABytes + slab_bytes, &tmB, &full_bar[s], kc * 64, w2 * P.Cn + t.n0);
           if (++s == P.stages) { s = 0; ph ^= 1u; }
           if (++kc == P.kchunks) { kc = 0; ++tap; }
         }
@@ -449,7 +460,7 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == kMmaWarp) {
     if (elect_one()) {
-      const uint32_t idesc = make_idesc(P.n_tile, 0, 0);
+      const uint32_t idesc1 = make_idesc(P.n_tile, 0, 0), idesc2 = make_idesc(2 * P.n_tile, 0, 0);
       const uint64_t desc0 = desc_kmajor_sw128(0);
       const uint32_t smem_u = smem_u32(smem) >> 4, stage_u = stage_bytes >> 4;
       int s = 0;
@@ -465,10 +476,11 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (!mbar_wait(&acc_empty[buf], aph ^ 1u, P.err, 4)) { ok = false; break; }   // epilogue drained this buffer
         if (prof) t_wacc += clock64() - ta0;
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * P.n_tile);
+        const uint32_t d_tmem0 = tmem_base + (uint32_t)(buf * acc_cols);
         // single issuing thread: no divisions, descriptors advance by constants (16-byte units)
         const int tph = tile_phase(P, tile);
-        const int iters = (P.ph_tap0[tph + 1] - P.ph_tap0[tph]) * P.kchunks;
+        int tap = P.ph_tap0[tph], kc = 0;
+        const int iters = (P.ph_tap0[tph + 1] - tap) * P.kchunks;
         for (int it = 0; it < iters; ++it) {
           const long long tw0 = prof ? clock64() : 0;
           if (!mbar_wait(&full_bar[s], ph, P.err, 2)) { ok = false; break; }
@@ -477,12 +489,20 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t sa_u = smem_u + (uint32_t)s * stage_u;
           const uint64_t ad = desc0 | (uint64_t)(sa_u & 0x3FFFu);
           const uint64_t bd = desc0 | (uint64_t)((sa_u + (kABytes >> 4)) & 0x3FFFu);
-          umma_f16(d_tmem, ad, bd, idesc, (uint32_t)(it != 0));
+          uint32_t idesc = idesc1, d_tmem = d_tmem0, acc = (uint32_t)(it != 0);
+          if (P.pair) {                            // entry = one A offset x the slab(s) of the even-w / odd-w phase
+            const bool has1 = P.twi[tap] >= 0, has2 = P.twi2[tap] >= 0;
+            idesc = (has1 && has2) ? idesc2 : idesc1;
+            d_tmem = d_tmem0 + (has1 ? 0u : (uint32_t)P.n_tile);
+            acc = (uint32_t)(P.eacc[tap] != 0 || kc != 0);
+          }
+          umma_f16(d_tmem, ad, bd, idesc, acc);
           umma_f16(d_tmem, ad + 2, bd + 2, idesc, 1u);
           umma_f16(d_tmem, ad + 4, bd + 4, idesc, 1u);
           umma_f16(d_tmem, ad + 6, bd + 6, idesc, 1u);
           umma_commit(&empty_bar[s]);
           if (++s == P.stages) { s = 0; ph ^= 1u; }
+          if (++kc == P.kchunks) { kc = 0; ++tap; }
         }
         if (ok) umma_commit(&acc_full[buf]);
         if (++buf == P.nbuf) { buf = 0; aph ^= 1u; }
@@ -526,13 +546,13 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (!ok) break;
       tc_fence_after();
       const long long te0 = (P.debug & 2) ? clock64() : 0;
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * P.n_tile);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
       uint64_t* rel_bar = &acc_empty[buf];
-      epilogue_tile(E, t_addr, W.c_begin, 2, nchunks, valid, obase, t.n0, lane, st_s, st_q, defer, d1, d2, [&]() {
+      epilogue_tile(E, t_addr, W.c_begin, 2, acc_cols / 32, valid, obase, t.n0, lane, st_s, st_q, defer, d1, d2, [&]() {
         tc_fence_before();                      // accumulator fully read: hand the buffer back to the MMA warp
         __syncwarp();
         if (lane == 0) mbar_arrive(rel_bar);
-      });
+      }, P.pair != 0, P.osw, valid);
       if ((P.debug & 2) && threadIdx.x == 0) atomicAdd(P.dbg + 4, (unsigned long long)(clock64() - te0));
       if (++buf == P.nbuf) { buf = 0; aph ^= 1u; }
     }
@@ -984,7 +1004,43 @@ inline bool gather_mergeable(const GatherPlan& plan) {
 }
 
 // One launch of gather_tc_kernel (one TMA box per filter tap): a single GatherLaunch of the plan, or all 8 parity
-// phases merged (`nl` = 8 consecutive launches starting at `Ls`).
+// phases merged (`nl` = 8 consecutive launches starting at `Ls`); with 64 output channels the merged phases are
+// paired along w (see GatherP::pair).
+struct PairEntry { int dd, dh, dw, w1, w2; };
+inline bool build_phase_pairs(const GatherLaunch* Ls, int slabs, std::vector<std::vector<PairEntry>>& items, int (*o0)[3]) {
+  bool used[8] = {false, false, false, false, false, false, false, false};
+  items.clear();
+  for (int a = 0; a < 8; ++a) {
+    if (used[a]) continue;
+    int b = -1;
+    for (int c = 0; c < 8; ++c)
+      if (c != a && !used[c] && Ls[c].o0[0] == Ls[a].o0[0] && Ls[c].o0[1] == Ls[a].o0[1] && abs(Ls[c].o0[2] - Ls[a].o0[2]) == 1) b = c;
+    if (b < 0) return false;
+    int lo = Ls[a].o0[2] < Ls[b].o0[2] ? a : b, hi = lo == a ? b : a;
+    used[a] = used[b] = true;
+    std::vector<PairEntry> both, only1, only2;
+    for (const Tap& t : Ls[lo].taps) {
+      if (t.widx >= slabs) return false;
+      int w2 = -1;
+      for (const Tap& u : Ls[hi].taps) if (u.dd == t.dd && u.dh == t.dh && u.dw == t.dw) w2 = u.widx;
+      (w2 >= 0 ? both : only1).push_back(PairEntry{t.dd, t.dh, t.dw, t.widx, w2});
+    }
+    for (const Tap& u : Ls[hi].taps) {
+      if (u.widx >= slabs) return false;
+      bool shared = false;
+      for (const Tap& t : Ls[lo].taps) if (u.dd == t.dd && u.dh == t.dh && u.dw == t.dw) shared = true;
+      if (!shared) only2.push_back(PairEntry{u.dd, u.dh, u.dw, -1, u.widx});
+    }
+    std::vector<PairEntry> e = both;                    // N = 128 entries first: they initialise both halves at once
+    e.insert(e.end(), only1.begin(), only1.end());
+    e.insert(e.end(), only2.begin(), only2.end());
+    const int idx = (int)items.size();
+    for (int i = 0; i < 3; ++i) o0[idx][i] = Ls[lo].o0[i];
+    items.push_back(e);
+  }
+  return items.size() == 4;
+}
+
 inline int run_gather_v1_launch(const GatherPlan& plan, const GatherLaunch* Ls, int nl, const GatherRun& R, const CUtensorMap& tmB,
                                 int n_tile, cudaStream_t st) {
   static bool attr_set = false;
@@ -996,12 +1052,20 @@ inline int run_gather_v1_launch(const GatherPlan& plan, const GatherLaunch* Ls, 
   MRA_REQUIRE(nl == 1 || nl == 8, "gather launch: 1 or 8 phases");
   GatherP P;
   memset(&P, 0, sizeof(P));
+  std::vector<std::vector<PairEntry>> pairs;
+  int pair_o0[4][3];
+  if (nl == 8 && n_tile == 64 && plan.cn == 64 && getenv("MRA_GATHER_NOPAIR") == nullptr && build_phase_pairs(Ls, R.slabs, pairs, pair_o0)) {
+    size_t ne = 0;
+    for (const auto& e : pairs) ne += e.size();
+    P.pair = ne <= (size_t)kMaxTaps ? 1 : 0;
+  }
+  const int items = P.pair ? 4 : nl;
   P.bd = L.box[0]; P.bh = L.box[1]; P.bw = L.box[2];
   P.Dl = L.dims[0]; P.Hl = L.dims[1]; P.Wl = L.dims[2];
   P.tilesD = (P.Dl + P.bd - 1) / P.bd; P.tilesH = (P.Hl + P.bh - 1) / P.bh; P.tilesW = (P.Wl + P.bw - 1) / P.bw;
   P.astep = L.astep;
   P.Cn = plan.cn; P.n_tile = n_tile; P.n_tiles = plan.cn / n_tile; P.kchunks = plan.ck / 64;
-  const long long total_tiles = (long long)plan.n * P.tilesD * P.tilesH * P.tilesW * P.n_tiles * nl;
+  const long long total_tiles = (long long)plan.n * P.tilesD * P.tilesH * P.tilesW * P.n_tiles * items;
   MRA_REQUIRE(total_tiles < (1ll << 31), "too many tiles");
   P.total_tiles = (int)total_tiles;
   P.ostep = L.ostep; P.od0 = L.o0[0]; P.oh0 = L.o0[1]; P.ow0 = L.o0[2];
@@ -1014,29 +1078,49 @@ inline int run_gather_v1_launch(const GatherPlan& plan, const GatherLaunch* Ls, 
   P.stats = R.stats; P.err = tc_err_flag();
   { const char* e = getenv("MRA_GATHER_DEBUG"); P.debug = e ? atoi(e) : 0; }
   P.dbg = tc_dbg_counters();
-  P.nph = nl;
+  P.nph = items;
   int nt = 0;
-  for (int p = 0; p < nl; ++p) {
-    const GatherLaunch& Lp = Ls[p];
-    P.ph_tap0[p] = (int16_t)nt;
-    P.ph_od[p] = (int8_t)Lp.o0[0]; P.ph_oh[p] = (int8_t)Lp.o0[1]; P.ph_ow[p] = (int8_t)Lp.o0[2];
-    for (const Tap& t : Lp.taps) {
-      MRA_REQUIRE(nt < kMaxTaps, "too many taps for the tensor-core path");
-      MRA_REQUIRE(t.dd >= -128 && t.dd < 128 && t.widx < R.slabs, "tap out of range");
-      P.tdd[nt] = (int8_t)t.dd; P.tdh[nt] = (int8_t)t.dh; P.tdw[nt] = (int8_t)t.dw;
-      P.twi[nt] = (int16_t)t.widx;
-      ++nt;
+  if (P.pair) {
+    for (int p = 0; p < 4; ++p) {
+      P.ph_tap0[p] = (int16_t)nt;
+      P.ph_od[p] = (int8_t)pair_o0[p][0]; P.ph_oh[p] = (int8_t)pair_o0[p][1]; P.ph_ow[p] = (int8_t)pair_o0[p][2];
+      bool init1 = false, init2 = false;
+      for (const PairEntry& e : pairs[p]) {
+        MRA_REQUIRE(e.dd >= -128 && e.dd < 128, "tap out of range");
+        P.tdd[nt] = (int8_t)e.dd; P.tdh[nt] = (int8_t)e.dh; P.tdw[nt] = (int8_t)e.dw;
+        P.twi[nt] = (int16_t)e.w1; P.twi2[nt] = (int16_t)e.w2;
+        if (e.w1 >= 0 && e.w2 >= 0) { MRA_REQUIRE(init1 == init2, "pair entry order"); P.eacc[nt] = init1 ? 1 : 0; init1 = init2 = true; }
+        else if (e.w1 >= 0) { P.eacc[nt] = init1 ? 1 : 0; init1 = true; }
+        else { P.eacc[nt] = init2 ? 1 : 0; init2 = true; }
+        ++nt;
+      }
+      MRA_REQUIRE(init1 && init2, "pair item without taps for one phase");
     }
+    P.ph_tap0[4] = (int16_t)nt;
+  } else {
+    for (int p = 0; p < nl; ++p) {
+      const GatherLaunch& Lp = Ls[p];
+      P.ph_tap0[p] = (int16_t)nt;
+      P.ph_od[p] = (int8_t)Lp.o0[0]; P.ph_oh[p] = (int8_t)Lp.o0[1]; P.ph_ow[p] = (int8_t)Lp.o0[2];
+      for (const Tap& t : Lp.taps) {
+        MRA_REQUIRE(nt < kMaxTaps, "too many taps for the tensor-core path");
+        MRA_REQUIRE(t.dd >= -128 && t.dd < 128 && t.widx < R.slabs, "tap out of range");
+        P.tdd[nt] = (int8_t)t.dd; P.tdh[nt] = (int8_t)t.dh; P.tdw[nt] = (int8_t)t.dw;
+        P.twi[nt] = (int16_t)t.widx; P.twi2[nt] = -1;
+        ++nt;
+      }
+    }
+    P.ph_tap0[nl] = (int16_t)nt;
   }
-  P.ph_tap0[nl] = (int16_t)nt;
   P.ntaps = nt;
-  const size_t stage_bytes = kABytes + (size_t)n_tile * 128;
+  const int acc_cols = P.pair ? 2 * n_tile : n_tile;
+  const size_t stage_bytes = kABytes + (size_t)acc_cols * 128;
   int stages = (int)((kSmemLimit - 2048 - kEpiRedBytes) / stage_bytes);
   if (stages > 6) stages = 6;
   P.stages = stages;
-  P.nbuf = 512 / n_tile > 8 ? 8 : 512 / n_tile;
+  P.nbuf = 512 / acc_cols > 8 ? 8 : 512 / acc_cols;
   { const char* e = getenv("MRA_GATHER_NBUF"); if (e && atoi(e) >= 2 && atoi(e) <= P.nbuf) P.nbuf = atoi(e); }
-  P.tmem_cols = pow2_cols(P.nbuf * n_tile);
+  P.tmem_cols = pow2_cols(P.nbuf * acc_cols);
   const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
   CUtensorMap tmA;
   if (int rc = make_act_map(&tmA, R.a, plan.n, plan.adims[0], plan.adims[1], plan.adims[2], plan.ck, P.bw, P.bh, P.bd,
