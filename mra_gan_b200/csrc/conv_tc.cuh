@@ -169,9 +169,9 @@ __device__ __forceinline__ uint64_t desc_mnmajor_sw128(uint32_t saddr, uint32_t 
          ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32, a=b=BF16, M=128, N=n
-__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major, int m = 128) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // Sum over the 32 lanes of each of 32 per-lane values; lane j ends up with column j's total.
@@ -563,6 +563,76 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, P.tmem_cols);
 }
 
+// ---- cta_group::2 (CTA pair) flavours of the PTX wrappers.  In pair mode two CTAs of a cluster (one TPC) each
+// own a 128-row tile and HALF of the weight slab; the leader (cluster rank 0) issues one M = 256 MMA for both,
+// so every CTA streams only half of the weights from L2.  TMA loads of both CTAs signal the LEADER's barrier
+// (peer bit 24 of the shared::cluster address cleared), tcgen05.commit multicasts to both CTAs' barriers.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <bool kPair>
+__device__ __forceinline__ void tma_load_5d_g(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                              int c4) {
+  if constexpr (kPair) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+  } else {
+    tma_load_5d(dst, tm, bar, c0, c1, c2, c3, c4);
+  }
+}
+template <bool kPair>
+__device__ __forceinline__ void tma_load_2d_g(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  if constexpr (kPair) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+  } else {
+    tma_load_2d(dst, tm, bar, c0, c1);
+  }
+}
+template <bool kPair>
+__device__ __forceinline__ void umma_commit_g(uint64_t* bar) {
+  if constexpr (kPair) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+  } else {
+    umma_commit(bar);
+  }
+}
+template <bool kPair>
+__device__ __forceinline__ void umma_f16_g(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kPair) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    umma_f16(d_tmem, adesc, bdesc, idesc, accumulate);
+  }
+}
+// arrive on the barrier at the same offset in the pair's leader CTA
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_m(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+
 // ------------------------------------------------------------------ wgrad kernel
 // D[tap][m][n] = sum_{positions q} Dense[q][m] * Shifted[q*sstep + tap][n]
 //   Dense   = the operand read at the K-block positions themselves (dy for Conv3d, x for ConvTranspose3d),
@@ -628,9 +698,9 @@ __device__ __forceinline__ int wg_item_ntap(const WgradP& P, int g, int item) {
   const WGroup& G = P.grp[g];
   return min(G.gpi, G.ntaps - (item - G.item0) * G.gpi);
 }
-__device__ __forceinline__ void wseg_begin(const WgradP& P, long long kblocks, WSegIter& it) {
-  const long long share = (P.total_cost + gridDim.x - 1) / gridDim.x;
-  it.pos = (long long)blockIdx.x * share;
+__device__ __forceinline__ void wseg_begin(const WgradP& P, long long kblocks, WSegIter& it, int unit, int nunits) {
+  const long long share = (P.total_cost + nunits - 1) / nunits;
+  it.pos = (long long)unit * share;
   it.end = min(it.pos + share, P.total_cost);
   it.work = 0; it.woff = 0;
   const int per_item = P.m_tiles * P.n_tiles;
@@ -666,14 +736,24 @@ __device__ __forceinline__ bool wseg_next(const WgradP& P, long long kblocks, WS
   return false;
 }
 
+// kPair: two CTAs of a cluster form one cta_group::2 unit.  Each CTA owns one 128-row m tile (M = 256 per MMA) and loads
+// only HALF of the shifted operand's channel chunks -- the tensor core reads the other half from the partner's shared
+// memory -- so the L2 -> SM traffic per FLOP drops by a third (G.rb wgrad was bound by exactly that traffic).
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ WMaps tmN,
                 const __grid_constant__ WgradP P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kCtas = kPair ? 2 : 1;
+  const int rank = kPair ? (int)cluster_ctarank() : 0;
+  const bool leader = rank == 0;
+  const int unit = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nunits = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int ncc_l = P.ncc / kCtas;                           // shifted-operand chunks held by this CTA
   const uint32_t m_bytes = 2 * kChunkBytes;                  // the m tile always owns two chunk slots
-  const uint32_t set_bytes = (uint32_t)P.ncc * (uint32_t)P.box_bytes;
+  const uint32_t set_bytes = (uint32_t)ncc_l * (uint32_t)P.box_bytes;
   const uint32_t stage_bytes = m_bytes + (uint32_t)P.sets_max * set_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + P.stages;
@@ -689,7 +769,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
     for (int g = 0; g < P.n_groups; ++g) prefetch_tmap(&tmN.m[g]);
     for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 4);
+    mbar_init(acc_empty, 4 * kCtas);
     fence_barrier_init();
   }
   if (P.m_chunks == 1) {
@@ -700,9 +780,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
     }
     fence_proxy_async();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, P.tmem_cols);
+  if (warp == 1) {
+    if constexpr (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(P.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      tmem_alloc(tmem_slot, P.tmem_cols);
+    }
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const bool prof = (P.debug & 2) != 0;
@@ -710,7 +798,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
   if (warp == 0) {
     // ---- TMA producer: lane j issues box j of every stage (box 0..m_chunks-1 dense, then the shifted boxes)
     WSegIter it; WSeg sg;
-    wseg_begin(P, kblocks, it);
+    wseg_begin(P, kblocks, it, unit, nunits);
     int s = 0;
     uint32_t ph = 0;
     long long t_wait = 0, t_begin = prof ? clock64() : 0;
@@ -718,8 +806,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
     while (ok && wseg_next(P, kblocks, it, sg)) {
       const WGroup& G = P.grp[sg.g];
       const int nsets = (sg.ntap + G.share - 1) / G.share;
-      const int nboxes = P.m_chunks + nsets * P.ncc;
-      const uint32_t tx_bytes = (uint32_t)P.m_chunks * kChunkBytes + (uint32_t)(nsets * P.ncc) * (uint32_t)G.box_tx;
+      const int nboxes = P.m_chunks + nsets * ncc_l;
+      // bytes landing per stage in the whole unit (pair: both CTAs' boxes complete on the leader's barrier)
+      const uint32_t tx_bytes = ((uint32_t)P.m_chunks * kChunkBytes + (uint32_t)(nsets * ncc_l) * (uint32_t)G.box_tx) * kCtas;
+      const int mt = kPair ? 2 * sg.mt + rank : sg.mt;
       // this lane's box
       const bool active = lane < nboxes;
       const bool dense = lane < P.m_chunks;
@@ -727,11 +817,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
       uint32_t soff = 0;
       const CUtensorMap* tm = &tmM;
       if (active) {
-        if (dense) { c0 = sg.mt * 128 + 64 * lane; soff = (uint32_t)lane * kChunkBytes; }
+        if (dense) { c0 = mt * 128 + 64 * lane; soff = (uint32_t)lane * kChunkBytes; }
         else {
-          const int bi = lane - P.m_chunks, bs = bi / P.ncc, j = bi - bs * P.ncc;
+          const int bi = lane - P.m_chunks, bs = bi / ncc_l, j = bi - bs * ncc_l;
           const int t = sg.tap0 + bs * G.share;
-          c0 = sg.nt * P.ncc * 64 + 64 * j; ow = P.odw[t]; oh = P.odh[t]; od = P.odd[t]; step = P.sstep;
+          c0 = sg.nt * P.ncc * 64 + 64 * (rank * ncc_l + j); ow = P.odw[t]; oh = P.odh[t]; od = P.odd[t]; step = P.sstep;
           soff = m_bytes + (uint32_t)bs * set_bytes + (uint32_t)j * (uint32_t)P.box_bytes;
           tm = &tmN.m[sg.g];
         }
@@ -746,20 +836,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
         const long long tw0 = prof ? clock64() : 0;
         if (!mbar_wait(&empty_bar[s], ph ^ 1u, P.err, 11)) { ok = false; break; }
         if (prof) t_wait += clock64() - tw0;
-        if (lane == 0) mbar_expect_tx(&full_bar[s], tx_bytes);
+        if (lane == 0 && leader) mbar_expect_tx(&full_bar[s], tx_bytes);
         __syncwarp();
         if (active)
-          tma_load_5d(smem + (size_t)s * stage_bytes + soff, tm, &full_bar[s], c0, tw * P.bw * step + ow,
-                      th * P.bh * step + oh, td * P.bd * step + od, n);
+          tma_load_5d_g<kPair>(smem + (size_t)s * stage_bytes + soff, tm, &full_bar[s], c0, tw * P.bw * step + ow,
+                               th * P.bh * step + oh, td * P.bd * step + od, n);
         if (++tw == P.tilesW) { tw = 0; if (++th == P.tilesH) { th = 0; if (++td == P.tilesD) { td = 0; ++n; } } }
         if (++s == P.stages) { s = 0; ph ^= 1u; }
       }
     }
     if (prof && lane == 0) { atomicAdd(P.dbg + 0, (unsigned long long)t_wait); atomicAdd(P.dbg + 1, (unsigned long long)(clock64() - t_begin)); }
   } else if (warp == 1) {
-    if (elect_one()) {
+    if (elect_one() && leader) {
       WSegIter it; WSeg sg;
-      wseg_begin(P, kblocks, it);
+      wseg_begin(P, kblocks, it, unit, nunits);
       const uint32_t smem_u = smem_u32(smem) >> 4, stage_u = stage_bytes >> 4;
       int s = 0;
       uint32_t ph = 0;
@@ -793,7 +883,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
           const int gi = min(g, sg.ntap - 1);
           m_boff[i] = (m_bytes + (uint32_t)(gi / G.share) * set_bytes + (uint32_t)P.rshift[sg.tap0 + gi] * 128u) >> 4;
           m_dcol[i] = (uint32_t)(gi * P.ncc * 64);
-          m_idesc[i] = make_idesc(nt * P.ncc * 64, 1, 1);
+          m_idesc[i] = make_idesc(nt * P.ncc * 64, 1, 1, 128 * kCtas);
         }
         const uint64_t a_desc0 = desc_mnmajor_sw128(0, kChunkBytes);
         const uint64_t b_desc0 = desc_mnmajor_sw128(0, (uint32_t)P.box_bytes);
@@ -812,15 +902,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
             const uint32_t d_tmem = tmem_base + m_dcol[i];
             const uint32_t bu = sa_u + m_boff[i];
             const uint32_t id = m_idesc[i];
-            umma_f16(d_tmem, ad, b_desc0 | (uint64_t)((bu + rm0) & 0x3FFFu), id, accf);
-            umma_f16(d_tmem, ad + 128, b_desc0 | (uint64_t)((bu + rm1) & 0x3FFFu), id, 1u);
-            umma_f16(d_tmem, ad + 256, b_desc0 | (uint64_t)((bu + rm2) & 0x3FFFu), id, 1u);
-            umma_f16(d_tmem, ad + 384, b_desc0 | (uint64_t)((bu + rm3) & 0x3FFFu), id, 1u);
+            umma_f16_g<kPair>(d_tmem, ad, b_desc0 | (uint64_t)((bu + rm0) & 0x3FFFu), id, accf);
+            umma_f16_g<kPair>(d_tmem, ad + 128, b_desc0 | (uint64_t)((bu + rm1) & 0x3FFFu), id, 1u);
+            umma_f16_g<kPair>(d_tmem, ad + 256, b_desc0 | (uint64_t)((bu + rm2) & 0x3FFFu), id, 1u);
+            umma_f16_g<kPair>(d_tmem, ad + 384, b_desc0 | (uint64_t)((bu + rm3) & 0x3FFFu), id, 1u);
           }
-          umma_commit(&empty_bar[s]);
+          umma_commit_g<kPair>(&empty_bar[s]);
           if (++s == P.stages) { s = 0; ph ^= 1u; }
         }
-        if (ok) umma_commit(acc_full);
+        if (ok) umma_commit_g<kPair>(acc_full);
         ++nseg;
       }
       if (prof) {
@@ -832,7 +922,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
     const int q = warp & 3;
     const int ml = q * 32 + lane;
     WSegIter it; WSeg sg;
-    wseg_begin(P, kblocks, it);
+    wseg_begin(P, kblocks, it, unit, nunits);
     int nseg = 0;
     long long t_epi = 0;
     const int ncols = P.ncc * 64;
@@ -840,7 +930,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
       if (!mbar_wait(acc_full, (uint32_t)nseg & 1u, P.err, 13)) break;
       tc_fence_after();
       const long long te0 = prof ? clock64() : 0;
-      const int m = sg.mt * 128 + ml;
+      const int m = (kPair ? 2 * sg.mt + rank : sg.mt) * 128 + ml;
       const int n0 = sg.nt * ncols;
       const bool valid = ml < 64 * P.m_chunks && m < P.Km && !(P.debug & 1);
       for (int g = 0; g < sg.ntap; ++g) {
@@ -868,15 +958,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty);              // accumulators are free for the next item
+      if (lane == 0) { if constexpr (kPair) mbar_arrive_leader(acc_empty); else mbar_arrive(acc_empty); }   // accumulators are free
       if (prof) t_epi += clock64() - te0;
       ++nseg;
     }
     if (prof && threadIdx.x == 64) atomicAdd(P.dbg + 4, (unsigned long long)t_epi);
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, P.tmem_cols);
+  if constexpr (kPair) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    if constexpr (kPair)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols) : "memory");
+    else
+      tmem_dealloc(tmem_base, P.tmem_cols);
+  }
 }
 
 // ------------------------------------------------------------------ host side
@@ -1139,7 +1234,8 @@ inline int run_wgrad_tc(const WgradPlan& plan, const void* x, const void* dy, fl
   MRA_REQUIRE(!plan.launches.empty() && (int)plan.launches.size() <= kMaxWGroups, "wgrad plan: bad group count");
   static bool attr_set = false;
   if (!attr_set) {
-    MRA_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
     attr_set = true;
   }
   // dense operand on the M side of the MMA, shifted operand on the N side
@@ -1163,7 +1259,13 @@ inline int run_wgrad_tc(const WgradPlan& plan, const void* x, const void* dy, fl
   P.Km = Km; P.Kn = Kn;
   P.m_chunks = Km >= 128 ? 2 : 1;
   P.ncc = plan.ncc;
-  P.m_tiles = (Km + 127) / 128;
+  // CTA pairs (cta_group::2): 256 dense channels per unit, each CTA loads half of the shifted chunks.  Needs whole
+  // 256-channel m tiles and one tap per MMA (ncc == 4), and enough K-blocks to feed 74 pairs.
+  long long pair_min = 64ll * 64 * 8;                       // K positions (MRA_WGRAD_PAIR_MIN: test hook)
+  { const char* e = getenv("MRA_WGRAD_PAIR_MIN"); if (e) pair_min = atoll(e); }
+  const bool pair = Km % 256 == 0 && plan.ncc == 4 && (num_sms() % 2) == 0 && getenv("MRA_WGRAD_NOPAIR") == nullptr &&
+                    (long long)plan.qdims[0] * plan.qdims[1] * plan.qdims[2] * plan.n >= pair_min;
+  P.m_tiles = pair ? Km / 256 : (Km + 127) / 128;
   P.n_tiles = Kn / (64 * P.ncc);
   P.dw = dw; P.err = err;
   { const char* e = getenv("MRA_WGRAD_DEBUG"); P.debug = e ? atoi(e) : 0; }
@@ -1207,18 +1309,33 @@ inline int run_wgrad_tc(const WgradPlan& plan, const void* x, const void* dy, fl
   }
   MRA_REQUIRE(tapc <= kMaxTaps, "wgrad plan: too many taps");
   P.n_items = itemc;
-  const size_t stage_bytes = 2 * kChunkBytes + (size_t)P.sets_max * P.ncc * P.box_bytes;
+  const size_t stage_bytes = 2 * kChunkBytes + (size_t)P.sets_max * (P.ncc / (pair ? 2 : 1)) * P.box_bytes;
   int stages = (int)((kSmemLimit - 2048) / stage_bytes);
   MRA_REQUIRE(stages >= 2, "wgrad plan: stage does not fit shared memory");
   if (stages > 6) stages = 6;
   P.stages = stages;
   P.tmem_cols = pow2_cols(max_cols);
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  if (pair) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(num_sms() & ~1), 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    MRA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<true>, tmM, maps, P));
+    MRA_LAUNCH_CHECK();
+    return 0;
+  }
   // one wave: a CTA per SM (fewer when there is less than ~4 K-blocks of work per CTA)
   long long ctas = num_sms();
   if (P.total_cost < ctas * 4) ctas = (P.total_cost + 3) / 4;
   if (ctas < 1) ctas = 1;
-  wgrad_tc_kernel<<<(unsigned)ctas, kThreads, smem, st>>>(tmM, maps, P);
+  wgrad_tc_kernel<false><<<(unsigned)ctas, kThreads, smem, st>>>(tmM, maps, P);
   MRA_LAUNCH_CHECK();
   return 0;
 }

@@ -94,75 +94,6 @@ __device__ __forceinline__ HaloTile halo_decode(const HaloP& P, int work, int pa
   return t;
 }
 
-// ---- cta_group::2 (CTA pair) flavours of the PTX wrappers.  In pair mode two CTAs of a cluster (one TPC) each
-// own a 128-row tile and HALF of the weight slab; the leader (cluster rank 0) issues one M = 256 MMA for both,
-// so every CTA streams only half of the weights from L2.  TMA loads of both CTAs signal the LEADER's barrier
-// (peer bit 24 of the shared::cluster address cleared), tcgen05.commit multicasts to both CTAs' barriers.
-constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-template <bool kPair>
-__device__ __forceinline__ void tma_load_5d_g(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3,
-                                              int c4) {
-  if constexpr (kPair) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
-  } else {
-    tma_load_5d(dst, tm, bar, c0, c1, c2, c3, c4);
-  }
-}
-template <bool kPair>
-__device__ __forceinline__ void tma_load_2d_g(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
-  if constexpr (kPair) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
-        : "memory");
-  } else {
-    tma_load_2d(dst, tm, bar, c0, c1);
-  }
-}
-template <bool kPair>
-__device__ __forceinline__ void umma_commit_g(uint64_t* bar) {
-  if constexpr (kPair) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-  } else {
-    umma_commit(bar);
-  }
-}
-template <bool kPair>
-__device__ __forceinline__ void umma_f16_g(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  if constexpr (kPair) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-  } else {
-    umma_f16(d_tmem, adesc, bdesc, idesc, accumulate);
-  }
-}
-// arrive on the barrier at the same offset in the pair's leader CTA
-__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
-}
-__host__ __device__ constexpr uint32_t make_idesc_m(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-
 template <bool kPair>
 __global__ void __launch_bounds__(kThreadsHalo, 1)
 gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,

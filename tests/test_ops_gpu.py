@@ -107,6 +107,16 @@ def test_conv_tcgen05_path(case):
     _check_conv(*case, torch.bfloat16, expect_tc=True)
 
 
+def test_wgrad_cta_pair_path(monkeypatch):
+    """wgrad_tc_kernel<true> (cta_group::2 pairs, used on G.rb at full size): force it on a shape the CPU reference can
+    check, with enough K-blocks that stream-K ranges cross work-item boundaries; then the single-CTA kernel again."""
+    case = (ConvGeom(256, 256, 3, 1, 0), (14, 12, 10), 2)
+    monkeypatch.setenv("MRA_WGRAD_PAIR_MIN", "0")
+    _check_conv(*case, torch.bfloat16, expect_tc=True)
+    monkeypatch.setenv("MRA_WGRAD_NOPAIR", "1")
+    _check_conv(*case, torch.bfloat16, expect_tc=True)
+
+
 @pytest.mark.parametrize("case", TC_CONVS[:3], ids=gid)
 def test_conv_same_shape_fp32_path(case):
     _check_conv(*case, torch.float32, expect_tc=False)
