@@ -50,10 +50,12 @@ struct GatherPlan {
 
 // One wgrad launch: a list of filter taps processed `gpi` at a time by one CTA (the accumulators of
 // all taps of an item live side by side in TMEM, so the dense operand is loaded once per item).
+// With share == K (K taps of a (K,1,1) filter, the stem / head lowerings) all taps read ONE box extended by K - 1
+// planes along d -- tap kd starts kd planes into it -- instead of K separate boxes (a third of the bytes at K = 7).
 // With share == 2 consecutive taps form pairs that read the SAME shared-memory box of the shifted
 // operand (box extended by `ext`), each through its own row shift -- the halo is loaded once.
 struct WgradLaunch {
-  int share;                 // 1 or 2
+  int share;                 // taps per shared box: 1, 2 or the whole (K,1,1) chain
   int gpi;                   // taps per item (multiple of share)
   int ext[3];                // box extension (d, h, w) of the shifted operand's box (zeros when share == 1)
   std::vector<int> taps;     // indices into WgradPlan::taps, item by item
@@ -180,7 +182,7 @@ inline void wgrad_add_launch(WgradPlan& P, const std::vector<int>& idx, int shar
   L.share = share; L.gpi = gpi; L.ext[0] = ed; L.ext[1] = eh; L.ext[2] = ew;
   L.taps = idx;
   for (size_t i = 0; i < idx.size(); ++i) {
-    const Tap& a = P.taps[idx[i - (share == 2 ? i % 2 : 0)]];      // first tap of the pair holds the minimum offsets
+    const Tap& a = P.taps[idx[i - i % share]];                     // first tap of a box set holds the minimum offsets
     L.origin.push_back(Tap{a.dd, a.dh, a.dw, 0});
   }
   P.launches.push_back(L);
@@ -209,6 +211,15 @@ inline bool build_wgrad_plan(const GeomEx& d, WgradPlan& P) {
   const int K0 = d.k[0], K1 = d.k[1], K2 = d.k[2];
   auto ti = [&](int a, int b, int c) { return (a * K1 + b) * K2 + c; };
   std::vector<int> wpairs, hpairs, rest;
+  // (K,1,1) filters (channel-expanded stem / head): one d-extended box for all K taps, 4x4x4 K-blocks so that the
+  // extension (K - 1 planes of 16 positions) stays small next to the 64 positions of the block itself
+  if (s == 1 && K1 == 1 && K2 == 1 && K0 >= 3 && K0 <= cap && getenv("MRA_WGRAD_NO_DCHAIN") == nullptr) {
+    P.box[0] = 4; P.box[1] = 4; P.box[2] = 4;
+    std::vector<int> all;
+    for (int kd = 0; kd < K0; ++kd) all.push_back(ti(kd, 0, 0));
+    wgrad_add_launch(P, all, K0, K0, K0 - 1, 0, 0);
+    return true;
+  }
   const bool can_share = s == 1 && P.box[2] % 16 == 0 && cap >= 2;
   if (can_share) {
     std::vector<int> left;                               // taps left over after pairing along w

@@ -873,7 +873,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
         // Per-segment table of the MMAs of one K-block: everything that does not depend on the stage is folded
         // into constants (descriptor offsets in 16-byte units), so the per-stage loop of this single issuing
         // thread is a wait, a handful of adds and the MMAs.
-        const int tpm = G.share == 1 ? (P.ncc >= 4 ? 1 : 4 / P.ncc) : 1;     // taps per MMA (unshared boxes sit back to back)
+        // taps per MMA: unshared boxes sit back to back (chunk stride = box size); the taps of a d-chain (share > 2,
+        // one chunk each) are the SAME box entered 16*n rows later, i.e. "chunks" with a stride of one plane: up to four
+        // of them form one N = 256 MMA (N = 64 MMAs run at 59 % of the tensor-pipe rate)
+        const bool chain = G.share > 2 && P.ncc == 1 && sg.ntap > 1;
+        const uint32_t chain_lbo = chain ? (uint32_t)(P.rshift[sg.tap0 + 1] - P.rshift[sg.tap0]) * 128u : 0u;
+        const int tpm = G.share == 1 ? (P.ncc >= 4 ? 1 : 4 / P.ncc) : (chain ? 4 : 1);
         uint32_t m_boff[8], m_dcol[8], m_idesc[8];
         const int nmma = (sg.ntap + tpm - 1) / tpm;
 #pragma unroll
@@ -886,7 +891,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
           m_idesc[i] = make_idesc(nt * P.ncc * 64, 1, 1, 128 * kCtas);
         }
         const uint64_t a_desc0 = desc_mnmajor_sw128(0, kChunkBytes);
-        const uint64_t b_desc0 = desc_mnmajor_sw128(0, (uint32_t)P.box_bytes);
+        const uint64_t b_desc0 = desc_mnmajor_sw128(0, chain ? chain_lbo : (uint32_t)P.box_bytes);
         const uint32_t rm0 = rowmap[0] * 8u, rm1 = rowmap[1] * 8u, rm2 = rowmap[2] * 8u, rm3 = rowmap[3] * 8u;
         for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
           const long long tw0 = prof ? clock64() : 0;
