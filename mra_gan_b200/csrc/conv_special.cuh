@@ -115,23 +115,33 @@ __global__ void __launch_bounds__(256) shift_sum_kernel(const TZ* __restrict__ Z
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    // Z lines are double-buffered: while line hz is being added up, line hz + 1 streams into the other buffer with
+    // cp.async (4-byte pieces: the 33-word pitch that makes the column reads conflict-free is not 16-byte aligned)
+    auto stage = [&](int hz, uint32_t* dst) {
+      if (hz >= 0 && hz < Hz && hz <= hz_hi) {
+        const uint32_t* gl = reinterpret_cast<const uint32_t*>(Z + ((r * Hz + hz) * (long long)Wz) * 64);
+        for (int i = threadIdx.x; i < Wz * 32; i += blockDim.x) {
+          const uint32_t sa = (uint32_t)__cvta_generic_to_shared(dst + (i >> 5) * 33 + (i & 31));
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gl + i) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int buf_words = Wz * 33;
+    __syncthreads();                                 // the previous band is done with both buffers
+    stage(hz_lo, s_z);
+    int cur = 0;
     // process the lines in groups of 8 so that the rotating window index is static
     for (int hz0 = hz_lo; hz0 <= hz_hi; hz0 += 8) {
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int hz = hz0 + u;
         if (hz > hz_hi) break;
+        const uint32_t* s_cur = s_z + cur * buf_words;
+        stage(hz + 1, s_z + (cur ^ 1) * buf_words);   // that buffer was last read before the barrier closing line hz - 1
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncthreads();
         const bool in_range = hz >= 0 && hz < Hz;
-        if (in_range) {
-          const uint4* gl = reinterpret_cast<const uint4*>(Z + ((r * Hz + hz) * (long long)Wz) * 64);
-          for (int i = threadIdx.x; i < Wz * 8; i += blockDim.x) {        // 8 x 16 B per position
-            const uint4 v = __ldg(gl + i);
-            uint32_t* d = s_z + (i >> 3) * 33 + (i & 7) * 4;
-            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-          }
-        }
-        __syncthreads();
         // contributions of line hz: to output line ho = hz - off - sgn*kh  for kh in [0, k)
         const int wo = threadIdx.x;                                        // Wo <= blockDim.x (checked on host)
         if (wo < Wo) {
@@ -147,7 +157,7 @@ __global__ void __launch_bounds__(256) shift_sum_kernel(const TZ* __restrict__ Z
                 if (kw >= k) break;
                 const int wz = wo + sgn * kw + off;
                 if (wz >= 0 && wz < Wz) {
-                  const uint32_t wrd = s_z[wz * 33 + ((kh * 8 + kw) >> 1)];
+                  const uint32_t wrd = s_cur[wz * 33 + ((kh * 8 + kw) >> 1)];
                   s += __uint_as_float((kw & 1) ? (wrd & 0xffff0000u) : (wrd << 16));
                 }
               }
@@ -162,9 +172,11 @@ __global__ void __launch_bounds__(256) shift_sum_kernel(const TZ* __restrict__ Z
             out[(r * Ho + ho_done) * (long long)Wo + wo] = from_f<TO>(apply_act(acc[slot_done] + b, act, slope));
           acc[slot_done] = 0.f;
         }
+        __syncthreads();                             // line hz fully consumed: its buffer may be refilled
+        cur ^= 1;
       }
     }
-    __syncthreads();
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
 }
 
@@ -300,7 +312,7 @@ inline int launch_shift_sum(const bf16* Z, bf16* out, long long rows, int Hz, in
   const long long nwork = rows * ((Ho + band - 1) / band);
   long long grid = nwork < (long long)num_sms() * 8 ? nwork : (long long)num_sms() * 8;
   if (grid < 1) grid = 1;
-  const size_t smem = (size_t)Wz * 33 * sizeof(uint32_t);
+  const size_t smem = (size_t)2 * Wz * 33 * sizeof(uint32_t);          // two line buffers
   MRA_REQUIRE(smem <= 48 * 1024, "shift_sum: Z line does not fit shared memory (Wz = %d)", Wz);
   shift_sum_kernel<bf16, bf16><<<(unsigned)grid, 256, smem, st>>>(Z, out, rows, Hz, Wz, Ho, Wo, k, sgn, off, bias, act, slope, band);
   MRA_LAUNCH_CHECK();
