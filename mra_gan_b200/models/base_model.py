@@ -49,6 +49,8 @@ class BaseModel:
             self.schedulers = [networks3D.get_scheduler(o, opt) for o in self.optimizers]
         if not self.isTrain or opt.continue_train:
             self.load_networks(opt.which_epoch)
+            if self.isTrain:
+                self.load_optimizers(opt.which_epoch)      # no-op for checkpoints written by the reference
         self.print_networks(opt.verbose)
 
     def eval(self):
@@ -85,6 +87,67 @@ class BaseModel:
             path = os.path.join(self.save_dir, "%s_net_%s.pth" % (which_epoch, n))
             sd = OrderedDict((k, v.detach().to("cpu").contiguous()) for k, v in net.state_dict().items())
             torch.save(sd, path)
+        if self.isTrain:
+            self.save_optimizers(which_epoch)              # extra file; the reference-format files are unchanged
+
+    # the reference's resume drops the Adam moments (base_model.py:89-148 saves the networks
+    # only).  These two write / restore them next to the reference-format files, keyed by the parameters'
+    # state_dict names and stored in torch's logical layout, so the extra file is independent of the packed memory
+    # layout of this build.  Rank 0 saves under data parallelism (every rank holds the same averaged state).
+    def save_optimizers(self, which_epoch):
+        if not getattr(self, "optimizers", None):
+            return None
+        os.makedirs(self.save_dir, exist_ok=True)
+        names = {}
+        for n, net in self._nets():
+            for k, p in net.named_parameters():
+                names[p] = "%s.%s" % (n, k)
+        out = OrderedDict()
+        for oi, opt in enumerate(self.optimizers):
+            entry = OrderedDict(param_groups=[{k: v for k, v in g.items() if k != "params"} for g in opt.param_groups],
+                                state=OrderedDict())
+            for p, st in opt.state.items():
+                if p in names and st:
+                    entry["state"][names[p]] = OrderedDict(
+                        (k, (v.detach().to("cpu").contiguous() if torch.is_tensor(v) else v)) for k, v in st.items())
+            out["optimizer_%d" % oi] = entry
+        path = os.path.join(self.save_dir, "%s_optim.pth" % which_epoch)
+        torch.save(out, path)
+        return path
+
+    def load_optimizers(self, which_epoch):
+        """Restore the Adam moments and step counters written by save_optimizers(); returns False when the checkpoint
+        has none (a checkpoint of the reference), in which case training resumes like the reference does."""
+        path = os.path.join(self.save_dir, "%s_optim.pth" % which_epoch)
+        if not getattr(self, "optimizers", None) or not os.path.exists(path):
+            return False
+        blob = torch.load(path, map_location="cpu")
+        params = {}
+        for n, net in self._nets():
+            for k, p in net.named_parameters():
+                params["%s.%s" % (n, k)] = p
+        for oi, opt in enumerate(self.optimizers):
+            entry = blob.get("optimizer_%d" % oi)
+            if entry is None:
+                continue
+            for g, saved in zip(opt.param_groups, entry["param_groups"]):
+                for k, v in saved.items():
+                    if k != "lr":                      # the schedulers own the learning rate (setup() re-creates them)
+                        g[k] = v
+            for name, st in entry["state"].items():
+                p = params.get(name)
+                if p is None:
+                    continue
+                dst = opt.state[p]
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        t = torch.empty_like(p, memory_format=torch.preserve_format) if v.shape == p.shape else \
+                            torch.empty(v.shape, dtype=v.dtype, device=p.device)
+                        t.copy_(v.to(p.device))        # logical-layout copy into the parameter's (packed) strides
+                        dst[k] = t
+                    else:
+                        dst[k] = v
+        return True
 
     def load_networks(self, which_epoch):
         for n, net in self._nets():
