@@ -118,6 +118,10 @@ int mra_act_fwd(const void* x, void* y, int64_t numel, int act, float slope, int
                 mra_stream_t stream);
 int mra_act_bwd(const void* dy, const void* y, void* dx, int64_t numel, int act, float slope,
                 int dtype, mra_stream_t stream);
+/* nn.Dropout(p) in training mode (models/networks3D.py:244-245, 332-333): y = x * keep / (1 - p) with the caller's
+ * keep mask (one byte per element, 0 / 1); pass scale = 1 / (1 - p).  The backward is the same call on the gradient. */
+int mra_mask_scale(const void* x, const unsigned char* keep, void* y, int64_t numel, float scale,
+                   int dtype, mra_stream_t stream);
 /* nn.ReplicationPad3d forward/backward on its own (models/networks3D.py:185,211 when the producer
  * is not a norm): y = pad(x); dx = fold_pad(gy). */
 int mra_reppad_fwd(const void* x, void* y, int n, int d, int h, int w, int c, int pad, int dtype,

@@ -53,6 +53,7 @@ _SIGNATURES = {
     "mra_inorm_act_pad_bwd": ([C.POINTER(NormDesc), _P, _P, _P, _P, _P, _P, _P, _P], C.c_int),
     "mra_act_fwd": ([_P, _P, _L, _I, _F, _I, _P], C.c_int),
     "mra_act_bwd": ([_P, _P, _P, _L, _I, _F, _I, _P], C.c_int),
+    "mra_mask_scale": ([_P, _P, _P, _L, _F, _I, _P], C.c_int),
     "mra_reppad_fwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "mra_reppad_bwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "mra_loss_fwd": ([_I, _P, _P, _F, _L, _I, _P, _P], C.c_int),

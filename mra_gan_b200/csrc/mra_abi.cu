@@ -246,6 +246,15 @@ int mra_act_bwd(const void* dy, const void* y, void* dx, int64_t numel, int act,
   return 0;
 }
 
+int mra_mask_scale(const void* x, const unsigned char* keep, void* y, int64_t numel, float scale, int dtype,
+                   mra_stream_t stream) {
+  if (numel <= 0) return 0;
+  MRA_REQUIRE(x && keep && y, "mra_mask_scale: null pointer");
+  DISPATCH_DTYPE(dtype, (mask_scale_kernel<T><<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>((const T*)x, keep, (T*)y, numel, scale)));
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+
 static mra_norm_desc pad_desc(int n, int d, int h, int w, int c, int pad, int dtype) {
   mra_norm_desc nd;
   memset(&nd, 0, sizeof(nd));

@@ -372,6 +372,15 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const T* __restrict__ dy, 
     dx[i] = from_f<T>(to_f(dy[i]) * act_grad_from_output(to_f(y[i]), act, slope));
 }
 
+// nn.Dropout (networks3D.py:244-245, 332-333): y = x * keep / (1 - p).  The keep mask (one byte per element) comes from
+// the caller's RNG; the same kernel is its own backward (dx = gy * keep / (1 - p)).
+template <typename T>
+__global__ void __launch_bounds__(256) mask_scale_kernel(const T* __restrict__ x, const unsigned char* __restrict__ keep,
+                                                          T* __restrict__ y, long long n, float scale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = from_f<T>(keep[i] ? to_f(x[i]) * scale : 0.f);
+}
+
 // ---- host-side launch helpers ----
 inline NormP make_norm_params(const mra_norm_desc& d, int vec) {
   NormP P;

@@ -125,6 +125,23 @@ class NormActPadFn(torch.autograd.Function):
         return dx, None, dres, None, None, None, None, None
 
 
+class DropoutFn(torch.autograd.Function):
+    """nn.Dropout(p) in training mode.  The keep mask is drawn from torch's generator of the tensor's device (the
+    reference's masks come from the same generator, in NCDHW order: the statistics agree, the bits cannot)."""
+
+    @staticmethod
+    def forward(ctx, x, p):
+        keep = torch.empty(x.shape, dtype=torch.uint8, device=x.device).bernoulli_(1.0 - p)
+        ctx.scale = 1.0 / (1.0 - p)
+        ctx.save_for_backward(keep)
+        return ops.impl().mask_scale(x.contiguous(), keep, ctx.scale)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (keep,) = ctx.saved_tensors
+        return ops.impl().mask_scale(gy.contiguous(), keep, ctx.scale), None
+
+
 class ActFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, act, slope):

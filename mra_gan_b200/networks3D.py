@@ -280,8 +280,10 @@ def compile_program(seq):
                 if peek_mod(j, (ReLU, LeakyReLU)):
                     act, slope = toks[j][1].act, toks[j][1].slope
                     j += 1
-                if peek_mod(j, Dropout):
-                    raise NotImplementedError("use_dropout is not implemented (the reference forces no_dropout)")
+                drop = None
+                if peek_mod(j, Dropout):                 # ResnetBlock: [.., norm, ReLU, Dropout(0.5), pad, conv, norm]
+                    drop = toks[j][1]
+                    j += 1
                 use_res = False
                 if j < n and toks[j][0] == "block_end":
                     use_res = True
@@ -290,9 +292,11 @@ def compile_program(seq):
                 jj, pad = j, 0
                 if jj < n and toks[jj][0] == "block_begin":
                     jj += 1
-                if peek_mod(jj, ReplicationPad3d):
-                    pad = toks[jj][1].padding
+                if peek_mod(jj, ReplicationPad3d) and drop is None:
+                    pad = toks[jj][1].padding            # (a dropout in between keeps the pad a separate instruction)
                 prog.append(("norm", norm, act, slope, pad, use_res))
+                if drop is not None:
+                    prog.append(("dropout", drop))
                 halo = pad
                 i = j
             else:
@@ -310,7 +314,8 @@ def compile_program(seq):
             prog.append(("norm", m, ACT_NONE, 0.0, 0, False))
             i += 1
         elif isinstance(m, Dropout):
-            raise NotImplementedError("use_dropout is not implemented (the reference forces no_dropout)")
+            prog.append(("dropout", m))
+            i += 1
         else:
             raise NotImplementedError("layer %s is not supported by the fused executor" % type(m).__name__)
     return prog
@@ -337,6 +342,9 @@ def run_program(prog, x):
             saved, saved_pad = x, ins[1]
         elif op == "act":
             x = MF.ActFn.apply(x, ins[1], ins[2])
+        elif op == "dropout":
+            if ins[1].training and ins[1].p > 0:
+                x = MF.DropoutFn.apply(x, ins[1].p)
         else:
             raise AssertionError(op)
     return x
@@ -639,7 +647,7 @@ class UnetSkipConnectionBlock(nn.Module):
             upconv = ConvTranspose3d(inner_nc * 2, outer_nc, kernel_size=4, stride=2, padding=1, bias=use_bias)
             model = [downrelu, downconv, downnorm, submodule, uprelu, upconv, upnorm]
             if use_dropout:
-                raise NotImplementedError("use_dropout is not implemented (the reference forces no_dropout)")
+                model = model + [Dropout(0.5)]          # networks3D.py:332-333
         self.model = nn.Sequential(*model)
 
     def run(self, x):
@@ -665,6 +673,8 @@ class UnetSkipConnectionBlock(nn.Module):
             u = MF.ActFn.apply(u, ACT_RELU, 0.0)
             u, st = MF.ConvFn.apply(u, m[5].weight, m[5].bias, m[5], ACT_NONE, 0.0, True, False)
             u = MF.NormActPadFn.apply(u, st, None, m[6], ACT_NONE, 0.0, 0, -1)
+            if len(m) > 7 and m[7].training and m[7].p > 0:
+                u = MF.DropoutFn.apply(u, m[7].p)
         return torch.cat([xs, u], 4)
 
     def forward(self, x):

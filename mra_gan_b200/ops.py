@@ -231,6 +231,14 @@ class CudaImpl:
                    "mra_act_bwd")
         return dx
 
+    def mask_scale(self, x, keep, scale):
+        """y = x * keep * scale (dropout forward, and its own backward on the gradient); keep: uint8 0 / 1."""
+        self._need(x, keep)
+        y = torch.empty_like(x)
+        _lib.check(self.L.mra_mask_scale(_ptr(x), _ptr(keep), _ptr(y), x.numel(), float(scale), _dt(x), self._stream()),
+                   "mra_mask_scale")
+        return y
+
     def reppad_fwd(self, x, pad):
         self._need(x)
         n, dd, hh, ww, c = x.shape

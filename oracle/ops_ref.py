@@ -185,6 +185,9 @@ class RefImpl:
     def act_bwd(self, dy, y, act, slope=0.2):
         return (self._c(dy) * _act_grad_from_output(self._c(y), act, slope)).to(dy.dtype)
 
+    def mask_scale(self, x, keep, scale):
+        return (self._c(x) * keep.to(self.cd) * scale).to(x.dtype)
+
     def reppad_fwd(self, x, pad):
         return to_ndhwc(F.pad(to_ncdhw(x), (pad,) * 6, mode="replicate"))
 

@@ -227,3 +227,46 @@ def test_no_cpu_fallback_in_product_path():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             ops.impl()
+
+
+def test_dropout_option_builds_runs_and_matches_reference_keys():
+    """use_dropout=True: nn.Dropout(0.5) inside the ResNet blocks / inner UNet blocks
+    (networks3D.py:244-245, 332-333).  Same state_dict keys as the reference; stochastic in train mode with the
+    1/(1-p) scaling and a matching gradient mask, identity in eval mode."""
+    import torch
+    from mra_gan_b200 import functional as MF
+    from mra_gan_b200 import networks3D as N3
+    from mra_gan_b200 import ops
+    from oracle import ops_ref as R
+    prev = ops.set_impl(R.RefImpl(torch.float32))
+    N3.set_default_compute_dtype(torch.float32)
+    try:
+        from oracle.ref_import import import_reference, reference_available
+        # the UNet only gets dropout in its (num_downs - 5) innermost ngf*8 blocks (networks3D.py:281-284): 6 downs, 64^3
+        builders = (("resnet_6blocks", 32, lambda M: M.define_G(1, 1, 4, "resnet_6blocks", "instance", True, "normal", 0.02, [])),
+                    ("unet6", 64, lambda M: M.UnetGenerator(1, 1, 6, 4, norm_layer=M.get_norm_layer("instance"), use_dropout=True)))
+        for name, size, build in builders:
+            torch.manual_seed(0)
+            net = build(N3)
+            keys = list(net.state_dict().keys())
+            if reference_available():                      # the build container; the GPU box has no /root/reference
+                assert keys == list(build(import_reference()[0]).state_dict().keys())
+            x = torch.randn(1, 1, size, size, size)
+            net.train()
+            torch.manual_seed(1); y1 = net(x)
+            torch.manual_seed(2); y2 = net(x)
+            assert torch.isfinite(y1).all() and not torch.allclose(y1, y2)
+            y1.square().mean().backward()
+            assert all(torch.isfinite(p.grad).all() for p in net.parameters() if p.grad is not None)
+        # the op itself: scaling, mask reuse in the backward pass
+        x = torch.randn(2, 4, 4, 4, 8, requires_grad=True)
+        torch.manual_seed(3)
+        y = MF.DropoutFn.apply(x, 0.5)
+        kept = y != 0
+        assert 0.3 < kept.float().mean() < 0.7
+        assert torch.allclose(y[kept], 2 * x.detach()[kept])
+        y.sum().backward()
+        assert torch.equal(x.grad != 0, kept) and torch.allclose(x.grad[kept], torch.full_like(x.grad[kept], 2.0))
+    finally:
+        ops.set_impl(prev)
+        N3.set_default_compute_dtype(torch.bfloat16)

@@ -218,6 +218,26 @@ def test_pad_act_standalone(dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_dropout_mask_scale(dtype):
+    """mra_mask_scale (nn.Dropout in training mode): exact against the oracle for a given keep mask, and through
+    functional.DropoutFn: 1/(1-p) scaling, the backward reuses the forward's mask."""
+    from mra_gan_b200 import functional as MF
+    I, ref = ops.impl(), R.RefImpl(torch.float64)
+    gen = torch.Generator().manual_seed(4)
+    x = torch.randn((2, 5, 6, 7, 24), generator=gen).to(dtype)
+    keep = (torch.rand(x.shape, generator=gen) > 0.5).to(torch.uint8)
+    y = I.mask_scale(x.cuda(), keep.cuda(), 2.0)
+    assert torch.equal(y.cpu(), ref.mask_scale(x, keep, 2.0))
+    xd = x.cuda().requires_grad_(True)
+    z = MF.DropoutFn.apply(xd, 0.5)
+    kept = z != 0
+    assert 0.4 < float(kept.float().mean()) < 0.6
+    assert torch.equal(z[kept], (2.0 * xd.detach().float()[kept]).to(dtype))
+    z.float().sum().backward()
+    assert torch.equal(xd.grad != 0, kept)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 def test_losses(dtype):
     I, ref = ops.impl(), R.RefImpl(torch.float64)
     gen = torch.Generator().manual_seed(4)
