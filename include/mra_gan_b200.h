@@ -93,7 +93,10 @@ typedef struct mra_norm_desc {
   int32_t res_pad;                   /* residual tensor's own halo; -1 = no residual */
   int32_t dtype;
   float   eps, momentum;
-  int32_t use_running;               /* eval mode: normalise with running_mean / running_var */
+  int32_t use_running;               /* 0: statistics from `stats` (training); 1: eval mode, normalise with
+                                      * running_mean / running_var; 2: mean / rstd ([n][c]) are INPUTS filled by the
+                                      * caller -- batch norm with its affine folded in: rstd' = gamma rstd_b,
+                                      * mean' = mean_b - beta / rstd' (models/networks3D.py:15-24, norm='batch') */
 } mra_norm_desc;
 
 /* stats[n][c][2] (double) = {sum x, sum x^2} over D*H*W  -- the exact pass, used when the producing
@@ -111,6 +114,15 @@ int mra_inorm_act_pad_fwd(const mra_norm_desc* d, const void* x, const double* s
 int mra_inorm_act_pad_bwd(const mra_norm_desc* d, const void* gy, const void* x, const float* mean,
                           const float* rstd, void* dx, void* dres, double* sums,
                           mra_stream_t stream);
+
+/* The two passes of mra_inorm_act_pad_bwd on their own.  Batch norm reduces `sums` over the batch and folds the affine
+ * between them: the apply pass computes dx = rstd (dy - sums[.][0]/V - xhat sums[.][1]/V) from whatever the caller
+ * left in `sums`. */
+int mra_inorm_act_pad_bwd_stats(const mra_norm_desc* d, const void* gy, const void* x, const float* mean,
+                                const float* rstd, double* sums, mra_stream_t stream);
+int mra_inorm_act_pad_bwd_apply(const mra_norm_desc* d, const void* gy, const void* x, const float* mean,
+                                const float* rstd, const double* sums, void* dx, void* dres,
+                                mra_stream_t stream);
 
 /* Stand-alone activations (UNet pre-activations :306,308; PatchGAN layer 0 :393; Tanh :213,316;
  * Sigmoid :420).  fwd: y = act(x).  bwd: dx = dy * act'(.) evaluated from the OUTPUT y. */

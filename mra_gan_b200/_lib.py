@@ -51,6 +51,8 @@ _SIGNATURES = {
     "mra_inorm_stats": ([C.POINTER(NormDesc), _P, _P, _P], C.c_int),
     "mra_inorm_act_pad_fwd": ([C.POINTER(NormDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P], C.c_int),
     "mra_inorm_act_pad_bwd": ([C.POINTER(NormDesc), _P, _P, _P, _P, _P, _P, _P, _P], C.c_int),
+    "mra_inorm_act_pad_bwd_stats": ([C.POINTER(NormDesc), _P, _P, _P, _P, _P, _P], C.c_int),
+    "mra_inorm_act_pad_bwd_apply": ([C.POINTER(NormDesc), _P, _P, _P, _P, _P, _P, _P, _P], C.c_int),
     "mra_act_fwd": ([_P, _P, _L, _I, _F, _I, _P], C.c_int),
     "mra_act_bwd": ([_P, _P, _P, _L, _I, _F, _I, _P], C.c_int),
     "mra_mask_scale": ([_P, _P, _P, _L, _F, _I, _P], C.c_int),

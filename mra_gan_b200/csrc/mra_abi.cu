@@ -218,7 +218,8 @@ int mra_inorm_act_pad_fwd(const mra_norm_desc* d, const void* x, const double* s
   MRA_REQUIRE(d->use_running || (long long)d->d * d->h * d->w > 1,
               "InstanceNorm needs more than 1 spatial element per channel in training mode");
   MRA_REQUIRE((d->res_pad >= 0) == (residual != nullptr), "residual pointer / res_pad mismatch");
-  MRA_REQUIRE(!d->use_running || (running_mean && running_var), "eval-mode norm needs running stats");
+  MRA_REQUIRE(d->use_running != 1 || (running_mean && running_var), "eval-mode norm needs running stats");
+  MRA_REQUIRE(d->use_running >= 0 && d->use_running <= 2, "bad use_running mode %d", (int)d->use_running);
   DISPATCH_NORM(d, return (ns::norm_fwd_launch_v2<T, VEC>(*d, x, stats, residual, y, mean, rstd, running_mean, running_var,
                                                    (cudaStream_t)stream)));
   return 0;
@@ -229,6 +230,22 @@ int mra_inorm_act_pad_bwd(const mra_norm_desc* d, const void* gy, const void* x,
   if (int rc = check_norm(d)) return rc;
   MRA_REQUIRE(!dres || d->res_pad >= 0, "dres requested without a residual");
   DISPATCH_NORM(d, return (ns::norm_bwd_launch_v2<T, VEC>(*d, gy, x, mean, rstd, dx, dres, sums, (cudaStream_t)stream)));
+  return 0;
+}
+
+int mra_inorm_act_pad_bwd_stats(const mra_norm_desc* d, const void* gy, const void* x, const float* mean, const float* rstd,
+                                double* sums, mra_stream_t stream) {
+  if (int rc = check_norm(d)) return rc;
+  DISPATCH_NORM(d, return (ns::norm_bwd_launch_v2<T, VEC>(*d, gy, x, mean, rstd, nullptr, nullptr, sums, (cudaStream_t)stream, 1)));
+  return 0;
+}
+
+int mra_inorm_act_pad_bwd_apply(const mra_norm_desc* d, const void* gy, const void* x, const float* mean, const float* rstd,
+                                const double* sums, void* dx, void* dres, mra_stream_t stream) {
+  if (int rc = check_norm(d)) return rc;
+  MRA_REQUIRE(!dres || d->res_pad >= 0, "dres requested without a residual");
+  DISPATCH_NORM(d, return (ns::norm_bwd_launch_v2<T, VEC>(*d, gy, x, mean, rstd, dx, dres, const_cast<double*>(sums),
+                                                         (cudaStream_t)stream, 2)));
   return 0;
 }
 

@@ -25,7 +25,7 @@ struct NormP {
   int pad, act; float slope;
   int res_pad;            // -1: none
   float eps, momentum;
-  int use_running;
+  int use_running;        // 0: statistics from `stats`; 1: running statistics (eval); 2: mean / rstd given by the caller
   long long V;            // D*H*W
   int G;                  // channel groups = C / VEC
   int Gs;                 // groups per slice (<= 256)
@@ -87,7 +87,7 @@ __global__ void inorm_finalize_kernel(const double* __restrict__ stats, float* _
                                       float* running_var, const NormP P) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= P.C) return;
-  if (P.use_running) {
+  if (P.use_running == 1) {
     const float m = running_mean[c], r = 1.0f / sqrtf(running_var[c] + P.eps);
     for (int n = 0; n < P.N; ++n) { mean[n * P.C + c] = m; rstd[n * P.C + c] = r; }
     return;
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(256) inorm_bwd_kernel(const T* __restrict__ gy
   for (int c = threadIdx.x; c < P.C; c += blockDim.x) {
     smf[c] = mean[n * P.C + c];
     smf[P.C + c] = rstd[n * P.C + c];
-    if (P.use_running) { smf[2 * P.C + c] = 0.f; smf[3 * P.C + c] = 0.f; }
+    if (P.use_running == 1) { smf[2 * P.C + c] = 0.f; smf[3 * P.C + c] = 0.f; }
     else {
       smf[2 * P.C + c] = (float)(sums[((long long)n * P.C + c) * 2 + 0] / (double)P.V);
       smf[3 * P.C + c] = (float)(sums[((long long)n * P.C + c) * 2 + 1] / (double)P.V);
@@ -421,8 +421,10 @@ template <typename T, int VEC>
 int norm_fwd_launch(const mra_norm_desc& d, const void* x, const double* stats, const void* res, void* y,
                     float* mean, float* rstd, float* rm, float* rv, cudaStream_t st) {
   NormP P = make_norm_params(d, VEC);
-  inorm_finalize_kernel<<<(d.c + 127) / 128, 128, 0, st>>>(stats, mean, rstd, rm, rv, P);
-  MRA_LAUNCH_CHECK();
+  if (d.use_running != 2) {                           // 2: the caller filled mean / rstd (batch norm with folded affine)
+    inorm_finalize_kernel<<<(d.c + 127) / 128, 128, 0, st>>>(stats, mean, rstd, rm, rv, P);
+    MRA_LAUNCH_CHECK();
+  }
   const long long items = (long long)(d.d + 2 * d.pad) * (d.h + 2 * d.pad) * (d.w + 2 * d.pad) * P.G;
   dim3 grid(grid_for(items, 256 * 4, (16 + d.n - 1) / d.n), d.n);
   inorm_fwd_kernel<T, VEC><<<grid, 256, 2 * d.c * sizeof(float), st>>>(
@@ -433,9 +435,9 @@ int norm_fwd_launch(const mra_norm_desc& d, const void* x, const double* stats, 
 
 template <typename T, int VEC>
 int norm_bwd_launch(const mra_norm_desc& d, const void* gy, const void* x, const float* mean,
-                    const float* rstd, void* dx, void* dres, double* sums, cudaStream_t st) {
+                    const float* rstd, void* dx, void* dres, double* sums, cudaStream_t st, int phases = 3) {
   NormP P = make_norm_params(d, VEC);
-  if (!d.use_running) {
+  if (d.use_running != 1 && (phases & 1)) {
     MRA_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * d.n * d.c, st));
     long long bx = ((long long)num_sms() * 4 + d.n - 1) / d.n;
     const long long maxbx = (P.V + P.rows_pb - 1) / P.rows_pb;
@@ -446,6 +448,7 @@ int norm_bwd_launch(const mra_norm_desc& d, const void* gy, const void* x, const
                                                          reinterpret_cast<const T*>(x), mean, rstd, sums, P);
     MRA_LAUNCH_CHECK();
   }
+  if (!(phases & 2)) return 0;
   const int rp = dres ? d.res_pad : 0;
   const long long items = (long long)(d.d + 2 * rp) * (d.h + 2 * rp) * (d.w + 2 * rp) * P.G;
   dim3 grid(grid_for(items, 256 * 4, (16 + d.n - 1) / d.n), d.n);

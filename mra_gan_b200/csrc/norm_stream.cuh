@@ -201,13 +201,14 @@ __global__ void __launch_bounds__(CONS + 32, 1) inorm_fwd_stream_kernel(const T*
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = cg * 8 + j;
-      if (P.use_running) { m8[j] = running_mean[c]; r8[j] = 1.0f / sqrtf(running_var[c] + P.eps); }
+      if (P.use_running == 1) { m8[j] = running_mean[c]; r8[j] = 1.0f / sqrtf(running_var[c] + P.eps); }
+      else if (P.use_running == 2) { m8[j] = mean[n * P.C + c]; r8[j] = rstd[n * P.C + c]; }     // given by the caller
       else mean_rstd_from_stats(stats + ((long long)n * P.C + c) * 2, P.V, P.eps, m8[j], r8[j]);
     }
-    if (blockIdx.x == 0 && wl == 0) {
+    if (blockIdx.x == 0 && wl == 0 && P.use_running != 2) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) { mean[n * P.C + cg * 8 + j] = m8[j]; rstd[n * P.C + cg * 8 + j] = r8[j]; }
-      if (n == 0 && !P.use_running && running_mean) {
+      if (n == 0 && P.use_running == 0 && running_mean) {
         for (int j = 0; j < 8; ++j) {
           const int c = cg * 8 + j;
           double msum = 0.0, vsum = 0.0;
@@ -423,7 +424,7 @@ __global__ void __launch_bounds__(CONS + 32, 1) inorm_bwd_stream_kernel(const T*
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float m[4] = {0.f, 0.f, 0.f, 0.f};
-    if (!P.use_running) {
+    if (P.use_running != 1) {
       const double* sp = sums + ((long long)n * P.C + cg * 8 + 2 * i) * 2;
       const double inv = 1.0 / (double)P.V;
 #pragma unroll
@@ -573,19 +574,20 @@ int norm_fwd_launch_v2(const mra_norm_desc& d, const void* x, const double* stat
 
 template <typename T, int CONS, int U>
 int norm_bwd_stream_launch(const mra_norm_desc& d, const StreamP& S, const void* gy, const void* x, const float* mean,
-                           const float* rstd, void* dx, void* dres, double* sums, cudaStream_t st) {
+                           const float* rstd, void* dx, void* dres, double* sums, cudaStream_t st, int phases) {
   static bool attr = false;
   if (!attr) {
     if (int rc = stream_attr(inorm_bwd_stats_stream_kernel<T, CONS, U>)) return rc;
     if (int rc = stream_attr(inorm_bwd_stream_kernel<T, CONS, U>)) return rc;
     attr = true;
   }
-  if (!d.use_running) {
+  if (d.use_running != 1 && (phases & 1)) {
     MRA_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * d.n * d.c, st));
     inorm_bwd_stats_stream_kernel<T, CONS, U><<<stream_grid(S), CONS + 32, stream_smem(S), st>>>(
         reinterpret_cast<const T*>(gy), reinterpret_cast<const T*>(x), mean, rstd, sums, S);
     MRA_LAUNCH_CHECK();
   }
+  if (!(phases & 2)) return 0;
   inorm_bwd_stream_kernel<T, CONS, U><<<stream_grid(S), CONS + 32, stream_smem(S), st>>>(
       reinterpret_cast<const T*>(gy), reinterpret_cast<const T*>(x), mean, rstd, sums, reinterpret_cast<T*>(dx),
       reinterpret_cast<T*>(dres), S);
@@ -595,22 +597,23 @@ int norm_bwd_stream_launch(const mra_norm_desc& d, const StreamP& S, const void*
 
 template <typename T, int CONS>
 int norm_bwd_stream_pick(const mra_norm_desc& d, const StreamP& S, const void* gy, const void* x, const float* mean,
-                         const float* rstd, void* dx, void* dres, double* sums, cudaStream_t st) {
+                         const float* rstd, void* dx, void* dres, double* sums, cudaStream_t st, int phases) {
   const int wpp = CONS >> S.lgG;
   const int u = (S.P.W + wpp - 1) / wpp;
-  if (u <= 1) return norm_bwd_stream_launch<T, CONS, 1>(d, S, gy, x, mean, rstd, dx, dres, sums, st);
-  if (u <= 2) return norm_bwd_stream_launch<T, CONS, 2>(d, S, gy, x, mean, rstd, dx, dres, sums, st);
-  return norm_bwd_stream_launch<T, CONS, 4>(d, S, gy, x, mean, rstd, dx, dres, sums, st);
+  if (u <= 1) return norm_bwd_stream_launch<T, CONS, 1>(d, S, gy, x, mean, rstd, dx, dres, sums, st, phases);
+  if (u <= 2) return norm_bwd_stream_launch<T, CONS, 2>(d, S, gy, x, mean, rstd, dx, dres, sums, st, phases);
+  return norm_bwd_stream_launch<T, CONS, 4>(d, S, gy, x, mean, rstd, dx, dres, sums, st, phases);
 }
 
 template <typename T, int VEC>
 int norm_bwd_launch_v2(const mra_norm_desc& d, const void* gy, const void* x, const float* mean, const float* rstd,
-                       void* dx, void* dres, double* sums, cudaStream_t st) {
+                       void* dx, void* dres, double* sums, cudaStream_t st, int phases = 3) {
   StreamP S;
-  // a residual gradient keeps the tensor's own geometry (its halo is written row by row)
-  if (VEC != 8 || !stream_plan<T>(d, VEC, true, dres != nullptr, S))
-    return norm_bwd_launch<T, VEC>(d, gy, x, mean, rstd, dx, dres, sums, st);
-  return norm_bwd_stream_pick<T, kConsumers>(d, S, gy, x, mean, rstd, dx, dres, sums, st);
+  // a residual gradient keeps the tensor's own geometry (its halo is written row by row); `want_res` keeps both
+  // phases of a split call on the same row geometry
+  if (VEC != 8 || !stream_plan<T>(d, VEC, true, dres != nullptr || d.res_pad >= 0, S))
+    return norm_bwd_launch<T, VEC>(d, gy, x, mean, rstd, dx, dres, sums, st, phases);
+  return norm_bwd_stream_pick<T, kConsumers>(d, S, gy, x, mean, rstd, dx, dres, sums, st, phases);
 }
 
 }  // namespace ns

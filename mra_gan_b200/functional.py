@@ -125,6 +125,77 @@ class NormActPadFn(torch.autograd.Function):
         return dx, None, dres, None, None, None, None, None
 
 
+class BatchNormActPadFn(torch.autograd.Function):
+    """BatchNorm3d(affine) -> ReLU/LeakyReLU -> (+ residual) -> ReplicationPad3d on the InstanceNorm kernels.
+
+    Batch statistics = the conv epilogue's per-sample {sum, sum of squares} added over the batch.  With
+    rstd' = gamma * rstd_b and mean' = mean_b - beta / rstd' the kernels' (x - mean') * rstd' IS gamma * xhat + beta, so the
+    forward is the same single pass.  Backward: the kernels' statistics pass yields sum(dy) and sum(dy * z)
+    (z = gamma xhat + beta) per sample; added over the batch they give dbeta and dgamma, and
+    dx = rstd' (dy - m1' - z m2') with m1' = M1 - beta M2 / gamma, m2' = M2 / gamma (M1, M2 the batch means of dy and
+    dy * xhat) is exactly what the apply pass computes from the sums it is handed.  The per-channel algebra in between
+    is a handful of [C]-sized torch operations."""
+
+    @staticmethod
+    def forward(ctx, x, stats, residual, weight, bias, mod, act, slope, pad, res_pad):
+        I = ops.impl()
+        n, d, h, w, c = x.shape
+        nv = float(n * d * h * w)
+        training = mod.training or not mod.track_running_stats
+        if training:
+            if stats is None:
+                stats = I.inorm_stats(x)
+            S = stats.sum(0)                                           # [C][2] fp64
+            mean_b = S[:, 0] / nv
+            var_b = (S[:, 1] / nv - mean_b * mean_b).clamp_min(0.0)
+            if mod.track_running_stats:
+                with torch.no_grad():
+                    mom = mod.momentum
+                    mod.running_mean.mul_(1 - mom).add_(mom * mean_b.to(mod.running_mean.dtype))
+                    mod.running_var.mul_(1 - mom).add_(mom * (var_b * (nv / max(nv - 1.0, 1.0))).to(mod.running_var.dtype))
+                    mod.num_batches_tracked += 1
+        else:
+            mean_b, var_b = mod.running_mean.double(), mod.running_var.double()
+        rstd_b = 1.0 / torch.sqrt(var_b + mod.eps)
+        g = weight.detach().double() if weight is not None else torch.ones_like(rstd_b)
+        b = bias.detach().double() if bias is not None else torch.zeros_like(rstd_b)
+        g = torch.where(g == 0, torch.full_like(g, 1e-12), g)          # keeps the folded form finite
+        r_f = g * rstd_b
+        m_f = mean_b - b / r_f
+        mean_in = m_f.float().unsqueeze(0).expand(n, c).contiguous()
+        rstd_in = r_f.float().unsqueeze(0).expand(n, c).contiguous()
+        rp = res_pad if residual is not None else -1
+        y, _, _ = I.inorm_fwd(x, stats, residual, pad, act, slope, rp, mod.eps, mod.momentum, given=(mean_in, rstd_in))
+        ctx.cfg = (act, slope, pad, rp, training, nv)
+        ctx.save_for_backward(x, mean_in, rstd_in, g, b)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        I = ops.impl()
+        x, mean_in, rstd_in, g, b = ctx.saved_tensors
+        act, slope, pad, res_pad, training, nv = ctx.cfg
+        n, d, h, w, c = x.shape
+        v = float(d * h * w)
+        want_res = res_pad >= 0 and ctx.needs_input_grad[2]
+        rp = res_pad if want_res else -1
+        gy = gy.contiguous()
+        sums = I.inorm_bwd_stats(gy, x, mean_in, rstd_in, pad, act, slope, rp)
+        T = sums.sum(0)                                                # [C][2]: sum dy, sum dy * z
+        dbeta = T[:, 0]
+        dgamma = (T[:, 1] - b * T[:, 0]) / g
+        if training:
+            M1, M2 = dbeta / nv, dgamma / nv
+            m1, m2 = M1 - b * M2 / g, M2 / g
+        else:
+            m1, m2 = torch.zeros_like(dbeta), torch.zeros_like(dbeta)
+        sums_in = (torch.stack([m1, m2], -1) * v).unsqueeze(0).expand(n, c, 2).contiguous()
+        dx, dres = I.inorm_bwd_apply(gy, x, mean_in, rstd_in, sums_in, pad, act, slope, rp)
+        dw = dgamma.float() if ctx.needs_input_grad[3] else None
+        db = dbeta.float() if ctx.needs_input_grad[4] else None
+        return dx, None, dres, dw, db, None, None, None, None, None
+
+
 class DropoutFn(torch.autograd.Function):
     """nn.Dropout(p) in training mode.  The keep mask is drawn from torch's generator of the tensor's device (the
     reference's masks come from the same generator, in NCDHW order: the statistics agree, the bits cannot)."""

@@ -192,6 +192,43 @@ class InstanceNorm3d(nn.Module):
             self.num_features, self.eps, self.momentum, self.track_running_stats)
 
 
+class BatchNorm3d(nn.Module):
+    """nn.BatchNorm3d(affine=True, track_running_stats=True) state (networks3D.py:17, norm='batch').  The arithmetic
+    runs on the InstanceNorm kernels: batch statistics are the per-sample statistics summed over the batch, and the
+    affine is folded into the (mean, rstd) pair the kernels are given (functional.BatchNormActPadFn)."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True):
+        super().__init__()
+        self.num_features, self.eps, self.momentum = num_features, eps, momentum
+        self.affine, self.track_running_stats = affine, track_running_stats
+        if affine:
+            self.weight = nn.Parameter(torch.ones(num_features))
+            self.bias = nn.Parameter(torch.zeros(num_features))
+        else:
+            self.register_parameter("weight", None)
+            self.register_parameter("bias", None)
+        if track_running_stats:
+            self.register_buffer("running_mean", torch.zeros(num_features))
+            self.register_buffer("running_var", torch.ones(num_features))
+            self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+        else:
+            self.running_mean = self.running_var = self.num_batches_tracked = None
+
+    def extra_repr(self):
+        return "%d, eps=%g, momentum=%g, affine=%s, track_running_stats=%s" % (
+            self.num_features, self.eps, self.momentum, self.affine, self.track_running_stats)
+
+
+_NORMS = (InstanceNorm3d, BatchNorm3d)
+
+
+def apply_norm(x, stats, res, m, act, slope, pad, res_pad):
+    """One fused norm instruction (normalise -> activation -> + residual -> replication pad) for either norm type."""
+    if isinstance(m, BatchNorm3d):
+        return MF.BatchNormActPadFn.apply(x, stats, res, m.weight, m.bias, m, act, slope, pad, res_pad)
+    return MF.NormActPadFn.apply(x, stats, res, m, act, slope, pad, res_pad)
+
+
 class ReplicationPad3d(nn.Module):
     def __init__(self, padding):
         super().__init__()
@@ -272,7 +309,7 @@ def compile_program(seq):
             i += 1
         elif isinstance(m, _ConvNd):
             j = i + 1
-            if peek_mod(j, InstanceNorm3d):
+            if peek_mod(j, _NORMS):
                 norm = toks[j][1]
                 prog.append(("conv", m, ACT_NONE, 0.0, True))
                 j += 1
@@ -310,7 +347,7 @@ def compile_program(seq):
         elif isinstance(m, _ACTS):
             prog.append(("act", m.act, m.slope))
             i += 1
-        elif isinstance(m, InstanceNorm3d):
+        elif isinstance(m, _NORMS):
             prog.append(("norm", m, ACT_NONE, 0.0, 0, False))
             i += 1
         elif isinstance(m, Dropout):
@@ -334,7 +371,7 @@ def run_program(prog, x):
         elif op == "norm":
             _, m, act, slope, pad, use_res = ins
             res = saved if use_res else None
-            x = MF.NormActPadFn.apply(x, stats, res, m, act, slope, pad, saved_pad)
+            x = apply_norm(x, stats, res, m, act, slope, pad, saved_pad)
             stats = None
         elif op == "pad":
             x = MF.RepPadFn.apply(x, ins[1])
@@ -381,7 +418,7 @@ class _FusedNet(nn.Module):
 ###############################################################################
 def get_norm_layer(norm_type='instance'):
     if norm_type == 'batch':
-        raise NotImplementedError('BatchNorm3d (norm=batch) is outside the hot path of this build (SURVEY.md 8f)')
+        norm_layer = functools.partial(BatchNorm3d, affine=True)
     elif norm_type == 'instance':
         norm_layer = functools.partial(InstanceNorm3d, affine=False, track_running_stats=True)
     elif norm_type == 'none':
@@ -428,6 +465,9 @@ def init_weights(net, init_type='normal', gain=0.02):
                 m.weight.copy_(w)
             if hasattr(m, 'bias') and m.bias is not None:
                 init.constant_(m.bias.data, 0.0)
+        elif classname.find('BatchNorm3d') != -1:
+            init.normal_(m.weight.data, 1.0, gain)
+            init.constant_(m.bias.data, 0.0)
 
     print('initialize network with %s' % init_type)
     net.apply(init_func)
@@ -665,14 +705,14 @@ class UnetSkipConnectionBlock(nn.Module):
             # the ReLU that follows has no norm in between: fuse it into the conv epilogue
             d, _ = MF.ConvFn.apply(xs, m[1].weight, m[1].bias, m[1], ACT_RELU, 0.0, False, True)
             u, st = MF.ConvFn.apply(d, m[3].weight, m[3].bias, m[3], ACT_NONE, 0.0, True, False)
-            u = MF.NormActPadFn.apply(u, st, None, m[4], ACT_NONE, 0.0, 0, -1)
+            u = apply_norm(u, st, None, m[4], ACT_NONE, 0.0, 0, -1)
         else:
             d, st = MF.ConvFn.apply(xs, m[1].weight, m[1].bias, m[1], ACT_NONE, 0.0, True, False)
-            d = MF.NormActPadFn.apply(d, st, None, m[2], ACT_NONE, 0.0, 0, -1)
+            d = apply_norm(d, st, None, m[2], ACT_NONE, 0.0, 0, -1)
             u = m[3].run(d)
             u = MF.ActFn.apply(u, ACT_RELU, 0.0)
             u, st = MF.ConvFn.apply(u, m[5].weight, m[5].bias, m[5], ACT_NONE, 0.0, True, False)
-            u = MF.NormActPadFn.apply(u, st, None, m[6], ACT_NONE, 0.0, 0, -1)
+            u = apply_norm(u, st, None, m[6], ACT_NONE, 0.0, 0, -1)
             if len(m) > 7 and m[7].training and m[7].p > 0:
                 u = MF.DropoutFn.apply(u, m[7].p)
         return torch.cat([xs, u], 4)

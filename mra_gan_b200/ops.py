@@ -191,12 +191,19 @@ class CudaImpl:
         return stats
 
     def inorm_fwd(self, x, stats, residual=None, pad=0, act=ACT_NONE, slope=0.2, res_pad=-1, eps=1e-5,
-                  momentum=0.1, running_mean=None, running_var=None, use_running=False):
+                  momentum=0.1, running_mean=None, running_var=None, use_running=False, given=None):
+        """``given=(mean, rstd)`` ([n][c] fp32): normalise with exactly these (use_running mode 2 of the C ABI; batch norm
+        passes its batch statistics with the affine folded in) instead of deriving them from ``stats``."""
         self._need(x, stats, residual, running_mean, running_var)
         n, dd, hh, ww, c = x.shape
         y = torch.empty((n, dd + 2 * pad, hh + 2 * pad, ww + 2 * pad, c), dtype=x.dtype, device=x.device)
-        mean = torch.empty((n, c), dtype=torch.float32, device=x.device)
-        rstd = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        if given is not None:
+            mean, rstd = given
+            self._need(mean, rstd)
+            use_running = 2
+        else:
+            mean = torch.empty((n, c), dtype=torch.float32, device=x.device)
+            rstd = torch.empty((n, c), dtype=torch.float32, device=x.device)
         d = self._norm_desc(x, pad, act, slope, res_pad if residual is not None else -1, eps, momentum, use_running)
         _lib.check(self.L.mra_inorm_act_pad_fwd(C.byref(d), _ptr(x), _ptr(stats), _ptr(residual), _ptr(y), _ptr(mean),
                                                 _ptr(rstd), _ptr(running_mean), _ptr(running_var), self._stream()),
@@ -216,6 +223,29 @@ class CudaImpl:
         d = self._norm_desc(x, pad, act, slope, res_pad, use_running=use_running)
         _lib.check(self.L.mra_inorm_act_pad_bwd(C.byref(d), _ptr(gy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(dx),
                                                 _ptr(dres), _ptr(sums), self._stream()), "mra_inorm_act_pad_bwd")
+        return dx, dres
+
+    def inorm_bwd_stats(self, gy, x, mean, rstd, pad=0, act=ACT_NONE, slope=0.2, res_pad=-1):
+        """First pass of inorm_bwd on its own: sums[n][c] = {sum dy, sum dy * xhat} (fp64), dy = act'(xhat) fold(gy)."""
+        self._need(gy, x, mean, rstd)
+        n, c = x.shape[0], x.shape[4]
+        sums = torch.empty((n, c, 2), dtype=torch.float64, device=x.device)
+        d = self._norm_desc(x, pad, act, slope, res_pad, use_running=2)
+        _lib.check(self.L.mra_inorm_act_pad_bwd_stats(C.byref(d), _ptr(gy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(sums),
+                                                      self._stream()), "mra_inorm_act_pad_bwd_stats")
+        return sums
+
+    def inorm_bwd_apply(self, gy, x, mean, rstd, sums, pad=0, act=ACT_NONE, slope=0.2, res_pad=-1):
+        """Second pass on its own: dx = rstd (dy - sums[.,0]/V - xhat sums[.,1]/V) with the caller's ``sums``."""
+        self._need(gy, x, mean, rstd, sums)
+        n, dd, hh, ww, c = x.shape
+        dx = torch.empty_like(x)
+        dres = None
+        if res_pad >= 0:
+            dres = torch.empty((n, dd + 2 * res_pad, hh + 2 * res_pad, ww + 2 * res_pad, c), dtype=x.dtype, device=x.device)
+        d = self._norm_desc(x, pad, act, slope, res_pad, use_running=2)
+        _lib.check(self.L.mra_inorm_act_pad_bwd_apply(C.byref(d), _ptr(gy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(sums),
+                                                      _ptr(dx), _ptr(dres), self._stream()), "mra_inorm_act_pad_bwd_apply")
         return dx, dres
 
     def act_fwd(self, x, act, slope=0.2):

@@ -137,10 +137,12 @@ class RefImpl:
         return torch.stack([xd.sum((1, 2, 3)), (xd * xd).sum((1, 2, 3))], -1)
 
     def inorm_fwd(self, x, stats, residual=None, pad=0, act=ACT_NONE, slope=0.2, res_pad=-1, eps=1e-5,
-                  momentum=0.1, running_mean=None, running_var=None, use_running=False):
+                  momentum=0.1, running_mean=None, running_var=None, use_running=False, given=None):
         n, d, h, w, c = x.shape
         V = d * h * w
-        if use_running:
+        if given is not None:
+            mean, rstd = given[0].to(self.cd), given[1].to(self.cd)
+        elif use_running:
             mean = running_mean.to(self.cd).expand(n, c).contiguous()
             rstd = (1.0 / torch.sqrt(running_var.to(self.cd) + eps)).expand(n, c).contiguous()
         else:
@@ -174,6 +176,29 @@ class RefImpl:
             m1 = dy.mean((1, 2, 3), keepdim=True)
             m2 = (dy * xh).mean((1, 2, 3), keepdim=True)
             dx = r * (dy - m1 - xh * m2)
+        dres = None
+        if res_pad >= 0:
+            dres = F.pad(g, (0, 0) + (res_pad,) * 6).contiguous().to(x.dtype)
+        return dx.contiguous().to(x.dtype), dres
+
+    def inorm_bwd_stats(self, gy, x, mean, rstd, pad=0, act=ACT_NONE, slope=0.2, res_pad=-1):
+        n, d, h, w, c = x.shape
+        g = to_ndhwc(_fold_pad(to_ncdhw(self._c(gy)), pad))
+        m, r = mean.to(self.cd).view(n, 1, 1, 1, c), rstd.to(self.cd).view(n, 1, 1, 1, c)
+        xh = (self._c(x) - m) * r
+        dy = g * _act_grad_from_output(xh, act, slope)
+        return torch.stack([dy.sum((1, 2, 3)), (dy * xh).sum((1, 2, 3))], -1).double()
+
+    def inorm_bwd_apply(self, gy, x, mean, rstd, sums, pad=0, act=ACT_NONE, slope=0.2, res_pad=-1):
+        n, d, h, w, c = x.shape
+        V = d * h * w
+        g = to_ndhwc(_fold_pad(to_ncdhw(self._c(gy)), pad))
+        m, r = mean.to(self.cd).view(n, 1, 1, 1, c), rstd.to(self.cd).view(n, 1, 1, 1, c)
+        xh = (self._c(x) - m) * r
+        dy = g * _act_grad_from_output(xh, act, slope)
+        m1 = (sums[..., 0] / V).to(self.cd).view(n, 1, 1, 1, c)
+        m2 = (sums[..., 1] / V).to(self.cd).view(n, 1, 1, 1, c)
+        dx = r * (dy - m1 - xh * m2)
         dres = None
         if res_pad >= 0:
             dres = F.pad(g, (0, 0) + (res_pad,) * 6).contiguous().to(x.dtype)

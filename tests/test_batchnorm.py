@@ -1,0 +1,123 @@
+"""norm='batch' (SURVEY.md 8f-1): BatchNorm3d(affine) on the InstanceNorm kernels (functional.BatchNormActPadFn).
+CPU: host algebra through the oracle ops against torch.nn.functional.batch_norm and against the reference's own
+networks; GPU: the same checks through the CUDA kernels."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from mra_gan_b200 import functional as MF
+from mra_gan_b200 import networks3D as N3
+from mra_gan_b200 import ops
+from mra_gan_b200.ops import ACT_LRELU, ACT_NONE, ACT_RELU
+from oracle import functional as OF
+from oracle import ops_ref as R
+
+
+def _fn_case(dev, dtype, act, pad, with_res, training, seed=0):
+    """BatchNormActPadFn vs F.batch_norm -> act -> (+ residual) -> replication pad in fp64."""
+    gen = torch.Generator().manual_seed(seed)
+    n, d, h, w, c = 3, 6, 5, 8, 16
+    x = (torch.randn((n, d, h, w, c), generator=gen) * 1.7 + 0.4)
+    gam = torch.randn(c, generator=gen) * 0.5 + 1.0
+    gam[3] = -0.7                                           # a negative scale must survive the folded form
+    bet = torch.randn(c, generator=gen) * 0.3
+    res = torch.randn((n, d + 2, h + 2, w + 2, c), generator=gen) if with_res else None
+    gy = torch.randn((n, d + 2 * pad, h + 2 * pad, w + 2 * pad, c), generator=gen)
+    rm0, rv0 = torch.randn(c, generator=gen) * 0.1, torch.rand(c, generator=gen) + 0.5
+    x, gy = x.to(dtype), gy.to(dtype)
+    if res is not None:
+        res = res.to(dtype)
+    # reference in fp64 on the values as stored
+    xr = x.double().permute(0, 4, 1, 2, 3).requires_grad_(True)
+    gr, br = gam.double().requires_grad_(True), bet.double().requires_grad_(True)
+    rm, rv = rm0.double().clone(), rv0.double().clone()
+    y = F.batch_norm(xr, rm, rv, gr, br, training=training, momentum=0.1, eps=1e-5)
+    y = F.relu(y) if act == ACT_RELU else (F.leaky_relu(y, 0.2) if act == ACT_LRELU else y)
+    rr = None
+    if res is not None:
+        rr = res.double().permute(0, 4, 1, 2, 3).requires_grad_(True)
+        y = y + rr[:, :, 1:-1, 1:-1, 1:-1]
+    if pad:
+        y = F.pad(y, (pad,) * 6, mode="replicate")
+    y.backward(gy.double().permute(0, 4, 1, 2, 3))
+    # ours
+    mod = N3.BatchNorm3d(c).to(dev)
+    mod.train(training)
+    with torch.no_grad():
+        mod.weight.copy_(gam); mod.bias.copy_(bet); mod.running_mean.copy_(rm0); mod.running_var.copy_(rv0)
+    xo = x.to(dev).requires_grad_(True)
+    ro = res.to(dev).requires_grad_(True) if res is not None else None
+    yo = MF.BatchNormActPadFn.apply(xo, None, ro, mod.weight, mod.bias, mod, act, 0.2, pad, 1)
+    yo.backward(gy.to(dev))
+    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    cl = lambda t: t.permute(0, 2, 3, 4, 1)
+    assert OF.rel_l2(yo.detach().cpu().double(), cl(y.detach())) < tol
+    assert OF.rel_l2(xo.grad.cpu().double(), cl(xr.grad)) < tol
+    assert OF.rel_l2(mod.weight.grad.cpu().double(), gr.grad) < tol
+    assert OF.rel_l2(mod.bias.grad.cpu().double(), br.grad) < tol
+    if res is not None:
+        assert OF.rel_l2(ro.grad.cpu().double(), cl(rr.grad)) < tol
+    if training:
+        assert OF.rel_l2(mod.running_mean.cpu().double(), rm) < 1e-5 and OF.rel_l2(mod.running_var.cpu().double(), rv) < 1e-5
+        assert int(mod.num_batches_tracked) == 1
+
+
+CASES = [(ACT_RELU, 1, False, True), (ACT_NONE, 1, True, True), (ACT_LRELU, 0, False, True), (ACT_RELU, 0, False, False)]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "act%d_pad%d_res%d_train%d" % c)
+def test_batchnorm_fn_cpu(case):
+    prev = ops.set_impl(R.RefImpl(torch.float64))
+    try:
+        _fn_case("cpu", torch.float32, *case)
+    finally:
+        ops.set_impl(prev)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "act%d_pad%d_res%d_train%d" % c)
+def test_batchnorm_fn_gpu(case, dtype):
+    _fn_case("cuda", dtype, *case)
+    assert ops.impl().tc_error() == 0
+
+
+def _nets_vs_reference(dev, dtype, tol):
+    from oracle.ref_import import import_reference, reference_available
+    if not reference_available():
+        pytest.skip("needs /root/reference")
+    ref_n3 = import_reference()[0]
+    N3.set_default_compute_dtype(dtype)
+    try:
+        for build, size in ((lambda M: M.define_G(1, 1, 8, "resnet_6blocks", "batch", False, "normal", 0.02, []), 32),
+                            (lambda M: M.define_D(1, 8, "n_layers", 3, "batch", False, "normal", 0.02, []), 32),
+                            (lambda M: M.define_G(1, 1, 8, "unet_custom", "batch", False, "normal", 0.02, []), 32)):
+            torch.manual_seed(3)
+            ref = build(ref_n3).double()
+            ours = build(N3).to(dev)
+            assert list(ours.state_dict().keys()) == list(ref.state_dict().keys())
+            ours.load_state_dict({k: v.clone().float() if v.is_floating_point() else v.clone() for k, v in ref.state_dict().items()})
+            x = torch.randn(2, 1, size, size, size, generator=torch.Generator().manual_seed(4))
+            yr = ref(x.double())
+            yo = ours(x.to(dev))
+            assert OF.rel_l2(yo.detach().cpu().double(), yr.detach()) < tol
+            yr.square().mean().backward()
+            yo.double().square().mean().backward()
+            ro, oo = dict(ref.named_parameters()), dict(ours.named_parameters())
+            for k, p in ro.items():
+                if p.grad is None or float(p.grad.norm()) < 1e-12:
+                    continue
+                assert OF.rel_l2(oo[k].grad.detach().cpu().double(), p.grad) < 20 * tol, k
+            for k, b in ref.named_buffers():
+                if b.is_floating_point():
+                    assert OF.rel_l2(dict(ours.named_buffers())[k].cpu().double(), b) < 1e-4, k
+    finally:
+        N3.set_default_compute_dtype(torch.bfloat16)
+
+
+def test_batchnorm_networks_match_reference_cpu():
+    prev = ops.set_impl(R.RefImpl(torch.float32))
+    try:
+        _nets_vs_reference("cpu", torch.float32, 2e-4)
+    finally:
+        ops.set_impl(prev)
