@@ -1,27 +1,33 @@
 // tcgen05 / TMEM / TMA implicit-GEMM convolution kernels for sm_100a (bf16 operands, fp32 accumulate).
 //
-// Two kernels serve every eligible conv-family op (see conv_plan.h for the lowering):
+// This file holds the PTX wrappers, the shared epilogue, gather_tc_kernel and wgrad_tc_kernel; the halo-plane and
+// column variants of the gather computation live in conv_tc_halo.cuh / conv_tc_col.cuh (see conv_plan.h for the
+// lowering every conv-family op goes through).
 //
 //  gather_tc_kernel : D[128 positions][n_tile channels] = sum_{tap, kchunk} A_tap[128][64] * B_tap[n_tile][64]^T
 //     A tile  = one 5-D TMA box (64 ch, bw, bh, bd, 1) of the channels-last activation tensor per filter
 //               tap (zero fill out of bounds gives the implicit zero padding; element strides give
 //               stride-2), landing in shared memory as 128 rows x 128 B, SWIZZLE_128B  -> K-major A.
 //     B tile  = 2-D TMA box (64, n_tile) of the packed weights [tap*Cn + cn][ck]        -> K-major B.
-//     MMA     = tcgen05.mma.cta_group::1.kind::f16, M=128, N=n_tile, K=16, 4 per 64-channel chunk,
-//               issued by one elected thread; accumulator lives in TMEM (n_tile fp32 columns).
-//     Epilogue= 4 warps, one TMEM lane quadrant each: tcgen05.ld 32x32b.x32 -> bias/activation,
-//               optional per-(n,channel) sum / sum-of-squares for the following InstanceNorm
-//               (warp transpose-reduce, fp64 atomics), convert, 64 B vector stores.
+//     MMA     = tcgen05.mma.cta_group::1.kind::f16, M=128, N=n_tile (128 for paired phases), K=16, 4 per
+//               64-channel chunk, issued by one elected thread; accumulators live in TMEM (up to 8 buffers).
+//     Work    = (spatial tile) for a plain launch; (spatial tile, parity phase) or (tile, phase pair) when the 8
+//               phases of a stride-2 dgrad-form plan are merged into one launch.
+//     Epilogue= 8 warps, two per TMEM lane quadrant: tcgen05.ld 32x32b.x32 -> bias/activation, optional
+//               per-(n,channel) sum / sum-of-squares for the following InstanceNorm (kept per thread across tiles
+//               when a warp owns one 32-column chunk, warp transpose-reduce otherwise; one fp64 atomic per channel
+//               and CTA), convert, 64 B vector stores.
 //
 //  wgrad_tc_kernel  : dW[tap][128 cm][n_tile cn] += sum_{positions} Mop[pos][cm] * Nop[pos'][cn]
 //     both operands are position-major in memory, i.e. MN-major for the MMA: each 64-channel chunk of
 //     a 64-position K-block is one TMA box landing as 64 rows x 128 B (SWIZZLE_128B); descriptors use
-//     the MN-major canonical layout (LBO = chunk stride 8 KiB, SBO = 1 KiB).  Split-K over position
-//     blocks, fp32 red.global.add epilogue.
+//     the MN-major canonical layout (LBO = chunk stride, SBO = 1 KiB).  Stream-K over position blocks, fp32
+//     red.global.add epilogue.  <true>: cta_group::2 CTA pairs (M = 256, each CTA loads half of the shifted chunks).
 //
-// Pipeline: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue,
-// ring of STAGES shared-memory stages guarded by full/empty mbarriers; every wait is bounded and
-// reports through an error flag instead of hanging the GPU.
+// Warp roles (gather kernels): warps 0..7 = epilogue, then the TMA producer(s), the TMEM allocator + MMA issuer last
+// (scheduler priority); wgrad: warp 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue.  Rings of
+// shared-memory stages are guarded by full/empty mbarriers; every wait is bounded and reports through an error flag
+// instead of hanging the GPU.
 #pragma once
 #include <cuda.h>
 
@@ -393,10 +399,10 @@ __device__ __forceinline__ TileCoord decode_tile(const GatherP& P, int tile) {
   return t;
 }
 
-// Persistent: gridDim.x CTAs (one per SM) walk the tile list with stride gridDim.x.  The accumulator is
-// double-buffered in TMEM so the epilogue of tile j overlaps the MMAs of tile j+1; InstanceNorm
-// statistics are accumulated per CTA in registers and flushed with one fp64 atomic per channel when the
-// sample index changes (instead of per tile).
+// Persistent: gridDim.x CTAs (one per SM) walk the work-item list with stride gridDim.x.  The accumulator is
+// multi-buffered in TMEM (P.nbuf) so the epilogue of item j overlaps the MMAs of the following items; InstanceNorm
+// statistics are accumulated per CTA and flushed with one fp64 atomic per channel when the sample index changes
+// (instead of per tile).
 __global__ void __launch_bounds__(kThreadsGather, 1)
 gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ GatherP P) {

@@ -4,6 +4,7 @@ that eight B200s are not starved by a ``workers=0`` loader.
 
 * ``read_nifti`` -- minimal NIfTI-1 reader (single-file ``.nii`` / ``.nii.gz``; neither SimpleITK nor nibabel exists in
   this image).  Returns the voxel array in file order (x fastest), scaled by ``scl_slope / scl_inter`` when set.
+* ``write_nifti`` -- the matching float32 writer for the translated volume (test.py:187-203).
 * ``to_unit_range`` / ``from_unit_range`` -- the reference's intensity convention ``(x - 127.5) / 127.5`` (test.py:152)
   and its inverse (test.py:164).
 * ``random_patch_pairs`` -- the role of ``RandCropByPosNegLabeld`` without labels: ``n`` random ``patch``-sized crops of
@@ -57,6 +58,30 @@ def read_nifti(path):
         if slope != 0.0:
             arr = arr * np.float32(slope) + np.float32(inter)
     return np.ascontiguousarray(arr), tuple(float(p) for p in pixdim[1:4])
+
+
+def write_nifti(path, array, voxel=(1.0, 1.0, 1.0)):
+    """Minimal NIfTI-1 writer (float32, single file, ``.nii`` or ``.nii.gz``): what ``test.py:187-203`` needs to put
+    the translated volume on disk.  ``array``: (x, y, z) numpy array or tensor."""
+    arr = np.asarray(array.detach().cpu() if torch.is_tensor(array) else array, dtype=np.float32)
+    if arr.ndim != 3:
+        raise ValueError("write_nifti expects a 3-D volume")
+    hdr = bytearray(352)
+    struct.pack_into("<i", hdr, 0, 348)
+    struct.pack_into("<8h", hdr, 40, 3, arr.shape[0], arr.shape[1], arr.shape[2], 1, 1, 1, 1)
+    struct.pack_into("<2h", hdr, 70, 16, 32)                       # datatype float32, bitpix
+    struct.pack_into("<8f", hdr, 76, 1.0, float(voxel[0]), float(voxel[1]), float(voxel[2]), 0.0, 0.0, 0.0, 0.0)
+    struct.pack_into("<f", hdr, 108, 352.0)                        # vox_offset
+    struct.pack_into("<2f", hdr, 112, 1.0, 0.0)                    # scl_slope, scl_inter
+    struct.pack_into("<2h", hdr, 252, 0, 1)                        # qform_code 0, sform_code 1 (scanner)
+    struct.pack_into("<4f", hdr, 280, float(voxel[0]), 0.0, 0.0, 0.0)
+    struct.pack_into("<4f", hdr, 296, 0.0, float(voxel[1]), 0.0, 0.0)
+    struct.pack_into("<4f", hdr, 312, 0.0, 0.0, float(voxel[2]), 0.0)
+    hdr[344:348] = b"n+1\x00"
+    opener = gzip.open if str(path).endswith(".gz") else open
+    with opener(path, "wb") as f:
+        f.write(bytes(hdr))
+        f.write(arr.tobytes(order="F"))
 
 
 def to_unit_range(x):

@@ -44,6 +44,15 @@ def test_read_nifti_round_trip(tmp_path, code, dt, endian, gz):
     assert vox == (0.5, 0.5, 1.25)
 
 
+def test_write_nifti_round_trip(tmp_path):
+    vol = torch.rand(9, 6, 5) * 255
+    for name in ("o.nii", "o.nii.gz"):
+        p = str(tmp_path / name)
+        data.write_nifti(p, vol, voxel=(0.4, 0.4, 0.8))
+        got, vox = data.read_nifti(p)
+        assert np.array_equal(got, vol.numpy()) and np.allclose(vox, (0.4, 0.4, 0.8))
+
+
 def test_read_nifti_rejects_garbage(tmp_path):
     p = str(tmp_path / "bad.nii")
     open(p, "wb").write(b"\x00" * 400)
