@@ -121,3 +121,40 @@ def test_batchnorm_networks_match_reference_cpu():
         _nets_vs_reference("cpu", torch.float32, 2e-4)
     finally:
         ops.set_impl(prev)
+
+
+def test_cyclegan_step_with_batchnorm_matches_reference_cpu(tmp_path):
+    """The whole drop-in surface with norm='batch' (the reference's own CycleGANModel on the CPU, same weights, same
+    inputs, same host RNG): the eight losses of two optimisation steps."""
+    import random
+    from mra_gan_b200.models import create_model
+    from oracle.ref_import import import_reference, make_opt, reference_available
+    if not reference_available():
+        pytest.skip("needs /root/reference")
+    _, cycle_mod, _, _ = import_reference()
+    prev = ops.set_impl(R.RefImpl(torch.float32))
+    N3.set_default_compute_dtype(torch.float32)
+    try:
+        opt = make_opt(ngf=4, ndf=4, pool_size=2, norm="batch", checkpoints_dir=str(tmp_path), gpu_ids=-1)
+        random.seed(5)
+        torch.manual_seed(5)
+        ref = cycle_mod.CycleGANModel()
+        ref.initialize(make_opt(ngf=4, ndf=4, pool_size=2, norm="batch", checkpoints_dir=str(tmp_path)))
+        ours = create_model(opt)
+        ours.setup(opt)
+        for name in ("G_A", "G_B", "D_A", "D_B"):
+            src = getattr(ref, "net" + name).state_dict()
+            getattr(ours, "net" + name).load_state_dict({k: v.clone() for k, v in src.items()})
+        for s in range(2):
+            A, B = OF.synthetic_patches(2, 32, seed=10 + s)
+            random.seed(100 + s)
+            ref.set_input([A, B]); ref.optimize_parameters()
+            want = ref.get_current_losses()
+            random.seed(100 + s)
+            ours.set_input([A, B]); ours.optimize_parameters()
+            got = ours.get_current_losses()
+            for k in want:
+                assert got[k] == pytest.approx(want[k], rel=2e-3, abs=1e-5), (s, k, got[k], want[k])
+    finally:
+        ops.set_impl(prev)
+        N3.set_default_compute_dtype(torch.bfloat16)
