@@ -142,6 +142,18 @@ def make_weights(spec, seed, dtype=torch.float32, scale=0.02):
     return sd
 
 
+def make_weights_like(state_dict, seed, scale=0.05):
+    """Deterministic weights for ANY network from the keys / shapes of its state_dict (used for norm='batch' nets,
+    whose affine scale must sit near 1: a 1-D '.weight' is a BatchNorm gamma)."""
+    spec = OrderedDict((k, tuple(v.shape)) for k, v in state_dict.items())
+    sd = make_weights(spec, seed, scale=scale)
+    g = torch.Generator().manual_seed(seed + 1000)
+    for k, shp in spec.items():
+        if k.endswith(".weight") and len(shp) == 1:
+            sd[k] = 1.0 + 0.3 * torch.randn(shp, generator=g)
+    return sd
+
+
 def weights_checksum(sd):
     """Order-sensitive fp64 checksum used by fixtures to detect RNG drift."""
     acc = 0.0

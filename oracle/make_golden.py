@@ -66,6 +66,51 @@ def gen_nets(nw):
     return out
 
 
+BN_NETS = {"resnet6_ngf8": ("G", "resnet_6blocks", 21), "nlayer3_ndf8": ("D", "n_layers", 22),
+           "unet5_ngf8": ("G", "unet_custom", 23)}
+
+
+def build_bn_net(mod, kind, which):
+    """norm='batch' networks of the fixture, built through either module's define_G / define_D."""
+    if kind == "G":
+        return mod.define_G(1, 1, 8, which, "batch", False, "normal", 0.02, [])
+    return mod.define_D(1, 8, which, 3, "batch", False, "normal", 0.02, [])
+
+
+def gen_batchnorm(nw):
+    """norm='batch' (networks3D.py:17): train-mode forward, backward of mean(y^2), buffers after the step, and an
+    eval-mode forward on the updated running statistics (reference modules cast to fp64, results stored as fp32)."""
+    out = {}
+    x, _ = OF.synthetic_patches(2, 32, seed=7)
+    for name, (kind, which, seed) in BN_NETS.items():
+        net = build_bn_net(nw, kind, which)
+        sd = OF.make_weights_like(net.state_dict(), seed)
+        _load(net, sd)
+        net.double().train()                               # the reference's modules evaluated in fp64: the 1^3 bottleneck of
+        x = x.double()                                     # the UNet (2 values per channel) is ill-conditioned in fp32
+        xi = x.clone().requires_grad_(True)
+        y = net(xi)
+        y.square().mean().backward()
+        grads = {k: p.grad.detach().float() for k, p in net.named_parameters()
+                 if p.grad is not None and (p.dim() == 1 or k in ("model.1.weight", "model.0.weight", "model.model.0.weight"))}
+        bufs = {k: (b.detach().float() if b.is_floating_point() else b.detach().clone()) for k, b in net.named_buffers()}
+        net.eval()
+        with torch.no_grad():
+            y_eval = net(x)
+        # the reference's own fp32 run against its fp64 run: the conditioning floor an fp32 implementation sits on
+        net32 = _load(build_bn_net(nw, kind, which), sd).train()
+        x32 = x.float().requires_grad_(True)
+        y32 = net32(x32)
+        y32.square().mean().backward()
+        g32 = dict(net32.named_parameters())
+        floor = dict(y=OF.rel_l2(y32.detach(), y.detach()), dx=OF.rel_l2(x32.grad, xi.grad),
+                     grads=max(OF.rel_l2(g32[k].grad, v) for k, v in grads.items() if float(v.norm()) > 1e-12))
+        out[name] = dict(weight_seed=seed, input_seed=7, checksum=OF.weights_checksum(sd), keys=list(sd.keys()),
+                         y=y.detach().float(), dx=xi.grad[:, :, ::2, ::2, ::2].float(), grads=grads, buffers=bufs,
+                         y_eval=y_eval.float(), fp32_floor=floor)
+    return out
+
+
 def gen_step(cycle_mod, no_lsgan, netG="resnet_9blocks", ngf=8, size=32, steps=2, batch=1):
     opt = make_opt(ngf=ngf, ndf=8, no_lsgan=no_lsgan, netG=netG, pool_size=2)
     torch.manual_seed(1234)
@@ -152,6 +197,9 @@ def main():
     torch.set_num_threads(8)
     nw, cycle_mod, testm, _ = import_reference()
     os.makedirs(GOLDEN, exist_ok=True)
+    if sys.argv[1:] == ["batchnorm"]:                      # regenerate this one fixture only
+        torch.save(gen_batchnorm(nw), os.path.join(GOLDEN, "batchnorm_small.pt"))
+        return 0
     torch.save(gen_nets(nw), os.path.join(GOLDEN, "nets_small.pt"))
     steps = {"lsgan": gen_step(cycle_mod, no_lsgan=False),
              "bce": gen_step(cycle_mod, no_lsgan=True, steps=1),
@@ -159,6 +207,7 @@ def main():
              "unet5": gen_step(cycle_mod, no_lsgan=False, netG="unet_custom", steps=1)}
     torch.save(steps, os.path.join(GOLDEN, "cyclegan_step_small.pt"))
     torch.save(gen_sliding(nw, testm), os.path.join(GOLDEN, "sliding_window_small.pt"))
+    torch.save(gen_batchnorm(nw), os.path.join(GOLDEN, "batchnorm_small.pt"))
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 

@@ -115,6 +115,68 @@ def _nets_vs_reference(dev, dtype, tol):
         N3.set_default_compute_dtype(torch.bfloat16)
 
 
+def _nets_vs_golden(golden_dir, dev, dtype, tol):
+    """The committed fixture (oracle/make_golden.py:gen_batchnorm, generated from the unmodified reference): runs on
+    the GPU box, where /root/reference is absent."""
+    import os
+    from oracle.make_golden import BN_NETS, build_bn_net
+    g = torch.load(os.path.join(golden_dir, "batchnorm_small.pt"), weights_only=False)
+    N3.set_default_compute_dtype(dtype)
+    try:
+        for name, (kind, which, seed) in BN_NETS.items():
+            r = g[name]
+            net = build_bn_net(N3, kind, which).to(dev)
+            assert list(net.state_dict().keys()) == r["keys"]
+            sd = OF.make_weights_like(net.state_dict(), r["weight_seed"])
+            assert OF.weights_checksum(sd) == pytest.approx(r["checksum"], rel=1e-12)
+            net.load_state_dict(sd)
+            net.train()
+            x, _ = OF.synthetic_patches(2, 32, seed=r["input_seed"])
+            xi = x.to(dev).requires_grad_(True)
+            y = net(xi)
+            assert OF.rel_l2(y.detach().cpu(), r["y"]) < tol, name
+            y.double().square().mean().backward()
+            # gradients: the fixture is the reference in fp64; fp32_floor = the reference's own fp32 run against it (the
+            # UNet's 1^3 bottleneck normalises 2 values per channel: 5e-3 on dx in fp32, whoever computes it)
+            fl = r["fp32_floor"]
+            assert OF.rel_l2(xi.grad.cpu()[:, :, ::2, ::2, ::2], r["dx"]) < max(20 * tol, 3 * fl["dx"]), name
+            params = dict(net.named_parameters())
+            for k, want in r["grads"].items():
+                if float(want.norm()) < 1e-12:
+                    continue
+                assert OF.rel_l2(params[k].grad.detach().cpu(), want) < max(20 * tol, 3 * fl["grads"]), (name, k)
+            bufs = dict(net.named_buffers())
+            for k, want in r["buffers"].items():
+                if want.is_floating_point():
+                    assert OF.rel_l2(bufs[k].cpu(), want) < max(tol, 1e-4), (name, k)
+                else:
+                    assert int(bufs[k]) == int(want), (name, k)
+            net.eval()
+            with torch.no_grad():
+                ye = net(x.to(dev))
+            assert OF.rel_l2(ye.cpu(), r["y_eval"]) < tol, name
+    finally:
+        N3.set_default_compute_dtype(torch.bfloat16)
+
+
+def test_batchnorm_networks_match_golden_cpu(golden_dir):
+    prev = ops.set_impl(R.RefImpl(torch.float32))
+    saved = N3.device
+    try:
+        N3.device = torch.device("cpu")
+        _nets_vs_golden(golden_dir, "cpu", torch.float32, 2e-4)
+    finally:
+        N3.device = saved
+        ops.set_impl(prev)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 6e-2)], ids=["fp32", "bf16"])     # bf16: storage floor 2.5e-2 (CPU oracle ops with bf16 storage)
+def test_batchnorm_networks_match_golden_gpu(golden_dir, dtype, tol):
+    _nets_vs_golden(golden_dir, "cuda", dtype, tol)
+    assert ops.impl().tc_error() == 0
+
+
 def test_batchnorm_networks_match_reference_cpu():
     prev = ops.set_impl(R.RefImpl(torch.float32))
     try:
