@@ -276,8 +276,9 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const EpiWarp W(warp);
     const int q = W.q;
     const int row = q * 32 + lane;
-    int nchunks = P.n_tile / 32;
-    const bool defer = P.stats != nullptr && nchunks <= 2;
+    const int nch_full = P.n_tile / 32;
+    int nchunks = nch_full;                  // of the current work item (half-width tail items: t.width < n_tile)
+    const bool defer = P.stats != nullptr && nch_full <= 2;
     double st_s[8], st_q[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) { st_s[c] = 0.0; st_q[c] = 0.0; }
@@ -299,7 +300,9 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const long long obase = (long long)t.n * P.osn + (long long)(t.d * P.ostep + P.od0) * P.osd +
                               (long long)(lh * P.ostep + P.oh0) * P.osh + (long long)(lw * P.ostep + P.ow0) * P.osw + t.n0;
       if (P.stats && (t.n != st_n || t.n0 != st_n0)) {
-        epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, W.q, W.c_begin, 2, nchunks, lane, st_s, st_q, defer, d1, d2, epi_red);
+        // flush over ALL chunks of a full-width tile, not the last item's: a half-width tail item may follow
+        // full-width tiles of the same (sample, channel base), whose upper chunks still sit in st_s / st_q
+        epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, W.q, W.c_begin, 2, nch_full, lane, st_s, st_q, defer, d1, d2, epi_red);
         st_n = t.n; st_n0 = t.n0;
       }
       nchunks = t.width / 32;
@@ -316,7 +319,7 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       });
       if (prof && threadIdx.x == 0) atomicAdd(P.dbg + 4, (unsigned long long)(clock64() - te0));
     }
-    if (P.stats) epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, W.q, W.c_begin, 2, nchunks, lane, st_s, st_q, defer, d1, d2, epi_red);
+    if (P.stats) epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, W.q, W.c_begin, 2, nch_full, lane, st_s, st_q, defer, d1, d2, epi_red);
   }
   tc_fence_before();
   if constexpr (kPair) cluster_sync_all(); else __syncthreads();

@@ -101,19 +101,24 @@ class RefImpl:
             stats = torch.stack([yd.sum((2, 3, 4)), (yd * yd).sum((2, 3, 4))], -1)
         return to_ndhwc(_act(y, act, slope)).to(x.dtype), stats
 
+    def _conv_backward(self, gy, x, w_ref, g, mask):
+        """ATen's convolution_backward -- the node torch's autograd runs for nn.Conv3d / nn.ConvTranspose3d -- called
+        directly (usable below the autograd dispatch key, e.g. from inside a torch.library operator)."""
+        op = [g.output_padding] * 3 if g.transposed else [0] * 3
+        return torch.ops.aten.convolution_backward(gy.contiguous(), x, w_ref.contiguous(), None, [g.stride] * 3, [g.pad] * 3,
+                                                   [1] * 3, g.transposed, op, 1, mask)
+
     def conv_dgrad(self, dy, wT, g, in_dims):
         wp = self._c(wT).transpose(1, 2).contiguous()
-        with torch.enable_grad():       # may be called from inside an autograd backward
-            x = torch.zeros((dy.shape[0], g.cin) + tuple(in_dims), dtype=self.cd, requires_grad=True)
-            y = self._conv(x, wp, None, g)
-            (dx,) = torch.autograd.grad(y, x, to_ncdhw(self._c(dy)))
+        x = torch.zeros((dy.shape[0], g.cin) + tuple(in_dims), dtype=self.cd)
+        dx = self._conv_backward(to_ncdhw(self._c(dy)), x, unpack_weight(wp, g.k, g.transposed), g, [True, False, False])[0]
         return to_ndhwc(dx).to(dy.dtype)
 
     def conv_wgrad(self, x, dy, g, want_bias=False, acc_dw=None, acc_db=None):
-        with torch.enable_grad():
-            wp = torch.zeros((g.taps, g.cout, g.cin), dtype=self.cd, requires_grad=True)
-            y = self._conv(to_ncdhw(self._c(x)).detach(), wp, None, g)
-            (dw,) = torch.autograd.grad(y, wp, to_ncdhw(self._c(dy)))
+        wp = torch.zeros((g.taps, g.cout, g.cin), dtype=self.cd)
+        gw = self._conv_backward(to_ncdhw(self._c(dy)), to_ncdhw(self._c(x)).contiguous(),
+                                 unpack_weight(wp, g.k, g.transposed), g, [False, True, False])[1]
+        dw = pack_weight(gw, g.transposed)
         db = self._c(dy).sum((0, 1, 2, 3)).float() if want_bias else None
         if acc_dw is not None:                       # MRA_CONV_ACCUMULATE: add into the caller's buffers
             acc_dw += dw.float()
