@@ -309,3 +309,15 @@ def test_generator_forward_full_size_window():
     print("resnet_9blocks ngf=64, 128^3 window, bf16 vs fp32 oracle: rel-L2 %.3e (bf16 storage floor 1.66e-2)" % err)
     assert err < 4e-2
     torch.cuda.empty_cache()
+
+
+@pytest.mark.gpu
+def test_halo_tail_items_share_a_sample_with_full_tiles():
+    """The scheduling case behind the statistics bug fixed in conv_tc_halo.cuh, at a size that runs in a blink: one sample
+    of 256 -> 256 channels with 80 CTA-pair tiles on 74 pairs, so the last 6 tiles are split into half-width items and
+    12 CTAs process a full-width tile AND a half-width item of the same sample (even units without a channel-base change
+    in between).  Statistics, crops (the far corner lies in the split tiles), masked wgrad and adjoints all apply."""
+    g, dims = ConvGeom(256, 256, 3, 1, 0), (42, 34, 18)
+    I = ops.impl()
+    check_conv_layer(I, R.RefImpl(torch.float32), g, dims, 1, torch.bfloat16, "cuda", 1e-2, stats=True)
+    assert I.tc_error() == 0
