@@ -64,7 +64,7 @@ class GradSync:
         self.bucket_elems = int(bucket_mb * 1024 * 1024 / 4)
         self.phases = {name: self._build(nets) for name, nets in phases.items()}
         self.active = None
-        self.stats = {"buckets": sum(len(b) for b in self.phases.values()), "allreduce_calls": 0}
+        self.stats = {"buckets": sum(len(b) for b in self.phases.values()), "allreduce_calls": 0, "late_launches": 0}
 
     def _build(self, nets):
         params = [p for net in nets for p in net.parameters()]
@@ -134,7 +134,12 @@ class GradSync:
     def finish(self, phase):
         """Issue any bucket whose parameters did not all receive a gradient, then wait."""
         for b in self.phases[phase]:
+            lo, hi = b.flat.data_ptr(), b.flat.data_ptr() + b.flat.numel() * 4
+            for p in b.params:                          # a replaced .grad would silently escape the averaging
+                if p.grad is None or not (lo <= p.grad.data_ptr() < hi):
+                    raise RuntimeError("GradSync: a gradient left its bucket during the backward pass")
             if not b.launched:
+                self.stats["late_launches"] += 1        # no overlap for this one: not every hook of the bucket fired
                 self._launch(b)
         for b in self.phases[phase]:
             if b.work is not None:
@@ -145,7 +150,7 @@ class GradSync:
         self.active = None
 
 
-def attach(model, bucket_mb=32.0):
+def attach(model, bucket_mb=32.0, fused_wgrad=None):
     """Make a CycleGANModel data-parallel: broadcast rank 0's weights and buffers, then average
     gradients across ranks every step.  Returns the GradSync (also stored as ``model.grad_sync``)."""
     if dist.is_initialized() and dist.get_world_size() > 1:
@@ -154,8 +159,15 @@ def attach(model, bucket_mb=32.0):
             for t in list(net.parameters()) + list(net.buffers()):
                 dist.broadcast(_dense_view(t.data), src=0)
     from . import networks3D
+    # Default: every use of a weight hands autograd its own gradient, AccumulateGrad adds them into the bucket view.
+    # fused_wgrad (MRA_DP_FUSED_WGRAD=1) keeps the single-process fusion instead: the wgrad kernels add every use
+    # straight into the bucket view and autograd is handed nothing.  The engine still runs each parameter's
+    # AccumulateGrad node -- and with it the post-accumulate hook the buckets listen to -- once all uses are done
+    # (observed on torch 2.11; were it ever skipped, finish() launches the bucket, losing overlap, not correctness).
+    # Opt-in until it has been measured at N > 1.
+    fused = os.environ.get("MRA_DP_FUSED_WGRAD", "0") == "1" if fused_wgrad is None else bool(fused_wgrad)
     for name in model.model_names:
-        networks3D.set_fused_wgrad(getattr(model, "net" + name), False)     # every gradient must pass AccumulateGrad
+        networks3D.set_fused_wgrad(getattr(model, "net" + name), fused)
     model.grad_sync = GradSync({"G": [model.netG_A, model.netG_B], "D": [model.netD_A, model.netD_B]},
                                bucket_mb=bucket_mb)
     return model.grad_sync

@@ -48,7 +48,7 @@ def _grads(m):
     return out
 
 
-def _worker(rank, world, port, tmp, q):
+def _worker(rank, world, port, tmp, q, fused):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.set_num_threads(2)
     from mra_gan_b200 import parallel
@@ -59,7 +59,8 @@ def _worker(rank, world, port, tmp, q):
         with torch.no_grad():
             for p in m.netG_A.parameters():
                 p.add_(0.5)
-    sync = parallel.attach(m, bucket_mb=0.05)       # small buckets -> several all-reduces per phase
+    sync = parallel.attach(m, bucket_mb=0.05, fused_wgrad=fused)   # small buckets -> several all-reduces per phase
+    assert all(c.fuse_wgrad == fused for c in m.netG_A.conv_modules())
     A, B = OF.synthetic_patches(2, 32, seed=9)
     m.set_input([A[rank:rank + 1], B[rank:rank + 1]])
     m.optimize_parameters()
@@ -71,11 +72,15 @@ def _worker(rank, world, port, tmp, q):
 
 
 @pytest.mark.timeout(600)
-def test_two_rank_gradient_averaging_matches_batch_two(tmp_path):
+@pytest.mark.parametrize("fused", [False, True], ids=["autograd_accumulate", "fused_wgrad"])
+def test_two_rank_gradient_averaging_matches_batch_two(tmp_path, fused):
+    """fused = True: the wgrad kernels add every use of a weight straight into its bucket view and the conv modules
+    tell the buckets when a weight is final (MRA_DP_FUSED_WGRAD); every bucket must still go out exactly once, from
+    inside the backward pass."""
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, str(tmp_path), q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, str(tmp_path), q, fused)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=500) for _ in range(world)]
@@ -100,3 +105,4 @@ def test_two_rank_gradient_averaging_matches_batch_two(tmp_path):
         assert OF.rel_l2(g0, v) < 5e-3, k
     stats = res[0][3]
     assert stats["buckets"] > 4 and stats["allreduce_calls"] == stats["buckets"]
+    assert stats["late_launches"] == 0, "every bucket must go out from inside the backward pass (overlap)"
