@@ -81,15 +81,50 @@ def make_opt(**kw):
     return ns
 
 
+WORKLOAD = ("resnet_9blocks G + 3-layer PatchGAN D, ngf=ndf=64, LSGAN, one CycleGAN optimize_parameters() on "
+            "synthetic 128^3 patches")
+
+
+def default_batch(world):
+    """BASELINE.json: config 2 (1 GPU) is quoted at batch 2, config 3 (2/4/8 GPUs) at batch 4 per GPU."""
+    return 2 if world == 1 else 4
+
+
+def workload_config(world, per_gpu_batch, launch):
+    """The `config` object of the JSON line -- the SAME for this framework's arm and for --impl reference (whose steps
+    are a bounded CPU sample of this workload, described in its cpu_baseline.sample)."""
+    return {"workload": WORKLOAD, "patch": PATCH, "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * world,
+            "parallelism": "dp%d" % world, "l2": "per-step working set (tens of GB) >> 126 MB L2",
+            "launch": launch, "model_tflop_per_sample_step": FLOP_PER_SAMPLE_STEP / 1e12}
+
+
+def launch_mode(world, no_graphs=False):
+    use_graphs = not no_graphs and (world == 1 or os.environ.get("MRA_DP_GRAPHS", "0") == "1")
+    return use_graphs, ("two CUDA graphs per step" if use_graphs else "eager")
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU baseline: the reference's algorithm (oracle port) on the host cores
 # ------------------------------------------------------------------------------------------------
+def use_all_host_cores():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core (and says how many)."""
+    import torch
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0)) or n
+    except Exception:  # noqa: BLE001
+        pass
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
 def cpu_step_seconds(size, steps, warmup, ngf=64):
     import random
 
     import torch
 
     from oracle import functional as OF
+    use_all_host_cores()
     random.seed(1234)
     sds = OF.build_cyclegan_weights(ngf, ngf, seed=1234)
     m = OF.CycleGANOracle(*sds, netG="resnet_9blocks", no_lsgan=False)
@@ -105,35 +140,48 @@ def cpu_step_seconds(size, steps, warmup, ngf=64):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is
-    pure Python on torch CPU and cannot be pip-installed: no setup.py), bounded sample per step."""
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is pure Python
+    on torch CPU with no setup.py, so there is nothing to pip-install or compile), on all host cores.  Each step is
+    BASELINE config 1 -- one optimize_parameters() on a 64^3 patch, batch 1, fp32 -- a bounded sample of the 128^3
+    workload (voxels/s is size-normalised); a slower host falls back to 48^3 / 32^3 to keep the run within minutes."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return 0
     import torch
-    # calibrate on a tiny patch, then pick the largest patch that keeps the run within ~3 minutes
-    t_small, threads = cpu_step_seconds(32, 1, 0)
-    budget = 170.0
+    threads = use_all_host_cores()
+    t_small, _ = cpu_step_seconds(32, 1, 0)
+    budget = 240.0
     size = 32
     for cand in (64, 48):
-        est = t_small * (cand / 32.0) ** 3 * (args.steps + args.warmup)
-        if est < budget:
+        if t_small * (cand / 32.0) ** 3 * (args.steps + args.warmup) < budget:
             size = cand
             break
     sec, threads = cpu_step_seconds(size, args.steps, args.warmup)
     vox = size ** 3 / sec
+    _, launch = launch_mode(world)
+    sample = ("each step = one optimize_parameters() of the oracle port on a %d^3 patch, batch 1, fp32%s; %d timed "
+              "step(s) after %d warm-up, %d host threads, torch CPU %s"
+              % (size, " (BASELINE config 1)" if size == 64 else " (host too slow for config 1's 64^3 within the time budget)",
+                 args.steps, args.warmup, threads, torch.__version__))
     line = {
         "impl": "reference", "metric": "cyclegan_train_voxels_per_sec", "value": vox, "unit": "voxels/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "resnet_9blocks G + 3-layer PatchGAN D, ngf=ndf=64, LSGAN, one optimize_parameters()",
-                   "patch": size, "batch": 1, "note": "CPU sample of the 128^3 workload (same model, smaller patch)"},
-        "cpu_baseline": {"value": vox, "unit": "voxels/s", "cores": threads, "kind": "port",
-                         "sample": "%d^3 patch, batch 1, fp32, %d timed step(s), torch CPU %s" % (size, args.steps, torch.__version__)},
+        "config": workload_config(world, args.batch if args.batch else default_batch(world), launch),
+        "cpu_baseline": {"value": vox, "unit": "voxels/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": vox, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
     return 0
+
+
+def cpu_baseline_block():
+    """Bounded CPU sample for the GPU arm's line: BASELINE config 1 (64^3, batch 1, fp32), 2nd and 3rd step."""
+    sec, threads = cpu_step_seconds(64, 2, 1)
+    return {"value": 64 ** 3 / sec, "unit": "voxels/s", "cores": threads, "kind": "port",
+            "sample": "BASELINE config 1: 64^3 patch, batch 1, fp32; mean of steps 2-3 of optimize_parameters() "
+                      "(%.1f s each) of the oracle port on %d host threads" % (sec, threads)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -221,7 +269,7 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     if args.gpus != world and rank == 0:
         print("warning: --gpus %d but WORLD_SIZE=%d (launch with torchrun for N>1)" % (args.gpus, world), file=sys.stderr)
-    per_gpu_batch = args.batch if args.batch else (2 if world == 1 else 4)
+    per_gpu_batch = args.batch if args.batch else default_batch(world)
     N3.set_default_compute_dtype(torch.bfloat16)
     torch.manual_seed(1234)
     import random
@@ -234,17 +282,9 @@ def run_gpu(args):
     I = ops.impl()
     if world > 1:
         parallel.attach(model)
-    # Data-parallel graph replay (NCCL all-reduces captured) measured +2 % at N = 2 but the process group did not shut
-    # down cleanly afterwards, so it stays opt-in (MRA_DP_GRAPHS=1) until that is understood.
-    use_graphs = not args.no_graphs and (world == 1 or os.environ.get("MRA_DP_GRAPHS", "0") == "1")
+    use_graphs, launch = launch_mode(world, args.no_graphs)
     if use_graphs:
         model.enable_cuda_graphs(warmup_steps=2)        # the step is replayed as two CUDA graphs after 2 eager steps
-
-    g = torch.Generator().manual_seed(1234 + rank)
-    shape = (per_gpu_batch, 1, PATCH, PATCH, PATCH)
-    host_A = (torch.rand(shape, generator=g) * 2 - 1).pin_memory()
-    host_B = (torch.rand(shape, generator=g) * 2 - 1).pin_memory()
-    dev_A, dev_B = host_A.cuda(), host_B.cuda()
 
     def barrier():
         if world > 1:
@@ -264,39 +304,53 @@ def run_gpu(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps
 
-    def step_resident():
-        model.set_input([dev_A, dev_B])
-        model.optimize_parameters()
+    def measure(batch, steps, warmup):
+        """(ms per resident step, ms per end-to-end step, kernels per step, host bytes per step) at one batch size."""
+        g = torch.Generator().manual_seed(1234 + rank)
+        shape = (batch, 1, PATCH, PATCH, PATCH)
+        host_A = (torch.rand(shape, generator=g) * 2 - 1).pin_memory()
+        host_B = (torch.rand(shape, generator=g) * 2 - 1).pin_memory()
+        dev_A, dev_B = host_A.cuda(), host_B.cuda()
 
-    last_losses = {}
+        def step_resident():
+            model.set_input([dev_A, dev_B])
+            model.optimize_parameters()
 
-    def step_e2e():
-        model.set_input([host_A, host_B])           # pinned host -> device inside the timed region
-        model.optimize_parameters()
-        last_losses.update(model.get_current_losses())   # device -> host read of the 8 losses
+        def step_e2e():
+            model.set_input([host_A, host_B])           # pinned host -> device inside the timed region
+            model.optimize_parameters()
+            model.get_current_losses()                  # device -> host read of the 8 losses (one transfer)
 
-    for _ in range(max(args.warmup, 3)):               # >= 3: two eager steps + the capture step of the graph replay
-        step_resident()
+        for _ in range(max(warmup, 3)):                 # >= 3: two eager steps + the capture step of the graph replay
+            step_resident()
+        launches0 = I.launch_count()
+        ms_step = timed(step_resident, steps)
+        launches = (I.launch_count() - launches0) // steps
+        graphs = getattr(model, "_graphs", None)
+        if graphs and graphs.get("launches"):
+            launches = graphs["launches"]               # replayed from the captured graphs: count taken at capture
+        ms_e2e = timed(step_e2e, steps)
+        return ms_step, ms_e2e, int(launches), int(host_A.numel() * 4 * 2)
+
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    launches0 = I.launch_count()
-    ms_step = timed(step_resident, args.steps)
-    launches = (I.launch_count() - launches0) // args.steps
-    graphs = getattr(model, "_graphs", None)
-    if graphs and graphs.get("launches"):
-        launches = graphs["launches"]                   # replayed from the captured graphs: count taken at capture
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_step, ms_e2e, launches, h2d = measure(per_gpu_batch, args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
     err = I.tc_error()
+    if err:
+        raise RuntimeError("tensor-core kernel barrier time-out (code %d): the timed steps are invalid" % err)
 
     global_batch = per_gpu_batch * world
     vox = global_batch * PATCH ** 3 / (ms_step * 1e-3)
     vox_e2e = global_batch * PATCH ** 3 / (ms_e2e * 1e-3)
-    if rank != 0:
-        model._graphs = None
-        dist.barrier()
+    if world > 1:
+        model._graphs = None                       # graphs holding NCCL nodes must go before the communicator
+        import gc
+        gc.collect()
+        barrier()
         dist.destroy_process_group()
+    if rank != 0:
         return 0
 
     peaks, peak_src = load_peaks()
@@ -308,13 +362,8 @@ def run_gpu(args):
         "metric": "cyclegan_train_voxels_per_sec", "value": vox, "unit": "voxels/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "resnet_9blocks G + 3-layer PatchGAN D, ngf=ndf=64, LSGAN, one CycleGAN "
-                               "optimize_parameters() on synthetic 128^3 patches",
-                   "patch": PATCH, "per_gpu_batch": per_gpu_batch, "global_batch": global_batch,
-                   "parallelism": "dp%d" % world, "l2": "per-step working set (tens of GB) >> 126 MB L2",
-                   "launch": "two CUDA graphs per step" if use_graphs else "eager",
-                   "model_tflop_per_sample_step": FLOP_PER_SAMPLE_STEP / 1e12},
-        "e2e": {"value": vox_e2e, "unit": "voxels/s", "h2d_bytes_per_step": int(host_A.numel() * 4 * 2),
+        "config": workload_config(world, per_gpu_batch, launch),
+        "e2e": {"value": vox_e2e, "unit": "voxels/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 8 * 4, "ms_per_step": ms_e2e},
         "gpu_launches": int(launches),
         "clocks": clocks,
@@ -327,16 +376,25 @@ def run_gpu(args):
         "roofline_hbm": norm_roof,
         "tc_error_flag": err,
     }
-    if world == 1 and not args.no_cpu_baseline:
-        sec, threads = cpu_step_seconds(64, 1, 0)
-        line["cpu_baseline"] = {"value": 64 ** 3 / sec, "unit": "voxels/s", "cores": threads, "kind": "port",
-                                "sample": "BASELINE config 1: 64^3 patch, batch 1, fp32, first optimize_parameters() "
-                                          "(%.1f s) of the oracle port on the host cores" % sec}
+    if world == 1 and not args.no_anchor and not args.batch:
+        # the weak-scaling anchor: the SAME program the N > 1 runs execute (config 3's per-GPU batch and launch mode)
+        # on one GPU, so that value(N) / (N * anchor.value) compares like with like
+        model._graphs = None
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        a_graphs, a_launch = launch_mode(2, args.no_graphs)
+        if a_graphs:
+            model.enable_cuda_graphs(warmup_steps=2)
+        a_batch = default_batch(2)
+        a_ms, a_e2e, a_l, _ = measure(a_batch, max(3, min(args.steps, 10)), 3)
+        line["anchor"] = {"what": "this program at the N>1 per-GPU batch on ONE GPU (weak-scaling denominator)",
+                          "per_gpu_batch": a_batch, "launch": a_launch, "ms_per_step": a_ms,
+                          "value": a_batch * PATCH ** 3 / (a_ms * 1e-3), "unit": "voxels/s",
+                          "e2e_value": a_batch * PATCH ** 3 / (a_e2e * 1e-3), "gpu_launches": a_l}
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_block()       # rank 0, after the timed region; the other ranks have exited
     print(json.dumps(line), flush=True)
-    if world > 1:
-        model._graphs = None                       # graphs holding NCCL nodes must go before the communicator
-        dist.barrier()
-        dist.destroy_process_group()
     return 0
 
 
@@ -348,6 +406,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 2 on 1 GPU, 4 per GPU on N>1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-anchor", action="store_true", help="skip the batch-4 single-GPU anchor measurement (N=1 only)")
     ap.add_argument("--no-graphs", action="store_true", help="run the step eagerly (no CUDA-graph replay)")
     args = ap.parse_args()
     if args.impl == "reference":

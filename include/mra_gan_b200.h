@@ -165,6 +165,12 @@ int mra_adam_multi(const mra_adam_tensor* tensors, int count, float lr, float be
  * sqrt(1 - beta2^t)} (6 floats).  Lets a captured CUDA graph of the training step be replayed while the host advances
  * the step count and the learning-rate schedule. */
 int mra_adam_multi_dev(const mra_adam_tensor* tensors, int count, const float* hyper, mra_stream_t stream);
+/* Device-resident step counter for mra_adam_multi_dev: state = {lr, beta1, beta2, eps, t, -, -, -} (8 doubles in
+ * device memory, written by the caller when a rate changes or a checkpoint is loaded).  One launch does t += 1 and
+ * writes hyper[0..5] with the bias corrections of step t computed in double (torch.optim.Adam's host arithmetic).
+ * Captured together with the sweep, a replayed graph advances exactly one step per replay, so the host may run any
+ * number of steps ahead of the device without a staging buffer to race on. */
+int mra_adam_advance(double* state, float* hyper, mra_stream_t stream);
 
 /* Sliding-window inference helpers (test.py:147-178): window extraction with the (x-127.5)/127.5
  * scaling, and label += pred*127.5+127.5 ; weight += 1 accumulation; final label/weight + 0.01. */

@@ -63,6 +63,7 @@ _SIGNATURES = {
     "mra_corr_sums": ([_P, _P, _L, _I, _P, _P], C.c_int),
     "mra_adam_multi": ([C.POINTER(AdamTensor), _I, _F, _F, _F, _F, _I, _P], C.c_int),
     "mra_adam_multi_dev": ([C.POINTER(AdamTensor), _I, _P, _P], C.c_int),
+    "mra_adam_advance": ([_P, _P, _P], C.c_int),
     "mra_window_extract": ([_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P], C.c_int),
     "mra_window_accumulate": ([_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "mra_window_finalize": ([_P, _P, _L, _P], C.c_int),

@@ -299,11 +299,15 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const bool valid = lw < P.Wl && lh < P.Hl && t.d < P.Dl;
       const long long obase = (long long)t.n * P.osn + (long long)(t.d * P.ostep + P.od0) * P.osd +
                               (long long)(lh * P.ostep + P.oh0) * P.osh + (long long)(lw * P.ostep + P.ow0) * P.osw + t.n0;
-      if (P.stats && (t.n != st_n || t.n0 != st_n0)) {
-        // flush over ALL chunks of a full-width tile, not the last item's: a half-width tail item may follow
-        // full-width tiles of the same (sample, channel base), whose upper chunks still sit in st_s / st_q
+      // Statistics are kept per TILE (channel base tb = nt * n_tile), indexed by the chunk's position inside the full
+      // tile: a half-width tail item (t.n0 = tb or tb + n_tile / 2) adds into chunks coff .. coff + width / 32 - 1 of
+      // the same partials as the full-width tiles of that (sample, tile) before it, and a flush covers exactly the
+      // tile's n_tile channels [tb, tb + n_tile) -- never past Cn.
+      const int tb = t.n0 - (t.n0 % P.n_tile);
+      const int coff = (t.n0 - tb) >> 5;        // even (n_tile >= 128 when items are split), keeps the warps' chunk parity
+      if (P.stats && (t.n != st_n || tb != st_n0)) {
         epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, W.q, W.c_begin, 2, nch_full, lane, st_s, st_q, defer, d1, d2, epi_red);
-        st_n = t.n; st_n0 = t.n0;
+        st_n = t.n; st_n0 = tb;
       }
       nchunks = t.width / 32;
       ok = mbar_wait(&acc_full[buf], aph, P.err, 23);
@@ -312,7 +316,7 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const long long te0 = prof ? clock64() : 0;
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * P.n_tile);
       uint64_t* rel_bar = &acc_empty[buf];
-      epilogue_tile(E, t_addr, W.c_begin, 2, nchunks, valid, obase, t.n0, lane, st_s, st_q, defer, d1, d2, [&]() {
+      epilogue_tile(E, t_addr, W.c_begin, 2, nchunks, valid, obase, t.n0, lane, st_s + coff, st_q + coff, defer, d1, d2, [&]() {
         tc_fence_before();                      // accumulator fully read: hand the buffer back to the MMA warp
         __syncwarp();
         if (lane == 0) { if constexpr (kPair) mbar_arrive_leader(rel_bar); else mbar_arrive(rel_bar); }

@@ -133,6 +133,21 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamBatch B) {
   }
 }
 
+// Device-resident step counter (CUDA-graph replay without a host <-> device race): state = {lr, beta1, beta2, eps, t}
+// as doubles; one thread bumps t and derives the two bias corrections in double, exactly as torch.optim.Adam does on
+// the host (bias_correction1 = 1 - beta1^t, step_size = lr / bias_correction1, bias_correction2_sqrt = sqrt(1 - beta2^t)),
+// into the float block adam_kernel reads.  Part of the captured graph, so every replay advances by exactly one step
+// no matter how far ahead the host runs.
+__global__ void adam_advance_kernel(double* __restrict__ state, float* __restrict__ hyper) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double lr = state[0], b1 = state[1], b2 = state[2], eps = state[3];
+  const double t = state[4] + 1.0;
+  state[4] = t;
+  hyper[0] = (float)lr; hyper[1] = (float)b1; hyper[2] = (float)b2; hyper[3] = (float)eps;
+  hyper[4] = (float)(lr / (1.0 - pow(b1, t)));
+  hyper[5] = (float)sqrt(1.0 - pow(b2, t));
+}
+
 // ---------------- conversions / packing ----------------
 template <typename S, typename D>
 __global__ void __launch_bounds__(256) convert_kernel(const S* __restrict__ s, D* __restrict__ d, long long n) {

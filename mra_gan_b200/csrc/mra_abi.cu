@@ -372,6 +372,13 @@ int mra_adam_multi_dev(const mra_adam_tensor* tensors, int count, const float* h
   return adam_launch(tensors, count, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, hyper, (cudaStream_t)stream);
 }
 
+int mra_adam_advance(double* state, float* hyper, mra_stream_t stream) {
+  MRA_REQUIRE(state != nullptr && hyper != nullptr, "bad adam_advance arguments");
+  adam_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(state, hyper);
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+
 // ------------------------------------------------------------------ sliding window helpers
 int mra_window_extract(const float* vol, int X, int Y, int Z, int i0, int j0, int k0, int px, int py, int pz,
                        void* patch, int dtype, mra_stream_t stream) {

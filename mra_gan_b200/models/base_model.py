@@ -73,11 +73,24 @@ class BaseModel:
         return OrderedDict((n, getattr(self, n)) for n in self.visual_names if isinstance(n, str))
 
     def get_current_losses(self):
-        out = OrderedDict()
-        for n in self.loss_names:
-            if isinstance(n, str):
-                v = getattr(self, "loss_" + n)
-                out[n] = float(v.detach()) if torch.is_tensor(v) else float(v)   # host sync, print time only
+        """Host values of the step's losses: ONE device -> host read for all of them (print time only).  The read
+        synchronises anyway, so the tensor-core kernels' time-out flag (a bounded mbarrier wait that expired leaves
+        partial output behind) is checked here too and raised instead of training on garbage."""
+        names = [n for n in self.loss_names if isinstance(n, str)]
+        vals = [getattr(self, "loss_" + n) for n in names]
+        dev = [v.detach().float().reshape(()) for v in vals if torch.is_tensor(v)]
+        host = torch.stack(dev).cpu().tolist() if dev else []
+        out, it = OrderedDict(), iter(host)
+        for n, v in zip(names, vals):
+            out[n] = next(it) if torch.is_tensor(v) else float(v)
+        if dev and dev[0].is_cuda:
+            from .. import ops
+            I = ops.impl()
+            if getattr(I, "name", "") == "cuda":
+                code = I.tc_error()
+                if code:
+                    raise RuntimeError("mra_gan_b200: a tensor-core kernel timed out waiting on a barrier "
+                                       "(code %d); the step's results are invalid" % code)
         return out
 
     # -- checkpoints ---------------------------------------------------------------------------

@@ -332,6 +332,12 @@ class CudaImpl:
         assert hyper.is_cuda and hyper.dtype == torch.float32 and hyper.numel() >= 6
         _lib.check(self.L.mra_adam_multi_dev(arr, len(params), _ptr(hyper), self._stream()), "mra_adam_multi_dev")
 
+    def adam_advance(self, state, hyper):
+        """t += 1 on the device and hyper <- {lr, b1, b2, eps, lr/(1-b1^t), sqrt(1-b2^t)} (see mra_adam_advance)."""
+        assert state.is_cuda and state.dtype == torch.float64 and state.numel() >= 5
+        assert hyper.is_cuda and hyper.dtype == torch.float32 and hyper.numel() >= 6
+        _lib.check(self.L.mra_adam_advance(_ptr(state), _ptr(hyper), self._stream()), "mra_adam_advance")
+
     @staticmethod
     def _need_dense(p, g, m, v, s):
         for t in (p, g, m, v, s):

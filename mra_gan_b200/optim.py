@@ -5,8 +5,6 @@ It is a regular ``torch.optim.Optimizer`` (param_groups / state_dict / LR schedu
 ``step()`` is one kernel sweep (``mra_adam_multi``) over every parameter that also refreshes the
 bf16 shadow copies the tensor-core convolutions read.
 """
-import math
-
 import torch
 
 from . import ops
@@ -19,24 +17,51 @@ class FusedAdam(torch.optim.Optimizer):
             raise NotImplementedError("the reference uses plain Adam (no weight decay, no amsgrad)")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
 
-    # -- device-resident hyper-parameters (CUDA-graph replay) -----------------------------------------
-    def _hyper_buffers(self, gi, device):
-        bufs = self.__dict__.setdefault("_hyper", {})
-        if gi not in bufs:
-            bufs[gi] = (torch.zeros(8, dtype=torch.float32).pin_memory(), torch.zeros(8, dtype=torch.float32, device=device))
-        return bufs[gi]
+    # -- device-resident hyper-parameters and step counter -------------------------------------------
+    # Per param group: ``state`` = {lr, beta1, beta2, eps, t} as doubles and ``hyper`` = the float block the sweep
+    # reads, both in DEVICE memory.  mra_adam_advance (launched right before the sweep, hence part of a captured
+    # graph) bumps t and derives the bias corrections on the device, so replaying the step never reads anything
+    # the host may already have overwritten for a later step (the pinned staging buffer this replaces was rewritten
+    # by the host while earlier replays' copies were still queued).  The host uploads ``state`` only when a rate
+    # changes (LR scheduler) or its own step count disagrees with what the device will hold (first step, loaded
+    # checkpoint); that copy comes from pageable memory, i.e. it is staged before the call returns and ordered on
+    # the current stream like every launch.
+    def _dev_state(self, gi, group, device, t_before):
+        recs = self.__dict__.setdefault("_dev", {})
+        rec = recs.get(gi)
+        if rec is None:
+            rec = recs[gi] = {"state": torch.zeros(8, dtype=torch.float64, device=device),
+                              "hyper": torch.zeros(8, dtype=torch.float32, device=device), "key": None, "t": None}
+        key = (float(group["lr"]), float(group["betas"][0]), float(group["betas"][1]), float(group["eps"]))
+        if rec["key"] != key or rec["t"] != t_before:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("FusedAdam: the device step counter must be in sync before a CUDA-graph capture "
+                                   "(run one eager step or call sync_device_state() first)")
+            rec["state"].copy_(torch.tensor(list(key) + [float(t_before), 0.0, 0.0, 0.0], dtype=torch.float64))
+            rec["key"] = key
+        rec["t"] = t_before + 1
+        return rec
 
-    @staticmethod
-    def _fill_hyper(host, group, step_no):
-        b1, b2 = group["betas"]
-        lr = float(group["lr"])
-        host[0], host[1], host[2], host[3] = lr, b1, b2, group["eps"]
-        host[4] = lr / (1.0 - b1 ** step_no)
-        host[5] = math.sqrt(1.0 - b2 ** step_no)
+    def _group_step(self, group):
+        for p in group["params"]:
+            st = self.state.get(p)
+            if st:
+                return int(st["step"])
+        return None
+
+    def sync_device_state(self):
+        """Upload rates / step counts the device does not have yet (call before capturing ``step()``)."""
+        for gi, group in enumerate(self.param_groups):
+            t = self._group_step(group)
+            if t is None:
+                continue
+            dev = next(p.device for p in group["params"])
+            rec = self._dev_state(gi, group, dev, t)
+            rec["t"] = t                                  # nothing was launched: the device still holds t
 
     def advance_host_state(self):
-        """Bookkeeping of one optimiser step WITHOUT launching anything: bump the step counters and refresh the
-        pinned hyper-parameter buffers (a captured graph of ``step()`` copies them to the device when replayed)."""
+        """Bookkeeping of one optimiser step WITHOUT launching the sweep (a captured graph of ``step()`` is about to
+        be replayed): bump the host's step counters, and re-upload the device state if a rate changed meanwhile."""
         for gi, group in enumerate(self.param_groups):
             step_no = None
             for p in group["params"]:
@@ -45,8 +70,8 @@ class FusedAdam(torch.optim.Optimizer):
                     st["step"] += 1
                     step_no = st["step"]
                     self._mark(p)                      # the replayed Adam kernel rewrites weight and shadow
-            if step_no is not None and gi in self.__dict__.get("_hyper", {}):
-                self._fill_hyper(self._hyper[gi][0], group, step_no)
+            if step_no is not None and gi in self.__dict__.get("_dev", {}):
+                self._dev_state(gi, group, self._dev[gi]["state"].device, step_no - 1)
         _WeightsEpoch.value += 1
 
     @torch.no_grad()
@@ -78,10 +103,9 @@ class FusedAdam(torch.optim.Optimizer):
                 shs.append(self._shadow(p))
             if ps:
                 if use_dev:
-                    host, dev = self._hyper_buffers(gi, ps[0].device)
-                    self._fill_hyper(host, group, step_no)
-                    dev.copy_(host, non_blocking=True)        # a memcpy node when the step is being captured
-                    I.adam_step_dev(ps, gs, ms, vs, shs, dev)
+                    rec = self._dev_state(gi, group, ps[0].device, step_no - 1)
+                    I.adam_advance(rec["state"], rec["hyper"])       # t += 1, bias corrections of step t (on device)
+                    I.adam_step_dev(ps, gs, ms, vs, shs, rec["hyper"])
                 else:
                     I.adam_step(ps, gs, ms, vs, shs, group["lr"], group["betas"][0], group["betas"][1], group["eps"],
                                 step_no)

@@ -154,10 +154,23 @@ def attach(model, bucket_mb=32.0, fused_wgrad=None):
     """Make a CycleGANModel data-parallel: broadcast rank 0's weights and buffers, then average
     gradients across ranks every step.  Returns the GradSync (also stored as ``model.grad_sync``)."""
     if dist.is_initialized() and dist.get_world_size() > 1:
+        if getattr(getattr(model, "opt", None), "norm", "instance") == "batch":
+            raise NotImplementedError("data parallelism with norm='batch': batch statistics would be per rank "
+                                      "(R ranks x b != batch R*b); use norm='instance' (the CycleGAN default)")
         for name in model.model_names:
             net = getattr(model, "net" + name)
             for t in list(net.parameters()) + list(net.buffers()):
                 dist.broadcast(_dense_view(t.data), src=0)
+            # the broadcast wrote through .data: neither ._version nor data_ptr() moved, so the conv modules' cached
+            # bf16 / transposed weight copies (and the Adam-maintained shadows) would still look valid -- a forward run
+            # before attach() would leave ranks != 0 computing their first step with pre-broadcast weights
+            for p in net.parameters():
+                p._mra_epoch = getattr(p, "_mra_epoch", 0) + 1
+                if hasattr(p, "_mra_shadow_tag"):
+                    p._mra_shadow_tag = None
+            for m in net.modules():
+                if isinstance(getattr(m, "_cache", None), dict):
+                    m._cache.clear()
     from . import networks3D
     # Default: every use of a weight hands autograd its own gradient, AccumulateGrad adds them into the bucket view.
     # fused_wgrad (MRA_DP_FUSED_WGRAD=1) keeps the single-process fusion instead: the wgrad kernels add every use

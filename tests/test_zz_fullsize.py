@@ -321,3 +321,45 @@ def test_halo_tail_items_share_a_sample_with_full_tiles():
     I = ops.impl()
     check_conv_layer(I, R.RefImpl(torch.float32), g, dims, 1, torch.bfloat16, "cuda", 1e-2, stats=True)
     assert I.tc_error() == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,dims", [(1, (42, 34, 18)), (2, (34, 34, 34)), (27, (4, 34, 18))])
+def test_halo_statistics_stay_inside_their_buffer(n, dims):
+    """Memory-safety canary for the epilogue statistics of gather_halo_kernel: the [N][Cn][2] fp64
+    block handed to mra_conv3d_fprop sits inside a larger buffer whose other words hold -0.0 -- a stray
+    ``atomicAdd(+0.0)`` turns that into +0.0, a stray real sum into anything else -- and every sample's sums must
+    equal the sums of the stored output (so nothing leaked into the NEXT sample's rows either).  (2, 34^3) is the
+    bench's G.rb launch: 256 pair tiles on 74 pairs, the last 34 split, the split falling inside the last sample;
+    (27, 4 x 34 x 18) has 108 tiles of 4 per sample, the last 34 split across samples 18..26."""
+    import ctypes as C
+
+    from mra_gan_b200 import _lib
+    I = ops.impl()
+    g = ConvGeom(256, 256, 3, 1, 0)
+    gen = torch.Generator().manual_seed(7)
+    x = torch.randn((n,) + dims + (256,), generator=gen).to(torch.bfloat16).cuda()
+    w = (torch.randn((27, 256, 256), generator=gen) * 0.02).to(torch.bfloat16).cuda()
+    out_dims = g.out_dims(dims)
+    y = torch.empty((n,) + out_dims + (256,), dtype=torch.bfloat16, device="cuda")
+    words, guard = n * 256 * 2, 4096
+    neg0 = torch.tensor([-0.0], dtype=torch.float64).view(torch.int64).item()
+    buf = torch.full((guard + words + guard,), -0.0, dtype=torch.float64, device="cuda")
+    stats = buf[guard:guard + words]
+    d = I._conv_desc(g, n, dims, out_dims, _lib.MRA_BF16)
+    _lib.check(I.L.mra_conv3d_fprop(C.byref(d), C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()), None,
+                                    C.c_void_p(y.data_ptr()), C.c_void_p(stats.data_ptr()), None, 0, I._stream()),
+               "mra_conv3d_fprop")
+    torch.cuda.synchronize()
+    assert I.tc_error() == 0
+    bits = buf.view(torch.int64)
+    assert bool((bits[:guard] == neg0).all()), "statistics flush wrote BEFORE its buffer"
+    assert bool((bits[guard + words:] == neg0).all()), "statistics flush wrote PAST its buffer"
+    # per-sample sums against the stored tensor (bf16-rounded output vs fp32 accumulators: loose on purpose, a leaked
+    # or lost tile is a >= 1/256 effect on sum of squares)
+    yf = y.double()
+    s1 = yf.sum(dim=(1, 2, 3))
+    s2 = (yf * yf).sum(dim=(1, 2, 3))
+    got = stats.view(n, 256, 2)
+    assert float((got[..., 1] - s2).abs().max() / s2.abs().max()) < 2e-3
+    assert float((got[..., 0] - s1).abs().max() / s2.sqrt().max()) < 2e-2
