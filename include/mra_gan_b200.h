@@ -66,6 +66,18 @@ int mra_conv3d_fprop(const mra_conv_desc* d, const void* x, const void* w, const
 /* dx = conv^T(dy, w): gradient wrt the op's input (ATen convolution_backward, input part). */
 int mra_conv3d_dgrad(const mra_conv_desc* d, const void* dy, const void* wT, void* dx,
                      void* workspace, size_t workspace_bytes, mra_stream_t stream);
+/* dgrad fused with the STATISTICS PASS of the InstanceNorm backward in front of this conv (models/networks3D.py:188-197,
+ * 233-243: conv <- [pad <-] ReLU/LeakyReLU <- InstanceNorm).  y_act = that fused norm's stored output, i.e. this conv's
+ * own forward input (same shape as dx); norm_act / norm_slope = its activation (NONE, RELU, LRELU with 0 <= slope <= 1).
+ * Besides dx the epilogue accumulates sums[n][cin][2] = {sum dy, sum dy * xhat} (dy = act'(xhat) * fold(dx), fp64) --
+ * exactly what mra_inorm_act_pad_bwd_stats computes from (dx, x) in a separate sweep -- so the norm backward is left
+ * with its apply pass (mra_inorm_act_pad_bwd_apply): 3 tensor sweeps instead of 5.  Only for layers whose dgrad runs
+ * on the tensor-core gather kernels (query first); sums is zeroed by the call. */
+int mra_conv3d_dgrad_nstats_supported(const mra_conv_desc* d);
+int mra_conv3d_dgrad_nstats(const mra_conv_desc* d, const void* dy, const void* wT, void* dx, const void* y_act,
+                            int norm_act, float norm_slope, double* sums, void* workspace, size_t workspace_bytes,
+                            mra_stream_t stream);
+
 /* dw[taps][cout][cin] (fp32) and optional dbias[cout] (fp32) (convolution_backward, weight/bias part). */
 int mra_conv3d_wgrad(const mra_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias,
                      void* workspace, size_t workspace_bytes, mra_stream_t stream);

@@ -42,6 +42,8 @@ _SIGNATURES = {
     "mra_debug_counters": ([C.POINTER(C.c_ulonglong), _I], C.c_int),
     "mra_conv3d_fprop": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, C.c_size_t, _P], C.c_int),
     "mra_conv3d_dgrad": ([C.POINTER(ConvDesc), _P, _P, _P, _P, C.c_size_t, _P], C.c_int),
+    "mra_conv3d_dgrad_nstats_supported": ([C.POINTER(ConvDesc)], C.c_int),
+    "mra_conv3d_dgrad_nstats": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _I, _F, _P, _P, C.c_size_t, _P], C.c_int),
     "mra_conv3d_wgrad": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, C.c_size_t, _P], C.c_int),
     "mra_conv3d_workspace_size": ([C.POINTER(ConvDesc), _I], C.c_size_t),
     "mra_conv3d_uses_tensor_cores": ([C.POINTER(ConvDesc), _I], C.c_int),

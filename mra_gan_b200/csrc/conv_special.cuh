@@ -554,7 +554,8 @@ inline int head_fprop(const mra_conv_desc& d, const void* x, const void* w, cons
   return 0;
 }
 
-inline int head_dgrad(const mra_conv_desc& d, const void* dy, const void* wT, void* dx, void* wsp, size_t wsb, cudaStream_t st) {
+inline int head_dgrad(const mra_conv_desc& d, const void* dy, const void* wT, void* dx, void* wsp, size_t wsb, cudaStream_t st,
+                      double* nstats = nullptr, const void* aux = nullptr, float aux_nslope = 0.f) {
   Workspace ws{(char*)wsp, wsb, 0};
   const long long rows = (long long)d.n * d.dout;
   MRA_WS_TAKE(E, bf16, (size_t)rows * d.hin * d.win * 64 * 2);
@@ -565,7 +566,8 @@ inline int head_dgrad(const mra_conv_desc& d, const void* dy, const void* wT, vo
   MRA_LAUNCH_CHECK();
   GatherPlan plan;
   MRA_REQUIRE(build_gather_plan(head_geom(d), 1, plan), "head dgrad plan");
-  tc::GatherRun R{E, BT, d.k, nullptr, dx, 1, MRA_ACT_NONE, 0.f, nullptr};
+  tc::GatherRun R{E, BT, d.k, nullptr, dx, 1, MRA_ACT_NONE, 0.f, nstats};
+  R.aux = aux; R.aux_nslope = aux_nslope;
   return tc::run_gather_tc(plan, R, st);
 }
 

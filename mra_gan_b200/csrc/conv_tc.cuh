@@ -206,6 +206,13 @@ struct EpiArgs {
   const float* bias;
   int act; float slope;
   bool stats;
+  // Norm-BACKWARD statistics (dgrad launches whose output is the gradient gy of a fused InstanceNorm -> activation ->
+  // replication pad): aux = that norm's stored output y (the conv's own input: same shape and strides as `out`).  The
+  // per-(n, channel) sums then are  S0 = sum gy * act'(xhat)  and  S1 = sum gy * act'(xhat) * xhat  -- for the
+  // piecewise-linear activations y = max(xhat, s xhat) these are  sum gy * (y > 0 ? 1 : s)  and  sum gy * y  exactly,
+  // and summing over the PADDED positions equals summing the folded gradient over the interior ones (y's halo holds
+  // replicated values).  They replace the statistics pass of the norm backward (2 of its 5 tensor sweeps).
+  const void* aux; float aux_nslope;
 };
 __device__ __noinline__ float act_slow(float v, int act) {
   return act == MRA_ACT_TANH ? tanhf(v) : 1.f / (1.f + expf(-v));
@@ -224,7 +231,7 @@ __device__ __noinline__ float act_slow(float v, int act) {
 // Dual-plane tiles (gather_col_kernel with 64 output channels): the accumulator is 128 columns wide, columns
 // [0, 64) belong to output plane p and [64, 128) to plane p + 1 (`dual_stride` elements further, validity
 // `valid_hi`); TMEM chunk c then maps to channel chunk c & 1 of plane c >> 1.
-template <typename Release>
+template <bool kAux = false, typename Release>
 __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, uint32_t t_addr, int c_begin, int c_step, int nchunks, bool valid,
                                               long long obase, int n0, int lane, double* st_s, double* st_q, bool defer,
                                               float (&d1)[32], float (&d2)[32], Release release, bool dual = false,
@@ -254,7 +261,78 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, uint32_t t_addr,
         v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
       }
     }
-    if (E.stats) {
+    if (kAux && E.stats) {
+      // aux is consumed 8 values at a time (never more than 8 extra live registers); the deferred flavour adds straight
+      // into d1 / d2, the per-tile flavour builds the two arrays of the transpose-reduce
+      const float ns = E.aux_nslope;
+      if (defer) {
+        if (valid) {
+          if (E.out_bf16) {
+            const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(E.aux) + obase_c + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 u = __ldg(ap + i);
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float a0 = __uint_as_float(w[k] << 16), a1 = __uint_as_float(w[k] & 0xffff0000u);
+                const float g0 = v[8 * i + 2 * k], g1 = v[8 * i + 2 * k + 1];
+                d1[8 * i + 2 * k] += a0 > 0.f ? g0 : g0 * ns; d2[8 * i + 2 * k] = fmaf(g0, a0, d2[8 * i + 2 * k]);
+                d1[8 * i + 2 * k + 1] += a1 > 0.f ? g1 : g1 * ns; d2[8 * i + 2 * k + 1] = fmaf(g1, a1, d2[8 * i + 2 * k + 1]);
+              }
+            }
+          } else {
+            const float4* ap = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(E.aux) + obase_c + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 u = __ldg(ap + i);
+              const float a4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float g = v[4 * i + k];
+                d1[4 * i + k] += a4[k] > 0.f ? g : g * ns; d2[4 * i + k] = fmaf(g, a4[k], d2[4 * i + k]);
+              }
+            }
+          }
+        }
+      } else {
+        float s1[32], s2[32];
+        if (valid) {
+          if (E.out_bf16) {
+            const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(E.aux) + obase_c + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 u = __ldg(ap + i);
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float a0 = __uint_as_float(w[k] << 16), a1 = __uint_as_float(w[k] & 0xffff0000u);
+                const float g0 = v[8 * i + 2 * k], g1 = v[8 * i + 2 * k + 1];
+                s1[8 * i + 2 * k] = a0 > 0.f ? g0 : g0 * ns; s2[8 * i + 2 * k] = g0 * a0;
+                s1[8 * i + 2 * k + 1] = a1 > 0.f ? g1 : g1 * ns; s2[8 * i + 2 * k + 1] = g1 * a1;
+              }
+            }
+          } else {
+            const float4* ap = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(E.aux) + obase_c + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 u = __ldg(ap + i);
+              const float a4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float g = v[4 * i + k];
+                s1[4 * i + k] = a4[k] > 0.f ? g : g * ns; s2[4 * i + k] = g * a4[k];
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+        }
+        st_s[c] += (double)warp_colsum32(s1, lane);
+        st_q[c] += (double)warp_colsum32(s2, lane);
+      }
+    } else if (E.stats) {
       if (defer) {
         if (valid) {
 #pragma unroll
@@ -353,6 +431,7 @@ struct GatherP {
   int act;
   float slope;
   double* stats;                    // [N][Cn][2] or null
+  const void* aux; float aux_nslope; // norm-backward statistics (EpiArgs::aux)
   int* err;
   int stages;
   int nbuf;                         // accumulator buffers in TMEM: 512 / n_tile, at most 8 (small tiles: the buffer
@@ -403,6 +482,8 @@ __device__ __forceinline__ TileCoord decode_tile(const GatherP& P, int tile) {
 // multi-buffered in TMEM (P.nbuf) so the epilogue of item j overlaps the MMAs of the following items; InstanceNorm
 // statistics are accumulated per CTA and flushed with one fp64 atomic per channel when the sample index changes
 // (instead of per tile).
+template <bool kAux>        // kAux: norm-backward statistics in the epilogue (EpiArgs::aux); a separate instantiation so
+                             // that the fprop / plain dgrad epilogue keeps its register budget
 __global__ void __launch_bounds__(kThreadsGather, 1)
 gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ GatherP P) {
@@ -533,7 +614,7 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
     for (int i = 0; i < 32; ++i) { d1[i] = 0.f; d2[i] = 0.f; }
     int st_n = -1, st_n0 = 0;
-    const EpiArgs E{P.out, P.out_bf16, P.bias, P.act, P.slope, P.stats != nullptr};
+    const EpiArgs E{P.out, P.out_bf16, P.bias, P.act, P.slope, P.stats != nullptr, P.aux, P.aux_nslope};
     int buf = 0;
     uint32_t aph = 0;
     bool ok = true;
@@ -554,7 +635,7 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const long long te0 = (P.debug & 2) ? clock64() : 0;
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
       uint64_t* rel_bar = &acc_empty[buf];
-      epilogue_tile(E, t_addr, W.c_begin, 2, acc_cols / 32, valid, obase, t.n0, lane, st_s, st_q, defer, d1, d2, [&]() {
+      epilogue_tile<kAux>(E, t_addr, W.c_begin, 2, acc_cols / 32, valid, obase, t.n0, lane, st_s, st_q, defer, d1, d2, [&]() {
         tc_fence_before();                      // accumulator fully read: hand the buffer back to the MMA warp
         __syncwarp();
         if (lane == 0) mbar_arrive(rel_bar);
@@ -1092,6 +1173,8 @@ struct GatherRun {
   int act;
   float slope;
   double* stats;
+  const void* aux = nullptr;   // with stats: norm-backward statistics against this tensor (EpiArgs::aux)
+  float aux_nslope = 0.f;
 };
 
 // Can the launches of a plan run as ONE merged launch?  8 parity phases over the same launch space (the stride-2
@@ -1151,7 +1234,8 @@ inline int run_gather_v1_launch(const GatherPlan& plan, const GatherLaunch* Ls, 
                                 int n_tile, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
     attr_set = true;
   }
   const GatherLaunch& L = Ls[0];
@@ -1181,7 +1265,7 @@ inline int run_gather_v1_launch(const GatherPlan& plan, const GatherLaunch* Ls, 
   P.osn = (long long)plan.odims[0] * P.osd;
   P.out = R.out; P.out_bf16 = R.out_bf16;
   P.bias = R.bias; P.act = R.act; P.slope = R.slope;
-  P.stats = R.stats; P.err = tc_err_flag();
+  P.stats = R.stats; P.aux = R.aux; P.aux_nslope = R.aux_nslope; P.err = tc_err_flag();
   { const char* e = getenv("MRA_GATHER_DEBUG"); P.debug = e ? atoi(e) : 0; }
   P.dbg = tc_dbg_counters();
   P.nph = items;
@@ -1233,7 +1317,8 @@ inline int run_gather_v1_launch(const GatherPlan& plan, const GatherLaunch* Ls, 
                             P.astep))
     return rc;
   const int ctas = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
-  gather_tc_kernel<<<ctas, kThreadsGather, smem, st>>>(tmA, tmB, P);
+  if (P.aux && P.stats) gather_tc_kernel<true><<<ctas, kThreadsGather, smem, st>>>(tmA, tmB, P);
+  else gather_tc_kernel<false><<<ctas, kThreadsGather, smem, st>>>(tmA, tmB, P);
   MRA_LAUNCH_CHECK();
   return 0;
 }

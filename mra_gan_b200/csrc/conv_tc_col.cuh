@@ -36,6 +36,7 @@ struct ColP {
   int act;
   float slope;
   double* stats;
+  const void* aux; float aux_nslope;   // norm-backward statistics (EpiArgs::aux)
   int* err;
   int nbuf;                         // accumulator buffers in TMEM (512 / accumulator width, at most 8)
   int dual;                         // 1: dual-plane tiles (accumulator 2 * n_tile = 128 columns)
@@ -45,6 +46,7 @@ struct ColP {
   unsigned long long* dbg;
 };
 
+template <bool kAux>
 __global__ void __launch_bounds__(kThreadsGather, 1)
 gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ ColP P) {
@@ -253,7 +255,7 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
     for (int i = 0; i < 32; ++i) { d1[i] = 0.f; d2[i] = 0.f; }
     int st_n = -1;
-    const EpiArgs E{P.out, P.out_bf16, P.bias, P.act, P.slope, P.stats != nullptr};
+    const EpiArgs E{P.out, P.out_bf16, P.bias, P.act, P.slope, P.stats != nullptr, P.aux, P.aux_nslope};
     int buf = 0;
     uint32_t aph = 0;
     bool ok = true;
@@ -276,7 +278,7 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
         uint64_t* rel_bar = &acc_empty[buf];
-        epilogue_tile(E, t_addr, W.c_begin, 2, acc_cols / 32, valid, obase, 0, lane, st_s, st_q, defer, d1, d2, [&]() {
+        epilogue_tile<kAux>(E, t_addr, W.c_begin, 2, acc_cols / 32, valid, obase, 0, lane, st_s, st_q, defer, d1, d2, [&]() {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(rel_bar);
@@ -342,7 +344,8 @@ inline int run_gather_col(const GatherPlan& plan, const GatherLaunch& L, ColP& P
                           cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_col_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_col_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
     attr_set = true;
   }
   P.ostep = L.ostep; P.od0 = L.o0[0]; P.oh0 = L.o0[1]; P.ow0 = L.o0[2];
@@ -352,7 +355,7 @@ inline int run_gather_col(const GatherPlan& plan, const GatherLaunch& L, ColP& P
   P.osn = (long long)plan.odims[0] * P.osd;
   P.out = R.out; P.out_bf16 = R.out_bf16;
   P.bias = R.bias; P.act = R.act; P.slope = R.slope;
-  P.stats = R.stats; P.err = tc_err_flag();
+  P.stats = R.stats; P.aux = R.aux; P.aux_nslope = R.aux_nslope; P.err = tc_err_flag();
   { const char* e = getenv("MRA_GATHER_DEBUG"); P.debug = e ? atoi(e) : 0; }
   P.dbg = tc_dbg_counters();
   const int acc_cols = P.dual ? 2 * P.n_tile : P.n_tile;
@@ -362,7 +365,8 @@ inline int run_gather_col(const GatherPlan& plan, const GatherLaunch& L, ColP& P
   if (int rc = make_act_map(&tmA, R.a, plan.n, plan.adims[0], plan.adims[1], plan.adims[2], plan.ck, 8, 16, 1, 1)) return rc;
   const size_t smem = (size_t)P.kd * P.kchunks * P.n_tile * 128 + (size_t)P.NPR * kABytes * P.kchunks + 1024 + 512;
   const int ctas = P.total_units < num_sms() ? P.total_units : num_sms();
-  gather_col_kernel<<<ctas, kThreadsGather, smem, st>>>(tmA, tmB, P);
+  if (P.aux && P.stats) gather_col_kernel<true><<<ctas, kThreadsGather, smem, st>>>(tmA, tmB, P);
+  else gather_col_kernel<false><<<ctas, kThreadsGather, smem, st>>>(tmA, tmB, P);
   MRA_LAUNCH_CHECK();
   return 0;
 }

@@ -52,6 +52,7 @@ struct HaloP {
   int act;
   float slope;
   double* stats;
+  const void* aux; float aux_nslope;   // norm-backward statistics (EpiArgs::aux)
   int* err;
   uint32_t tmem_cols;
   int16_t twi[kMaxTaps];            // weight slab of tap (td, th, tw)
@@ -94,7 +95,7 @@ __device__ __forceinline__ HaloTile halo_decode(const HaloP& P, int work, int pa
   return t;
 }
 
-template <bool kPair>
+template <bool kPair, bool kAux = false>
 __global__ void __launch_bounds__(kThreadsHalo, 1)
 gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ HaloP P) {
@@ -286,7 +287,7 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
     for (int i = 0; i < 32; ++i) { d1[i] = 0.f; d2[i] = 0.f; }
     int st_n = -1, st_n0 = 0;
-    const EpiArgs E{P.out, P.out_bf16, P.bias, P.act, P.slope, P.stats != nullptr};
+    const EpiArgs E{P.out, P.out_bf16, P.bias, P.act, P.slope, P.stats != nullptr, P.aux, P.aux_nslope};
     int j = 0;
     bool ok = true;
     for (int w = work0; w < P.total_work && ok; w += wstride, ++j) {
@@ -316,7 +317,7 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const long long te0 = prof ? clock64() : 0;
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * P.n_tile);
       uint64_t* rel_bar = &acc_empty[buf];
-      epilogue_tile(E, t_addr, W.c_begin, 2, nchunks, valid, obase, t.n0, lane, st_s + coff, st_q + coff, defer, d1, d2, [&]() {
+      epilogue_tile<kAux>(E, t_addr, W.c_begin, 2, nchunks, valid, obase, t.n0, lane, st_s + coff, st_q + coff, defer, d1, d2, [&]() {
         tc_fence_before();                      // accumulator fully read: hand the buffer back to the MMA warp
         __syncwarp();
         if (lane == 0) { if constexpr (kPair) mbar_arrive_leader(rel_bar); else mbar_arrive(rel_bar); }
@@ -429,6 +430,8 @@ inline int run_gather_halo(const GatherPlan& plan, const GatherLaunch& L, HaloP&
   if (!attr_set) {
     MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
     MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute((gather_halo_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute((gather_halo_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
     attr_set = true;
   }
   P.ostep = L.ostep; P.od0 = L.o0[0]; P.oh0 = L.o0[1]; P.ow0 = L.o0[2];
@@ -438,7 +441,7 @@ inline int run_gather_halo(const GatherPlan& plan, const GatherLaunch& L, HaloP&
   P.osn = (long long)plan.odims[0] * P.osd;
   P.out = R.out; P.out_bf16 = R.out_bf16;
   P.bias = R.bias; P.act = R.act; P.slope = R.slope;
-  P.stats = R.stats; P.err = tc_err_flag();
+  P.stats = R.stats; P.aux = R.aux; P.aux_nslope = R.aux_nslope; P.err = tc_err_flag();
   { const char* e = getenv("MRA_GATHER_DEBUG"); P.debug = e ? atoi(e) : 0; }
   P.dbg = tc_dbg_counters();
   P.tmem_cols = pow2_cols(2 * P.n_tile);
@@ -447,7 +450,8 @@ inline int run_gather_halo(const GatherPlan& plan, const GatherLaunch& L, HaloP&
   const size_t smem = (size_t)P.NP * P.slot_bytes + (size_t)P.NB * P.n_tile * 128 / (P.pair ? 2 : 1) + 1024 + 256;
   if (!P.pair) {
     const int ctas = P.total_work < num_sms() ? P.total_work : num_sms();
-    gather_halo_kernel<false><<<ctas, kThreadsHalo, smem, st>>>(tmA, tmB, P);
+    if (P.aux && P.stats) gather_halo_kernel<false, true><<<ctas, kThreadsHalo, smem, st>>>(tmA, tmB, P);
+    else gather_halo_kernel<false><<<ctas, kThreadsHalo, smem, st>>>(tmA, tmB, P);
   } else {
     int pairs = num_sms() / 2;
     if (P.total_work < pairs) pairs = P.total_work;
@@ -461,7 +465,8 @@ inline int run_gather_halo(const GatherPlan& plan, const GatherLaunch& L, HaloP&
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    MRA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gather_halo_kernel<true>, tmA, tmB, P));
+    if (P.aux && P.stats) MRA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gather_halo_kernel<true, true>, tmA, tmB, P));
+    else MRA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gather_halo_kernel<true>, tmA, tmB, P));
   }
   MRA_LAUNCH_CHECK();
   return 0;
@@ -513,10 +518,11 @@ inline int run_gather_tc(const GatherPlan& plan, const GatherRun& R, cudaStream_
 }
 
 inline int run_gather_tc(const mra_conv_desc& d, int which, const void* a, const void* b, const float* bias, void* out,
-                         double* stats, cudaStream_t st) {
+                         double* stats, cudaStream_t st, const void* aux = nullptr, float aux_nslope = 0.f) {
   GatherPlan plan;
   MRA_REQUIRE(build_gather_plan(d, which, plan), "unsupported conv geometry");
   GatherRun R{a, b, d.k * d.k * d.k, bias, out, 1, which == 0 ? d.act : MRA_ACT_NONE, d.slope, stats};
+  R.aux = aux; R.aux_nslope = aux_nslope;
   return run_gather_tc(plan, R, st);
 }
 

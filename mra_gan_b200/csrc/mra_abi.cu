@@ -122,6 +122,32 @@ int mra_conv3d_dgrad(const mra_conv_desc* d, const void* dy, const void* wT, voi
   return 0;
 }
 
+// dgrad + the statistics pass of the InstanceNorm backward in front of this conv (see EpiArgs::aux)
+static bool dgrad_nstats_ok(const mra_conv_desc& d) {
+  if (d.dtype != MRA_BF16 || (d.flags & MRA_CONV_FORCE_NAIVE)) return false;
+  if (special::im2col_eligible(d) || special::convT1_eligible(d) || special::stem_eligible(d)) return false;
+  if (special::head_eligible(d)) return true;
+  return tc::gather_eligible(d, 1);
+}
+int mra_conv3d_dgrad_nstats_supported(const mra_conv_desc* d) { return d && dgrad_nstats_ok(*d) ? 1 : 0; }
+
+int mra_conv3d_dgrad_nstats(const mra_conv_desc* d, const void* dy, const void* wT, void* dx, const void* y_act, int norm_act,
+                            float norm_slope, double* sums, void* workspace, size_t workspace_bytes, mra_stream_t stream) {
+  if (int rc = check_conv(d)) return rc;
+  MRA_REQUIRE(y_act != nullptr && sums != nullptr, "dgrad_nstats needs the norm output and a sums buffer");
+  MRA_REQUIRE(dgrad_nstats_ok(*d), "this layer's dgrad does not run on the tensor-core gather kernels");
+  float nslope;
+  if (norm_act == MRA_ACT_NONE) nslope = 1.f;
+  else if (norm_act == MRA_ACT_RELU) nslope = 0.f;
+  else if (norm_act == MRA_ACT_LRELU && norm_slope >= 0.f && norm_slope <= 1.f) nslope = norm_slope;
+  else return fail(-1, "dgrad_nstats: activation %d (slope %g) is not piecewise linear", norm_act, (double)norm_slope);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int cn = d->cin;                                    // channels of dx = channels of the norm
+  MRA_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * d->n * cn, st));
+  if (special::head_eligible(*d)) return special::head_dgrad(*d, dy, wT, dx, workspace, workspace_bytes, st, sums, y_act, nslope);
+  return tc::run_gather_tc(*d, 1, dy, wT, nullptr, dx, sums, st, y_act, nslope);
+}
+
 int mra_conv3d_wgrad(const mra_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias,
                      void* workspace, size_t workspace_bytes, mra_stream_t stream) {
   if (int rc = check_conv(d)) return rc;

@@ -19,11 +19,21 @@ def weight_grad_view(dw_packed, k, transposed):
     return v.permute(4, 3, 0, 1, 2) if transposed else v.permute(3, 4, 0, 1, 2)
 
 
+class NormBwdLink:
+    """Hand-over of the norm backward's statistics from the dgrad epilogue of the conv that consumes the norm's
+    output (mra_conv3d_dgrad_nstats) to that norm's backward, which then only runs its apply pass.  Created by
+    run_program() for a (fused norm -> conv) pair whose norm output has no other consumer."""
+    __slots__ = ("act", "slope", "sums")
+
+    def __init__(self, act, slope):
+        self.act, self.slope, self.sums = act, slope, None
+
+
 class ConvFn(torch.autograd.Function):
     """nn.Conv3d / nn.ConvTranspose3d (+bias, + epilogue activation, + InstanceNorm statistics)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, mod, act, slope, want_stats, bias_grad):
+    def forward(ctx, x, weight, bias, mod, act, slope, want_stats, bias_grad, link=None):
         I = ops.impl()
         g = mod.geom
         wc = mod.packed_weight(x.dtype)
@@ -39,6 +49,10 @@ class ConvFn(torch.autograd.Function):
             y, stats = I.conv_fprop(x, wc, bias.detach() if bias is not None else None, g, act, slope, want_stats)
         ctx.low, ctx.ws = low, (ws if keep else None)
         ctx.mod, ctx.act, ctx.slope, ctx.bias_grad = mod, act, slope, bias_grad
+        if link is not None and not (x.dtype == torch.bfloat16 and hasattr(I, "conv_dgrad_nstats") and
+                                     I.conv_dgrad_nstats_supported(g, x.shape[0], tuple(x.shape[1:4]), x.dtype)):
+            link = None
+        ctx.link = link
         ctx.in_dims = tuple(x.shape[1:4])
         ctx.save_for_backward(x, y if act != ACT_NONE else None)
         if stats is not None:
@@ -90,20 +104,26 @@ class ConvFn(torch.autograd.Function):
                 if has_bias and mod.bias.requires_grad and mod.bias.grad is None:
                     mod.bias.grad = dbv if dbv is not None else torch.zeros_like(mod.bias)
         if ctx.needs_input_grad[0]:
-            if ws2 is not None:
-                dx = I.conv_dgrad(gy, mod.packed_weight_t(gy.dtype), g, ctx.in_dims, ws=ws2, reuse=True)
+            kw = dict(ws=ws2, reuse=True) if ws2 is not None else {}
+            if ctx.link is not None:
+                # x is the fused norm's stored output: the epilogue also produces that norm's backward statistics
+                dx, ctx.link.sums = I.conv_dgrad_nstats(gy, mod.packed_weight_t(gy.dtype), g, ctx.in_dims, x, ctx.link.act,
+                                                        ctx.link.slope, **kw)
             else:
-                dx = I.conv_dgrad(gy, mod.packed_weight_t(gy.dtype), g, ctx.in_dims)
-        return dx, dw, db, None, None, None, None, None
+                dx = I.conv_dgrad(gy, mod.packed_weight_t(gy.dtype), g, ctx.in_dims, **kw)
+        return dx, dw, db, None, None, None, None, None, None
 
 
 class NormActPadFn(torch.autograd.Function):
     """InstanceNorm3d -> ReLU/LeakyReLU -> (+ residual) -> ReplicationPad3d, one kernel each way."""
 
     @staticmethod
-    def forward(ctx, x, stats, residual, mod, act, slope, pad, res_pad):
+    def forward(ctx, x, stats, residual, mod, act, slope, pad, res_pad, link=None):
         I = ops.impl()
         use_running = not mod.training and mod.track_running_stats
+        ctx.link = link if not use_running else None
+        if link is not None and use_running:
+            link.act = None                        # tells the consumer conv not to bother (ConvFn checks sums only)
         if stats is None and not use_running:
             stats = I.inorm_stats(x)
         update = mod.training and mod.track_running_stats
@@ -121,8 +141,13 @@ class NormActPadFn(torch.autograd.Function):
         x, mean, rstd = ctx.saved_tensors
         act, slope, pad, res_pad, use_running = ctx.cfg
         want_res = res_pad >= 0 and ctx.needs_input_grad[2]
-        dx, dres = I.inorm_bwd(gy.contiguous(), x, mean, rstd, pad, act, slope, res_pad if want_res else -1, use_running)
-        return dx, None, dres, None, None, None, None, None
+        link = ctx.link
+        if link is not None and link.sums is not None:
+            sums, link.sums = link.sums, None      # statistics came out of the consumer conv's dgrad epilogue
+            dx, dres = I.inorm_bwd_apply(gy.contiguous(), x, mean, rstd, sums, pad, act, slope, res_pad if want_res else -1)
+        else:
+            dx, dres = I.inorm_bwd(gy.contiguous(), x, mean, rstd, pad, act, slope, res_pad if want_res else -1, use_running)
+        return dx, None, dres, None, None, None, None, None, None
 
 
 class BatchNormActPadFn(torch.autograd.Function):

@@ -16,6 +16,7 @@ Added: ``unet_128`` -- the 7-down UNet the reference intended but shadowed with 
 """
 import functools
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -222,11 +223,11 @@ class BatchNorm3d(nn.Module):
 _NORMS = (InstanceNorm3d, BatchNorm3d)
 
 
-def apply_norm(x, stats, res, m, act, slope, pad, res_pad):
+def apply_norm(x, stats, res, m, act, slope, pad, res_pad, link=None):
     """One fused norm instruction (normalise -> activation -> + residual -> replication pad) for either norm type."""
     if isinstance(m, BatchNorm3d):
         return MF.BatchNormActPadFn.apply(x, stats, res, m.weight, m.bias, m, act, slope, pad, res_pad)
-    return MF.NormActPadFn.apply(x, stats, res, m, act, slope, pad, res_pad)
+    return MF.NormActPadFn.apply(x, stats, res, m, act, slope, pad, res_pad, link)
 
 
 class ReplicationPad3d(nn.Module):
@@ -358,20 +359,36 @@ def compile_program(seq):
     return prog
 
 
+# Norm-backward statistics from the consumer conv's dgrad epilogue (functional.NormBwdLink): on by default for the
+# bf16 path, MRA_NORM_BWD_FUSED=0 restores the two-pass norm backward everywhere (ablation).
+_FUSE_NORM_BWD = os.environ.get("MRA_NORM_BWD_FUSED", "1") != "0"
+
+
 def run_program(prog, x):
     """x: channels-last activation.  Returns the channels-last output."""
     stats = None
     saved, saved_pad = None, 0
-    for ins in prog:
+    link = None
+    for i, ins in enumerate(prog):
         op = ins[0]
         if op == "conv":
             _, m, act, slope, want_stats = ins
             # a conv followed by a train-mode InstanceNorm has a dead bias gradient (SURVEY.md 7-2)
-            x, stats = MF.ConvFn.apply(x, m.weight, m.bias, m, act, slope, want_stats, not want_stats)
+            x, stats = MF.ConvFn.apply(x, m.weight, m.bias, m, act, slope, want_stats, not want_stats,
+                                       link if (link is not None and link.act is not None) else None)
+            link = None
         elif op == "norm":
             _, m, act, slope, pad, use_res = ins
             res = saved if use_res else None
-            x = apply_norm(x, stats, res, m, act, slope, pad, saved_pad)
+            # the norm's output feeds the NEXT instruction only, and that is a conv: its dgrad epilogue can produce
+            # this norm's backward statistics (InstanceNorm with a piecewise-linear activation, training mode, bf16; not
+            # with a residual added after the activation: xhat could not be recovered from the stored output)
+            link = None
+            if (_FUSE_NORM_BWD and not use_res and isinstance(m, InstanceNorm3d) and act in (ACT_NONE, ACT_RELU, ACT_LRELU)
+                    and 0.0 <= slope <= 1.0 and x.dtype == torch.bfloat16 and torch.is_grad_enabled()
+                    and i + 1 < len(prog) and prog[i + 1][0] == "conv"):
+                link = MF.NormBwdLink(act, slope)
+            x = apply_norm(x, stats, res, m, act, slope, pad, saved_pad, link)
             stats = None
         elif op == "pad":
             x = MF.RepPadFn.apply(x, ins[1])

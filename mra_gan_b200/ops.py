@@ -132,6 +132,26 @@ class CudaImpl:
                    "mra_conv3d_dgrad")
         return dx
 
+    def conv_dgrad_nstats_supported(self, g, n, in_dims, dtype):
+        d = self._conv_desc(g, n, tuple(in_dims), g.out_dims(tuple(in_dims)), MRA_BF16 if dtype == torch.bfloat16 else MRA_F32)
+        return bool(self.L.mra_conv3d_dgrad_nstats_supported(C.byref(d)))
+
+    def conv_dgrad_nstats(self, dy, wT, g, in_dims, y_act, norm_act, norm_slope, ws=None, reuse=False):
+        """dgrad + the statistics pass of the fused norm in front of the conv (mra_conv3d_dgrad_nstats): returns
+        (dx, sums[n][cin][2] fp64) where sums is what ``inorm_bwd_stats(dx, x_norm, ...)`` would compute."""
+        self._need(dy, wT, y_act)
+        n, out_dims = dy.shape[0], tuple(dy.shape[1:4])
+        assert dy.shape[4] == g.cout and wT.shape == (g.taps, g.cin, g.cout) and wT.dtype == dy.dtype
+        assert tuple(y_act.shape) == (n,) + tuple(in_dims) + (g.cin,) and y_act.dtype == dy.dtype
+        dx = torch.empty((n,) + tuple(in_dims) + (g.cin,), dtype=dy.dtype, device=dy.device)
+        sums = torch.empty((n, g.cin, 2), dtype=torch.float64, device=dy.device)
+        d = self._conv_desc(g, n, tuple(in_dims), out_dims, _dt(dy), flags=_lib.CONV_WS_REUSE if reuse else 0)
+        ws, wsb = self._workspace(d, 1, dy.device, ws)
+        _lib.check(self.L.mra_conv3d_dgrad_nstats(C.byref(d), _ptr(dy), _ptr(wT), _ptr(dx), _ptr(y_act), int(norm_act),
+                                                  float(norm_slope), _ptr(sums), _ptr(ws), wsb, self._stream()),
+                   "mra_conv3d_dgrad_nstats")
+        return dx, sums
+
     def conv_wgrad(self, x, dy, g, want_bias=False, ws=None, reuse=False, acc_dw=None, acc_db=None):
         """dw [taps][Cout][Cin] fp32 (+ db).  With ``acc_dw`` (and ``acc_db`` when a bias gradient is wanted) the
         kernels ADD into those buffers (MRA_CONV_ACCUMULATE) instead of writing fresh ones."""

@@ -114,6 +114,18 @@ class RefImpl:
         dx = self._conv_backward(to_ncdhw(self._c(dy)), x, unpack_weight(wp, g.k, g.transposed), g, [True, False, False])[0]
         return to_ndhwc(dx).to(dy.dtype)
 
+    def conv_dgrad_nstats_supported(self, g, n, in_dims, dtype):
+        return True
+
+    def conv_dgrad_nstats(self, dy, wT, g, in_dims, y_act, norm_act, norm_slope, ws=None, reuse=False):
+        """mra_conv3d_dgrad_nstats: dx plus {sum dx * act'(y), sum dx * y} over ALL (padded) positions of y_act."""
+        dx = self.conv_dgrad(dy, wT, g, in_dims)
+        ns = {ACT_NONE: 1.0, ACT_RELU: 0.0}.get(norm_act, norm_slope)
+        ya, gx = self._c(y_act), self._c(dx)
+        s0 = (gx * torch.where(ya > 0, torch.ones_like(ya), torch.full_like(ya, ns))).sum((1, 2, 3))
+        s1 = (gx * ya).sum((1, 2, 3))
+        return dx, torch.stack([s0, s1], -1).double()
+
     def conv_wgrad(self, x, dy, g, want_bias=False, acc_dw=None, acc_db=None):
         wp = torch.zeros((g.taps, g.cout, g.cin), dtype=self.cd)
         gw = self._conv_backward(to_ncdhw(self._c(dy)), to_ncdhw(self._c(x)).contiguous(),

@@ -281,6 +281,88 @@ def test_adam_matches_torch_optim():
             assert torch.equal(s.cpu(), a.cpu().to(torch.bfloat16))
 
 
+NSTATS = [
+    # geom, in_dims (= shape of the norm's stored output), N, norm act, slope      -> kernel
+    (ConvGeom(256, 256, 3, 1, 0), (10, 10, 10), 2, 1, 0.0),             # res-block conv2 dgrad: gather_halo (2D / flat tiles)
+    (ConvGeom(256, 256, 3, 1, 0), (34, 34, 34), 2, 1, 0.0),             # the same at config-2 size (split tail items)
+    (ConvGeom(64, 128, 3, 2, 1), (16, 16, 16), 2, 1, 0.0),              # G.d1 dgrad: merged phases, paired (n_tile 64)
+    (ConvGeom(64, 128, 3, 2, 1), (128, 128, 128), 1, 1, 0.0),           # ... at full size (64 ch x 128^3)
+    (ConvGeom(128, 256, 3, 2, 1), (16, 16, 16), 2, 1, 0.0),             # G.d2 dgrad: merged 8 phases
+    (ConvGeom(128, 64, 3, 2, 1, True, 1), (8, 8, 8), 2, 1, 0.0),        # G.u2 dgrad (ConvTranspose3d): strided gather
+    (ConvGeom(64, 1, 7, 1, 0), (22, 22, 22), 2, 1, 0.0),                # head dgrad: column kernel, dual planes
+    (ConvGeom(128, 256, 4, 2, 1), (16, 16, 16), 2, 2, 0.2),             # D.3 dgrad, LeakyReLU(0.2)
+    (ConvGeom(256, 512, 4, 1, 1), (9, 9, 9), 2, 2, 0.2),                # D.4 dgrad (zero-padded stride 1)
+    (ConvGeom(256, 256, 3, 1, 0), (10, 10, 10), 1, 0, 0.0),             # no activation between norm and conv
+]
+
+
+@pytest.mark.parametrize("case", NSTATS, ids=lambda c: "%d-%d_k%ds%d%s_%s_n%d_act%d" % (
+    c[0].cin, c[0].cout, c[0].k, c[0].stride, "T" if c[0].transposed else "", "x".join(map(str, c[1])), c[2], c[3]))
+def test_conv_dgrad_norm_backward_statistics(case):
+    """mra_conv3d_dgrad_nstats: dx is bit-identical to the plain dgrad, and sums[n][c] = {sum dx act'(y), sum dx y}
+    over every (padded) position -- what the statistics pass of the norm backward computes from (dx, x) -- here checked
+    in fp64 from the stored dx (bf16) and y."""
+    g, dims, n, act, slope = case
+    I = ops.impl()
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    out_dims = g.out_dims(dims)
+    dy = torch.randn((n,) + out_dims + (g.cout,), generator=gen, device="cuda").to(torch.bfloat16)
+    w = (torch.randn((g.taps, g.cout, g.cin), generator=gen, device="cuda") / (g.taps * g.cout) ** 0.5).to(torch.bfloat16)
+    wT = I.pack_weight_t(w, torch.bfloat16)
+    xh = torch.randn((n,) + dims + (g.cin,), generator=gen, device="cuda")
+    ns = {0: 1.0, 1: 0.0}.get(act, slope)
+    y = torch.where(xh > 0, xh, xh * ns).to(torch.bfloat16)
+    assert I.conv_dgrad_nstats_supported(g, n, dims, torch.bfloat16)
+    low, ws = I.conv_shared_workspace(g, n, dims, torch.bfloat16, "cuda")
+    kw = dict(ws=ws) if low else {}
+    dx_ref = I.conv_dgrad(dy, wT, g, dims, **kw)
+    dx, sums = I.conv_dgrad_nstats(dy, wT, g, dims, y, act, slope, **kw)
+    assert I.tc_error() == 0
+    assert torch.equal(dx, dx_ref)
+    d64, y64 = dx.double(), y.double()
+    wgt = torch.where(y64 > 0, torch.ones_like(y64), torch.full_like(y64, ns))
+    s0, s1 = (d64 * wgt).sum((1, 2, 3)), (d64 * y64).sum((1, 2, 3))
+    a0, a1 = (d64 * wgt).abs().sum((1, 2, 3)), (d64 * y64).abs().sum((1, 2, 3))
+    cnt = dx[0, ..., 0].numel()
+    # the epilogue sums the fp32 accumulators, the check the bf16-rounded stores: |diff| <= 2^-9 * sum|term| / sqrt(count)
+    # statistically; a lost or doubled tile would be >= 1 / tiles of sum|term|
+    tol = lambda a: 4 * 2.0 ** -9 * a / cnt ** 0.5 + 1e-6 * a + 1e-9
+    assert bool(((sums[..., 0] - s0).abs() <= tol(a0)).all()), float(((sums[..., 0] - s0).abs() / a0).max())
+    assert bool(((sums[..., 1] - s1).abs() <= tol(a1)).all()), float(((sums[..., 1] - s1).abs() / a1).max())
+
+
+def test_norm_backward_with_statistics_from_the_dgrad_epilogue_matches_two_pass():
+    """End to end through autograd: (InstanceNorm -> ReLU -> pad) -> conv with the NormBwdLink (statistics from the conv's
+    dgrad epilogue, apply pass only) against the same program with MRA_NORM_BWD_FUSED off (two-pass norm backward)."""
+    from mra_gan_b200 import networks3D as N3
+    N3.set_default_compute_dtype(torch.bfloat16)
+    torch.manual_seed(0)
+    seq = torch.nn.Sequential(N3.Conv3d(64, 256, 3, 1, 1), N3.InstanceNorm3d(256), N3.ReLU(True), N3.ReplicationPad3d(1),
+                              N3.Conv3d(256, 256, 3, 1, 0), N3.InstanceNorm3d(256), N3.ReLU(True),
+                              N3.Conv3d(256, 128, 3, 2, 1)).cuda()
+    prog = N3.compile_program(seq)
+    x = torch.randn(2, 12, 12, 12, 64, device="cuda").to(torch.bfloat16)
+    outs = []
+    for fused in (True, False):
+        N3._FUSE_NORM_BWD = fused
+        try:
+            for p in seq.parameters():
+                p.grad = None
+            xi = x.clone().requires_grad_(True)
+            n0 = ops.impl().launch_count()
+            y = N3.run_program(prog, xi)
+            y.float().square().mean().backward()
+            outs.append((xi.grad.float(), [p.grad.float().clone() for p in seq.parameters() if p.grad is not None],
+                         ops.impl().launch_count() - n0))
+        finally:
+            N3._FUSE_NORM_BWD = True
+    assert outs[0][2] == outs[1][2] - 2                     # two statistics launches fewer
+    assert rel_l2(outs[0][0], outs[1][0]) < 5e-3
+    for a, b in zip(outs[0][1], outs[1][1]):
+        if float(b.abs().max()) > 0:
+            assert rel_l2(a, b) < 5e-3
+
+
 def test_fused_adam_graph_replay_runs_ahead_of_the_device():
     """VERDICT r1 weak #3 / ADVICE (medium): the captured optimiser step must advance by exactly ONE Adam step per
     replay even when the host runs many replays ahead of the device (no sync in between; a busy-wait kernel in front
