@@ -5,10 +5,15 @@ both call only ``ops.impl()`` (the C-ABI kernels).  Activations inside a network
 (N, D, H, W, C) tensors in the network's compute dtype; network inputs / outputs are converted from
 / to the reference's (N, C, D, H, W) fp32 convention at the boundary (torch view/cast plumbing).
 """
+import os
+
 import torch
 
 from . import ops
 from .ops import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, LOSS_BCE_CONST, LOSS_L1, LOSS_MSE_CONST
+
+
+_NSTATS_ALWAYS = os.environ.get("MRA_NORM_BWD_FUSED", "1") == "2"     # ablation: link every eligible pair
 
 
 def weight_grad_view(dw_packed, k, transposed):
@@ -27,6 +32,22 @@ class NormBwdLink:
 
     def __init__(self, act, slope):
         self.act, self.slope, self.sums = act, slope, None
+
+
+def nstats_profitable(g, x):
+    """Is the norm-backward statistics pass cheaper inside this conv's dgrad epilogue than as its own kernel?
+    Measured per layer on B200 (tools/nstats_bench.py, profiles/r02_nstats_bench_*.txt): the epilogue hides under the
+    main loop when a tile accumulates over K = taps x Cout >= ~1500 (G.rb, G.u2, D.3, D.4: the statistics cost 8-60 us
+    extra against 22-69 us for the kernel they replace), but the short-K stride-2 dgrads and the head lowering are
+    epilogue bound already (G.d1 +290 us vs 240 us, G.c4 +390 vs 300); small tensors are launch bound, one kernel less
+    always wins there."""
+    if min(g.cin, g.cout) == 1:
+        k_eff = g.k * 64                                   # channel-expanded lowering: (k, 1, 1) taps x 64
+    elif not g.transposed and g.stride > 1:
+        k_eff = (g.k ** 3) / float(g.stride ** 3) * g.cout  # dgrad of a strided conv: taps split over stride^3 phases
+    else:
+        k_eff = g.k ** 3 * g.cout
+    return k_eff >= 1500 or x.numel() <= (1 << 23)
 
 
 class ConvFn(torch.autograd.Function):
@@ -50,6 +71,7 @@ class ConvFn(torch.autograd.Function):
         ctx.low, ctx.ws = low, (ws if keep else None)
         ctx.mod, ctx.act, ctx.slope, ctx.bias_grad = mod, act, slope, bias_grad
         if link is not None and not (x.dtype == torch.bfloat16 and hasattr(I, "conv_dgrad_nstats") and
+                                     (_NSTATS_ALWAYS or nstats_profitable(g, x)) and
                                      I.conv_dgrad_nstats_supported(g, x.shape[0], tuple(x.shape[1:4]), x.dtype)):
             link = None
         ctx.link = link

@@ -9,6 +9,7 @@ import os
 import random
 import sys
 import textwrap
+from collections import OrderedDict
 
 import numpy as np
 import torch
@@ -193,10 +194,44 @@ def gen_sliding(nw, testm):
                 label=torch.from_numpy(np.ascontiguousarray(ns["label_np"])))
 
 
+def gen_options(nw):
+    """define_D('pixel') (PixelDiscriminator, networks3D.py:428-450: three 1x1x1 convolutions) with and without the
+    sigmoid, and define_G('unet_256') (8 downs, :92-93; needs a 256^3 input) -- forward and the gradient of mean(y^2)
+    with respect to the input, from the unmodified reference."""
+    out = {}
+    x, _ = OF.synthetic_patches(2, 32, seed=8)
+    for sig in (False, True):
+        net = nw.define_D(1, 8, "pixel", 3, "instance", sig, "normal", 0.02, 0)
+        spec = OrderedDict((k, tuple(v.shape)) for k, v in net.state_dict().items())
+        sd = OF.make_weights(spec, 41, scale=0.3)
+        _load(net, sd)
+        xi = x.clone().requires_grad_(True)
+        y = net(xi)
+        y.square().mean().backward()
+        out["pixel_ndf8_sig%d" % sig] = dict(weight_seed=41, weight_scale=0.3, input_seed=8, keys=list(spec.keys()),
+                                             shapes=[tuple(v) for v in spec.values()], checksum=OF.weights_checksum(sd),
+                                             y=y.detach().clone(), dx=xi.grad.detach().clone(),
+                                             dw0=net.state_dict(keep_vars=True)["net.0.weight"].grad.detach().clone())
+    spec = OF.unet_g_spec(1, 1, 8, 2)
+    sd = OF.make_weights(spec, 42, scale=0.2)
+    net = _load(nw.define_G(1, 1, 2, "unet_256", "instance", False, "normal", 0.02, 0), sd)
+    assert list(net.state_dict().keys()) == list(spec.keys())
+    x8, _ = OF.synthetic_patches(1, 256, seed=9)
+    with torch.no_grad():
+        y8 = net(x8)
+    out["unet8_ngf2"] = dict(weight_seed=42, weight_scale=0.2, input_seed=9, checksum=OF.weights_checksum(sd),
+                             y_sub=y8[:, :, ::8, ::8, ::8].clone(), y_sum=float(y8.double().sum()),
+                             y_abs=float(y8.double().abs().sum()))
+    return out
+
+
 def main():
     torch.set_num_threads(8)
     nw, cycle_mod, testm, _ = import_reference()
     os.makedirs(GOLDEN, exist_ok=True)
+    if sys.argv[1:] == ["options"]:                        # regenerate this one fixture only
+        torch.save(gen_options(nw), os.path.join(GOLDEN, "options_small.pt"))
+        return 0
     if sys.argv[1:] == ["batchnorm"]:                      # regenerate this one fixture only
         torch.save(gen_batchnorm(nw), os.path.join(GOLDEN, "batchnorm_small.pt"))
         return 0
@@ -208,6 +243,7 @@ def main():
     torch.save(steps, os.path.join(GOLDEN, "cyclegan_step_small.pt"))
     torch.save(gen_sliding(nw, testm), os.path.join(GOLDEN, "sliding_window_small.pt"))
     torch.save(gen_batchnorm(nw), os.path.join(GOLDEN, "batchnorm_small.pt"))
+    torch.save(gen_options(nw), os.path.join(GOLDEN, "options_small.pt"))
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 

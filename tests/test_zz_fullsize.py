@@ -116,8 +116,12 @@ def check_conv_layer(I, ref, g, dims, n, dtype, dev, tol, act=ACT_NONE, stats=Tr
     assert bool(torch.isfinite(y.float()).all())
     if stats:
         yd = y.double()
-        assert rel_l2(cpu(st[..., 0]), cpu(yd.sum((1, 2, 3)))) < 1e-3, "epilogue sum"
-        assert rel_l2(cpu(st[..., 1]), cpu((yd * yd).sum((1, 2, 3)))) < 1e-3, "epilogue sum of squares"
+        # the statistics come from the fp32 accumulators, the check sums the STORED tensor: in bf16 the two differ by
+        # the rounding of y (2^-9 rms per element), which averages out only over many positions per channel
+        npos = lay.odims[0] * lay.odims[1] * lay.odims[2]
+        stol = 1e-3 if (dtype != torch.bfloat16 or npos >= 512) else 4e-3
+        assert rel_l2(cpu(st[..., 0]), cpu(yd.sum((1, 2, 3)))) < stol, "epilogue sum"
+        assert rel_l2(cpu(st[..., 1]), cpu((yd * yd).sum((1, 2, 3)))) < stol, "epilogue sum of squares"
         del yd
     if not g.transposed:
         xpad = _pad_cl(x, lay.lo, lay.hi)
@@ -230,6 +234,38 @@ def test_checker_rejects_an_indexing_error(case, which):
 @pytest.mark.parametrize("name", list(FULL_LAYERS))
 def test_conv_full_size(name):
     g, dims, act, stats = FULL_LAYERS[name]
+    I = ops.impl()
+    for which in range(3):
+        assert I.conv_uses_tensor_cores(g, 2, dims, torch.bfloat16, which), "tcgen05 path expected"
+    check_conv_layer(I, R.RefImpl(torch.float32), g, dims, 2, torch.bfloat16, "cuda", 1e-2, act=act, stats=stats)
+    assert I.tc_error() == 0
+    torch.cuda.empty_cache()
+
+
+# UNet-7 (= the intended unet_128, BASELINE config 4) at ngf = 64 on a 128^3 patch: models/networks3D.py:270-343.
+# 7 x Conv3d(k4, s2, p1, no bias) 128^3 -> 1^3 and 7 x ConvTranspose3d(k4, s2, p1) back.
+UNET7_LAYERS = {
+    "U.d1": (ConvGeom(1, 64, 4, 2, 1), (128,) * 3, ACT_NONE, False),              # outermost down: no norm (:312-314)
+    "U.d2": (ConvGeom(64, 128, 4, 2, 1), (64,) * 3, ACT_NONE, True),
+    "U.d3": (ConvGeom(128, 256, 4, 2, 1), (32,) * 3, ACT_NONE, True),
+    "U.d4": (ConvGeom(256, 512, 4, 2, 1), (16,) * 3, ACT_NONE, True),
+    "U.d5": (ConvGeom(512, 512, 4, 2, 1), (8,) * 3, ACT_NONE, True),
+    "U.d6": (ConvGeom(512, 512, 4, 2, 1), (4,) * 3, ACT_NONE, True),
+    "U.d7": (ConvGeom(512, 512, 4, 2, 1), (2,) * 3, ACT_RELU, False),             # innermost: 2^3 -> 1^3, ReLU, no norm (:319-321)
+    "U.u7": (ConvGeom(512, 512, 4, 2, 1, True, 0), (1,) * 3, ACT_NONE, True),     # innermost up: 1^3 -> 2^3
+    "U.u6": (ConvGeom(1024, 512, 4, 2, 1, True, 0), (2,) * 3, ACT_NONE, True),
+    "U.u5": (ConvGeom(1024, 512, 4, 2, 1, True, 0), (4,) * 3, ACT_NONE, True),
+    "U.u4": (ConvGeom(1024, 256, 4, 2, 1, True, 0), (8,) * 3, ACT_NONE, True),
+    "U.u3": (ConvGeom(512, 128, 4, 2, 1, True, 0), (16,) * 3, ACT_NONE, True),
+    "U.u2": (ConvGeom(256, 64, 4, 2, 1, True, 0), (32,) * 3, ACT_NONE, True),
+    "U.u1": (ConvGeom(128, 1, 4, 2, 1, True, 0), (64,) * 3, ACT_TANH, False),     # outermost up (+ bias, Tanh) (:312-316)
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(UNET7_LAYERS))
+def test_unet7_conv_full_size(name):
+    g, dims, act, stats = UNET7_LAYERS[name]
     I = ops.impl()
     for which in range(3):
         assert I.conv_uses_tensor_cores(g, 2, dims, torch.bfloat16, which), "tcgen05 path expected"
