@@ -83,6 +83,13 @@ def make_opt(**kw):
 
 WORKLOAD = ("resnet_9blocks G + 3-layer PatchGAN D, ngf=ndf=64, LSGAN, one CycleGAN optimize_parameters() on "
             "synthetic 128^3 patches")
+# --workload unet = BASELINE config 4 (the 7-down UNet as both generators), --workload infer = config 5 (sliding window)
+WORKLOAD_UNET = ("unet_128 (7-down UNet) G + 3-layer PatchGAN D, ngf=ndf=64, LSGAN, one CycleGAN optimize_parameters() "
+                 "on synthetic 128^3 patches (BASELINE config 4)")
+WORKLOAD_INFER = ("sliding-window G_A inference (test.py path): resnet_9blocks ngf=64 over a synthetic 256x256x160 volume, "
+                  "128^3 windows, stride %d/%d = %d windows sharded over the ranks, one reduce to rank 0 (BASELINE config 5)")
+FLOP_PER_SAMPLE_STEP_UNET = 5.245e12
+G_FWD_FLOP_PER_WINDOW = 2.619e12        # resnet_9blocks forward on one 128^3 window (1309.7 GMAC)
 
 
 def default_batch(world):
@@ -90,12 +97,14 @@ def default_batch(world):
     return 2 if world == 1 else 4
 
 
-def workload_config(world, per_gpu_batch, launch):
+def workload_config(world, per_gpu_batch, launch, workload="train"):
     """The `config` object of the JSON line -- the SAME for this framework's arm and for --impl reference (whose steps
     are a bounded CPU sample of this workload, described in its cpu_baseline.sample)."""
-    return {"workload": WORKLOAD, "patch": PATCH, "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * world,
-            "parallelism": "dp%d" % world, "l2": "per-step working set (tens of GB) >> 126 MB L2",
-            "launch": launch, "model_tflop_per_sample_step": FLOP_PER_SAMPLE_STEP / 1e12}
+    unet = workload == "unet"
+    return {"workload": WORKLOAD_UNET if unet else WORKLOAD, "patch": PATCH, "per_gpu_batch": per_gpu_batch,
+            "global_batch": per_gpu_batch * world, "parallelism": "dp%d" % world,
+            "l2": "per-step working set (tens of GB) >> 126 MB L2", "launch": launch,
+            "model_tflop_per_sample_step": (FLOP_PER_SAMPLE_STEP_UNET if unet else FLOP_PER_SAMPLE_STEP) / 1e12}
 
 
 def launch_mode(world, no_graphs=False):
@@ -281,9 +290,12 @@ def run_gpu(args):
     random.seed(1234 + rank)
     import contextlib
     import io
+    unet = args.workload == "unet"
+    flop_per_sample = FLOP_PER_SAMPLE_STEP_UNET if unet else FLOP_PER_SAMPLE_STEP
+    netG = "unet_128" if unet else "resnet_9blocks"
     with contextlib.redirect_stdout(io.StringIO()):
-        model = create_model(make_opt())
-        model.setup(make_opt())
+        model = create_model(make_opt(netG=netG))
+        model.setup(make_opt(netG=netG))
     I = ops.impl()
     if world > 1:
         parallel.attach(model)
@@ -358,6 +370,7 @@ def run_gpu(args):
     if rank != 0:
         return 0
 
+    sync_stats = dict(model.grad_sync.stats) if getattr(model, "grad_sync", None) is not None else None
     peaks, peak_src = load_peaks()
     k_ms, k_flops = time_dominant_kernel(torch, I, per_gpu_batch)
     norm_roof = time_norm_kernels(torch, I, per_gpu_batch, float(peaks.get("hbm_gbs", 6650.0)))
@@ -367,12 +380,12 @@ def run_gpu(args):
         "metric": "cyclegan_train_voxels_per_sec", "value": vox, "unit": "voxels/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": workload_config(world, per_gpu_batch, launch),
+        "config": workload_config(world, per_gpu_batch, launch, args.workload),
         "e2e": {"value": vox_e2e, "unit": "voxels/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 8 * 4, "ms_per_step": ms_e2e},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "model_tflops": global_batch * FLOP_PER_SAMPLE_STEP / (ms_step * 1e-3) / 1e12,
+        "model_tflops": global_batch * flop_per_sample / (ms_step * 1e-3) / 1e12,
         "roofline": {"bound": "tensor", "kernel": "gather_halo_kernel (Conv3d 256->256 k3 fprop, 34^3->32^3, batch %d)" % per_gpu_batch,
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "peak_source": peak_src + " bf16_tflops (burst: kernel timed alone)", "ms_per_launch": k_ms,
@@ -381,7 +394,10 @@ def run_gpu(args):
         "roofline_hbm": norm_roof,
         "tc_error_flag": err,
     }
-    if world == 1 and not args.no_anchor and not args.batch:
+    if sync_stats is not None:
+        line["grad_sync"] = dict(sync_stats, fused_wgrad=os.environ.get("MRA_DP_FUSED_WGRAD", "0") == "1",
+                                 skip_allreduce=os.environ.get("MRA_DP_SKIP_ALLREDUCE", "0") == "1")
+    if world == 1 and not args.no_anchor and not args.batch and not unet:
         # the weak-scaling anchor: the SAME program the N > 1 runs execute (config 3's per-GPU batch and launch mode)
         # on one GPU, so that value(N) / (N * anchor.value) compares like with like
         model._graphs = None
@@ -403,6 +419,109 @@ def run_gpu(args):
     return 0
 
 
+def run_infer(args):
+    """BASELINE config 5: the test.py sliding-window path on a synthetic 256 x 256 x 160 volume; a "step" is one whole
+    volume.  value = volume voxels / s with the volume resident on the device, e2e = volume handed over from pinned
+    host memory and the result read back to the host."""
+    import contextlib
+    import io
+
+    import torch
+    import torch.distributed as dist
+
+    from mra_gan_b200 import networks3D as N3
+    from mra_gan_b200 import ops, parallel
+    from mra_gan_b200.inference import sliding_window_inference, window_grid
+    from mra_gan_b200.models import create_model
+
+    rank, world = parallel.init_distributed()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    N3.set_default_compute_dtype(torch.bfloat16)
+    I = ops.impl()
+    ck = "/tmp/mra_cfg5_%d" % rank
+    os.makedirs(ck + "/cfg5", exist_ok=True)
+    opt = make_opt(isTrain=False, model="test", model_suffix="", checkpoints_dir=ck, name="cfg5")
+    with contextlib.redirect_stdout(io.StringIO()):
+        torch.manual_seed(7)                                  # same weights on every rank
+        g = N3.define_G(1, 1, 64, "resnet_9blocks", "instance")
+        torch.save({k: v.detach().cpu().contiguous() for k, v in g.state_dict().items()}, ck + "/cfg5/latest_net_G.pth")
+        del g
+        tm = create_model(opt)
+        tm.setup(opt)
+    shape, patch, stride = (256, 256, 160), (128, 128, 128), args.stride
+    host_vol = (torch.rand(shape, generator=torch.Generator().manual_seed(1234)) * 255).pin_memory()
+    dev_vol = host_vol.cuda()
+    nwin = len(window_grid(shape, patch, stride, stride))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    out = {}
+
+    def step_resident():
+        out["v"] = sliding_window_inference(tm, dev_vol, patch, stride, stride, rank, world, dtype=torch.bfloat16)
+
+    def step_e2e():
+        r = sliding_window_inference(tm, host_vol, patch, stride, stride, rank, world, dtype=torch.bfloat16)
+        if rank == 0:
+            out["h"] = r.cpu()
+
+    for _ in range(max(args.warmup, 1)):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = I.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = (I.launch_count() - l0) // args.steps
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if sampler else None
+    err = I.tc_error()
+    check = None
+    if rank == 0 and world > 1:                                # the sharded result against this rank running every window
+        ref = sliding_window_inference(tm, dev_vol, patch, stride, stride, 0, 1, dtype=torch.bfloat16)
+        check = float((out["v"] - ref).abs().max())
+    if world > 1:
+        barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return 0
+    nvox = shape[0] * shape[1] * shape[2]
+    my_windows = len(range(0, nwin, world))
+    line = {
+        "metric": "sliding_window_volume_voxels_per_sec", "value": nvox / (ms * 1e-3), "unit": "voxels/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD_INFER % (stride, stride, nwin), "volume": list(shape), "window": list(patch),
+                   "stride": stride, "windows": nwin, "windows_on_rank0": my_windows, "parallelism": "windows round-robin over %d rank(s)" % world,
+                   "l2": "each window's activations (GBs) >> 126 MB L2", "launch": "eager"},
+        "window_voxels_per_sec": nwin * patch[0] ** 3 / (ms * 1e-3),
+        "model_tflops": nwin * G_FWD_FLOP_PER_WINDOW / (ms * 1e-3) / 1e12,
+        "e2e": {"value": nvox / (ms_e2e * 1e-3), "unit": "voxels/s", "h2d_bytes_per_step": nvox * 4,
+                "d2h_bytes_per_step": nvox * 4, "ms_per_step": ms_e2e},
+        "gpu_launches": int(launches), "clocks": clocks, "tc_error_flag": err,
+        "sharded_vs_single_max_abs": check,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -413,9 +532,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-anchor", action="store_true", help="skip the batch-4 single-GPU anchor measurement (N=1 only)")
     ap.add_argument("--no-graphs", action="store_true", help="run the step eagerly (no CUDA-graph replay)")
+    ap.add_argument("--workload", default="train", choices=["train", "unet", "infer"],
+                    help="train = BASELINE configs 2/3 (the headline metric), unet = config 4, infer = config 5")
+    ap.add_argument("--stride", type=int, default=32, help="--workload infer: window stride (reference default 32)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "infer":
+        return run_infer(args)
     return run_gpu(args)
 
 

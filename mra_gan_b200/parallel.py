@@ -64,6 +64,8 @@ class GradSync:
         self.bucket_elems = int(bucket_mb * 1024 * 1024 / 4)
         self.phases = {name: self._build(nets) for name, nets in phases.items()}
         self.active = None
+        # ablation only (bench: how much of a step is exposed communication): gradients are NOT averaged
+        self.skip = os.environ.get("MRA_DP_SKIP_ALLREDUCE", "0") == "1"
         self.stats = {"buckets": sum(len(b) for b in self.phases.values()), "allreduce_calls": 0, "late_launches": 0}
 
     def _build(self, nets):
@@ -102,7 +104,7 @@ class GradSync:
 
     def _launch(self, bucket):
         bucket.launched = True
-        if self.world > 1:
+        if self.world > 1 and not self.skip:
             op = dist.ReduceOp.AVG if self.use_avg else dist.ReduceOp.SUM
             bucket.work = dist.all_reduce(bucket.flat, op=op, group=self.group, async_op=True)
             self.stats["allreduce_calls"] += 1
