@@ -146,6 +146,15 @@ int mra_act_bwd(const void* dy, const void* y, void* dx, int64_t numel, int act,
  * keep mask (one byte per element, 0 / 1); pass scale = 1 / (1 - p).  The backward is the same call on the gradient. */
 int mra_mask_scale(const void* x, const unsigned char* keep, void* y, int64_t numel, float scale,
                    int dtype, mra_stream_t stream);
+/* UNet skip connection (models/networks3D.py:339-343 torch.cat([x, model(x)], 1) + the parent's ReLU(True) :319,326):
+ * out[pos][0:ca] = act(a[pos][:]), out[pos][ca:ca+cb] = act(b[pos][:]) for `positions` channels-last positions -- both
+ * halves written into one buffer, no concat copy.  bwd: da = dout[:, 0:ca] * act'(.), db = dout[:, ca:] * act'(.) with
+ * act' taken from the stored output (NONE / RELU / LRELU); da or db may be null. */
+int mra_cat2_act_fwd(const void* a, const void* b, void* out, int64_t positions, int ca, int cb, int act, float slope,
+                     int dtype, mra_stream_t stream);
+int mra_cat2_act_bwd(const void* dout, const void* out, void* da, void* db, int64_t positions, int ca, int cb, int act,
+                     float slope, int dtype, mra_stream_t stream);
+
 /* nn.ReplicationPad3d forward/backward on its own (models/networks3D.py:185,211 when the producer
  * is not a norm): y = pad(x); dx = fold_pad(gy). */
 int mra_reppad_fwd(const void* x, void* y, int n, int d, int h, int w, int c, int pad, int dtype,

@@ -57,6 +57,8 @@ _SIGNATURES = {
     "mra_inorm_act_pad_bwd_apply": ([C.POINTER(NormDesc), _P, _P, _P, _P, _P, _P, _P, _P], C.c_int),
     "mra_act_fwd": ([_P, _P, _L, _I, _F, _I, _P], C.c_int),
     "mra_act_bwd": ([_P, _P, _P, _L, _I, _F, _I, _P], C.c_int),
+    "mra_cat2_act_fwd": ([_P, _P, _P, _L, _I, _I, _I, _F, _I, _P], C.c_int),
+    "mra_cat2_act_bwd": ([_P, _P, _P, _P, _L, _I, _I, _I, _F, _I, _P], C.c_int),
     "mra_mask_scale": ([_P, _P, _P, _L, _F, _I, _P], C.c_int),
     "mra_reppad_fwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "mra_reppad_bwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),

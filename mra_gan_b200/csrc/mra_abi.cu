@@ -289,6 +289,32 @@ int mra_act_bwd(const void* dy, const void* y, void* dx, int64_t numel, int act,
   return 0;
 }
 
+int mra_cat2_act_fwd(const void* a, const void* b, void* out, int64_t positions, int ca, int cb, int act, float slope, int dtype,
+                     mra_stream_t stream) {
+  MRA_REQUIRE(a && b && out && ca > 0 && cb > 0, "mra_cat2_act_fwd: bad arguments");
+  if (positions <= 0) return 0;
+  const bool v8 = dtype == MRA_BF16 && ca % 8 == 0 && cb % 8 == 0;
+  const int vec = v8 ? 8 : 1;
+  const long long items = positions * (long long)((ca + cb) / vec);
+  if (v8) cat2_act_fwd_kernel<bf16, 8><<<ew_grid(items, 1), 256, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b, (bf16*)out, items, ca / 8, cb / 8, act, slope);
+  else DISPATCH_DTYPE(dtype, (cat2_act_fwd_kernel<T, 1><<<ew_grid(items), 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b, (T*)out, items, ca, cb, act, slope)));
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+int mra_cat2_act_bwd(const void* dout, const void* out, void* da, void* db, int64_t positions, int ca, int cb, int act, float slope,
+                     int dtype, mra_stream_t stream) {
+  MRA_REQUIRE(dout && out && (da || db) && ca > 0 && cb > 0, "mra_cat2_act_bwd: bad arguments");
+  MRA_REQUIRE(act == MRA_ACT_NONE || act == MRA_ACT_RELU || act == MRA_ACT_LRELU, "mra_cat2_act_bwd: activation %d", act);
+  if (positions <= 0) return 0;
+  const bool v8 = dtype == MRA_BF16 && ca % 8 == 0 && cb % 8 == 0;
+  const int vec = v8 ? 8 : 1;
+  const long long items = positions * (long long)((ca + cb) / vec);
+  if (v8) cat2_act_bwd_kernel<bf16, 8><<<ew_grid(items, 1), 256, 0, (cudaStream_t)stream>>>((const bf16*)dout, (const bf16*)out, (bf16*)da, (bf16*)db, items, ca / 8, cb / 8, act, slope);
+  else DISPATCH_DTYPE(dtype, (cat2_act_bwd_kernel<T, 1><<<ew_grid(items), 256, 0, (cudaStream_t)stream>>>((const T*)dout, (const T*)out, (T*)da, (T*)db, items, ca, cb, act, slope)));
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+
 int mra_mask_scale(const void* x, const unsigned char* keep, void* y, int64_t numel, float scale, int dtype,
                    mra_stream_t stream) {
   if (numel <= 0) return 0;

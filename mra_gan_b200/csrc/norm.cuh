@@ -372,6 +372,62 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const T* __restrict__ dy, 
     dx[i] = from_f<T>(to_f(dy[i]) * act_grad_from_output(to_f(y[i]), act, slope));
 }
 
+// UNet skip connection (networks3D.py:339-343: torch.cat([x, self.model(x)], 1), followed in the parent block by the
+// up-path's ReLU(True), :319,326): both halves are written straight into ONE channels-last buffer with the activation
+// applied on the way -- out[pos][0:ca] = act(a[pos]), out[pos][ca:ca+cb] = act(b[pos]) -- instead of a concat copy plus
+// an activation pass; the backward splits dout the same way with act'(.) taken from the stored output.
+// One thread moves VEC consecutive channels (16 bytes for bf16 / VEC = 8); ca, cb are multiples of VEC.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) cat2_act_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out,
+                                                            long long items, int ga, int gb, int act, float slope) {
+  const int g = ga + gb;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+    const long long pos = i / g;
+    const int cg = (int)(i - pos * g);
+    const T* src = cg < ga ? a + (pos * ga + cg) * VEC : b + (pos * gb + (cg - ga)) * VEC;
+    T v[VEC];
+    if (VEC == 8 && sizeof(T) == 2) *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(src);
+    else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) v[j] = src[j];
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) v[j] = from_f<T>(apply_act(to_f(v[j]), act, slope));
+    T* dst = out + i * VEC;
+    if (VEC == 8 && sizeof(T) == 2) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
+    else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) dst[j] = v[j];
+    }
+  }
+}
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) cat2_act_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ out, T* __restrict__ da,
+                                                            T* __restrict__ db, long long items, int ga, int gb, int act, float slope) {
+  const int g = ga + gb;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+    const long long pos = i / g;
+    const int cg = (int)(i - pos * g);
+    T gv[VEC], yv[VEC];
+    if (VEC == 8 && sizeof(T) == 2) {
+      *reinterpret_cast<uint4*>(gv) = *reinterpret_cast<const uint4*>(dout + i * VEC);
+      *reinterpret_cast<uint4*>(yv) = *reinterpret_cast<const uint4*>(out + i * VEC);
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) { gv[j] = dout[i * VEC + j]; yv[j] = out[i * VEC + j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) gv[j] = from_f<T>(to_f(gv[j]) * act_grad_from_output(to_f(yv[j]), act, slope));
+    T* dst = cg < ga ? (da ? da + (pos * ga + cg) * VEC : nullptr) : (db ? db + (pos * gb + (cg - ga)) * VEC : nullptr);
+    if (!dst) continue;
+    if (VEC == 8 && sizeof(T) == 2) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(gv);
+    else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) dst[j] = gv[j];
+    }
+  }
+}
+
 // nn.Dropout (networks3D.py:244-245, 332-333): y = x * keep / (1 - p).  The keep mask (one byte per element) comes from
 // the caller's RNG; the same kernel is its own backward (dx = gy * keep / (1 - p)).
 template <typename T>

@@ -274,6 +274,24 @@ class ActFn(torch.autograd.Function):
         return ops.impl().act_bwd(gy.contiguous(), y, *ctx.cfg), None, None
 
 
+class CatActFn(torch.autograd.Function):
+    """act(torch.cat([a, b], channel axis)) in one pass (the UNet skip concat + the parent block's ReLU)."""
+
+    @staticmethod
+    def forward(ctx, a, b, act, slope):
+        out = ops.impl().cat2_act_fwd(a.contiguous(), b.contiguous(), act, slope)
+        ctx.cfg = (a.shape[4], act, slope)
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (out,) = ctx.saved_tensors
+        ca, act, slope = ctx.cfg
+        da, db = ops.impl().cat2_act_bwd(gout.contiguous(), out, ca, act, slope, (ctx.needs_input_grad[0], ctx.needs_input_grad[1]))
+        return da, db, None, None
+
+
 class RepPadFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, pad):

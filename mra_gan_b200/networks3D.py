@@ -708,13 +708,14 @@ class UnetSkipConnectionBlock(nn.Module):
         self.model = nn.Sequential(*model)
 
     def run(self, x):
-        """x: channels-last.  Non-outermost blocks return cat([LeakyReLU(x), up(...)]) on the channel
-        axis -- the skip carries the activated tensor (in-place quirk of the reference)."""
+        """x: channels-last.  A non-outermost block returns the PAIR (LeakyReLU(x), up(...)) whose channel concat is the
+        reference's output (networks3D.py:339-343) -- the skip carries the activated tensor (in-place quirk of the
+        reference).  The only consumer of that concat is the parent's up-path ReLU(True) + ConvTranspose3d, so the
+        parent writes ReLU(cat(.)) straight into one buffer (functional.CatActFn: no torch.cat, no separate ReLU)."""
         m = self.model
         if self.outermost:
             d, _ = MF.ConvFn.apply(x, m[0].weight, m[0].bias, m[0], ACT_NONE, 0.0, False, True)
-            u = m[1].run(d)
-            u = MF.ActFn.apply(u, ACT_RELU, 0.0)
+            u = MF.CatActFn.apply(*m[1].run(d), ACT_RELU, 0.0)
             y, _ = MF.ConvFn.apply(u, m[3].weight, m[3].bias, m[3], ACT_TANH, 0.0, False, True)
             return y
         xs = MF.ActFn.apply(x, ACT_LRELU, m[0].slope)
@@ -726,13 +727,12 @@ class UnetSkipConnectionBlock(nn.Module):
         else:
             d, st = MF.ConvFn.apply(xs, m[1].weight, m[1].bias, m[1], ACT_NONE, 0.0, True, False)
             d = apply_norm(d, st, None, m[2], ACT_NONE, 0.0, 0, -1)
-            u = m[3].run(d)
-            u = MF.ActFn.apply(u, ACT_RELU, 0.0)
+            u = MF.CatActFn.apply(*m[3].run(d), ACT_RELU, 0.0)
             u, st = MF.ConvFn.apply(u, m[5].weight, m[5].bias, m[5], ACT_NONE, 0.0, True, False)
             u = apply_norm(u, st, None, m[6], ACT_NONE, 0.0, 0, -1)
             if len(m) > 7 and m[7].training and m[7].p > 0:
                 u = MF.DropoutFn.apply(u, m[7].p)
-        return torch.cat([xs, u], 4)
+        return xs, u
 
     def forward(self, x):
         raise RuntimeError("UnetSkipConnectionBlock is executed through UnetGenerator.forward")

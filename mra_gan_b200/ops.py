@@ -281,6 +281,25 @@ class CudaImpl:
                    "mra_act_bwd")
         return dx
 
+    def cat2_act_fwd(self, a, b, act, slope=0.0):
+        """out[..., :Ca] = act(a), out[..., Ca:] = act(b): the UNet skip concat with the following activation fused."""
+        self._need(a, b)
+        assert a.shape[:4] == b.shape[:4] and a.dtype == b.dtype
+        ca, cb = a.shape[4], b.shape[4]
+        out = torch.empty(tuple(a.shape[:4]) + (ca + cb,), dtype=a.dtype, device=a.device)
+        _lib.check(self.L.mra_cat2_act_fwd(_ptr(a), _ptr(b), _ptr(out), a.numel() // ca, ca, cb, act, slope, _dt(a),
+                                           self._stream()), "mra_cat2_act_fwd")
+        return out
+
+    def cat2_act_bwd(self, dout, out, ca, act, slope=0.0, want=(True, True)):
+        self._need(dout, out)
+        cb = out.shape[4] - ca
+        da = torch.empty(tuple(out.shape[:4]) + (ca,), dtype=out.dtype, device=out.device) if want[0] else None
+        db = torch.empty(tuple(out.shape[:4]) + (cb,), dtype=out.dtype, device=out.device) if want[1] else None
+        _lib.check(self.L.mra_cat2_act_bwd(_ptr(dout), _ptr(out), _ptr(da), _ptr(db), out.numel() // (ca + cb), ca, cb, act,
+                                           slope, _dt(out), self._stream()), "mra_cat2_act_bwd")
+        return da, db
+
     def mask_scale(self, x, keep, scale):
         """y = x * keep * scale (dropout forward, and its own backward on the gradient); keep: uint8 0 / 1."""
         self._need(x, keep)

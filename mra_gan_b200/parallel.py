@@ -46,6 +46,13 @@ def _dense_view(t):
     return v
 
 
+def _slot(numel, align=64):
+    """Elements a parameter occupies in its flat bucket: every view starts on a 256-byte boundary, so the wgrad
+    kernels' 16-byte vector reductions (red.global.add.v4.f32, fused_wgrad mode) and the Adam sweep stay aligned
+    whatever odd-sized tensors (1-element biases) precede it; the padding stays zero and rides along in the all-reduce."""
+    return (numel + align - 1) // align * align
+
+
 class _Bucket:
     __slots__ = ("flat", "params", "pending", "work", "launched")
 
@@ -81,14 +88,13 @@ class GradSync:
             buckets.append(cur)
         out = []
         for plist in buckets:
-            flat = torch.zeros(sum(p.numel() for p in plist), dtype=torch.float32, device=plist[0].device)
+            flat = torch.zeros(sum(_slot(p.numel()) for p in plist), dtype=torch.float32, device=plist[0].device)
             off = 0
             b = _Bucket(flat, plist)
             for p in plist:
-                n = p.numel()
                 # a view with the parameter's (packed) strides so AccumulateGrad adds in place
                 p.grad = torch.as_strided(flat, p.shape, p.stride(), off)
-                off += n
+                off += _slot(p.numel())
                 p.register_post_accumulate_grad_hook(self._make_hook(b))
             out.append(b)
         return out
@@ -131,7 +137,7 @@ class GradSync:
         b.flat.zero_()
         for p in b.params:
             p.grad = torch.as_strided(b.flat, p.shape, p.stride(), off)
-            off += p.numel()
+            off += _slot(p.numel())
 
     def finish(self, phase):
         """Issue any bucket whose parameters did not all receive a gradient, then wait."""

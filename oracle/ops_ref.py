@@ -227,6 +227,15 @@ class RefImpl:
     def act_bwd(self, dy, y, act, slope=0.2):
         return (self._c(dy) * _act_grad_from_output(self._c(y), act, slope)).to(dy.dtype)
 
+    def cat2_act_fwd(self, a, b, act, slope=0.0):
+        return _act(torch.cat([self._c(a), self._c(b)], 4), act, slope).contiguous().to(a.dtype)
+
+    def cat2_act_bwd(self, dout, out, ca, act, slope=0.0, want=(True, True)):
+        g = self._c(dout) * _act_grad_from_output(self._c(out), act, slope)
+        da = g[..., :ca].contiguous().to(out.dtype) if want[0] else None
+        db = g[..., ca:].contiguous().to(out.dtype) if want[1] else None
+        return da, db
+
     def mask_scale(self, x, keep, scale):
         return (self._c(x) * keep.to(self.cd) * scale).to(x.dtype)
 

@@ -145,6 +145,34 @@ def test_resnet_ngf64_tensor_core_path():
     assert OF.rel_l2(xin.grad.cpu(), xr.grad) < 1.5 * f_x + 2e-2
 
 
+def _emulated_bf16_step(opt, r, A, B):
+    """The same optimisation step on the CPU oracle ops with bf16 STORAGE between kernels: the deviation of its losses
+    and gradient norms from the reference's fp32 values is the floor any bf16 implementation of the step sits on."""
+    from mra_gan_b200.models import base_model
+    from oracle.ops_ref import RefImpl
+    prev = ops.set_impl(RefImpl(torch.float32))
+    saved = (N3.device, base_model.device)
+    try:
+        N3.device = base_model.device = torch.device("cpu")
+        random.seed(1234)
+        m = create_model(opt)
+        m.setup(opt)
+        for net, sd in zip((m.netG_A, m.netG_B, m.netD_A, m.netD_B),
+                           OF.build_cyclegan_weights(r["ngf"], r["ndf"], seed=r["weight_seed"], netG=r["netG"])):
+            _load(net, sd)
+        m.set_input([A, B])
+        m.optimize_parameters()
+        named = {"G_A": dict(m.netG_A.named_parameters()), "D_A": dict(m.netD_A.named_parameters())}
+        norms = {}
+        for key in r["steps"][0]["grads"]:
+            net, pk = key.split(".", 1)
+            norms[key] = float(named[net][pk].grad.double().norm())
+        return m.get_current_losses(), norms
+    finally:
+        N3.device, base_model.device = saved
+        ops.set_impl(prev)
+
+
 @pytest.mark.parametrize("case", ["lsgan", "bce", "lsgan_b2", "unet5"])
 def test_cyclegan_step_matches_golden(golden_dir, case, mode, tmp_path):
     r = torch.load(os.path.join(golden_dir, "cyclegan_step_small.pt"), weights_only=False)[case]
@@ -162,13 +190,22 @@ def test_cyclegan_step_matches_golden(golden_dir, case, mode, tmp_path):
     m.optimize_parameters()
     got = m.get_current_losses()
     ltol, atol = (1e-3, 1e-4) if mode == "fp32" else (5e-2, 4e-2)
+    gtol = 5e-3
+    if mode == "bf16":
+        # whole-step bf16 tolerances = 1.5 x the measured bf16-storage floor (CPU oracle ops, bf16 between kernels) + a
+        # small absolute term, instead of a fixed loose bound: a wrong-by-30 % gradient no longer passes
+        f_loss, f_norm = _emulated_bf16_step(opt, r, A, B)
+        rel = lambda a, b: abs(a - b) / max(abs(b), 1e-12)
+        fl = max(rel(f_loss[k], v) for k, v in st["losses"].items())
+        fg = max(rel(f_norm[k], nrm) for k, (nrm, _) in st["grads"].items())
+        ltol, gtol = 1.5 * fl + 5e-3, 1.5 * fg + 1e-2
+        print("bf16 step floors (%s): losses %.3e -> tol %.3e, gradient norms %.3e -> tol %.3e" % (case, fl, ltol, fg, gtol))
     for k, v in st["losses"].items():
         assert got[k] == pytest.approx(v, rel=ltol, abs=1e-5), k
     assert float(m.loss_cor_coe_GA) == pytest.approx(st["cor_coe_GA"], rel=10 * ltol)
     assert OF.rel_l2(m.fake_B.cpu(), st["fake_B"]) < atol and OF.rel_l2(m.rec_A.cpu(), st["rec_A"]) < 2 * atol
     assert OF.rel_l2(m.idt_A.cpu(), st["idt_A"]) < atol
     named = {"G_A": dict(m.netG_A.named_parameters()), "D_A": dict(m.netD_A.named_parameters())}
-    gtol = 5e-3 if mode == "fp32" else 3.5e-1      # bf16: storage-noise floor, see test_gradients_match_oracle
     for key, (nrm, samp) in st["grads"].items():
         net, pk = key.split(".", 1)
         assert float(named[net][pk].grad.double().norm()) == pytest.approx(nrm, rel=gtol), key

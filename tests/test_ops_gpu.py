@@ -281,6 +281,26 @@ def test_adam_matches_torch_optim():
             assert torch.equal(s.cpu(), a.cpu().to(torch.bfloat16))
 
 
+@pytest.mark.parametrize("dtype,ca,cb", [(torch.bfloat16, 64, 128), (torch.bfloat16, 8, 8), (torch.bfloat16, 4, 12),
+                                         (torch.float32, 16, 8), (torch.float32, 3, 5)])
+def test_cat2_act(dtype, ca, cb):
+    """UNet skip: act(cat([a, b], C)) written in one pass and its backward (networks3D.py:339-343 + the parent's ReLU)."""
+    I, ref = ops.impl(), R.RefImpl(torch.float32)
+    gen = torch.Generator().manual_seed(9)
+    a = torch.randn((2, 5, 6, 7, ca), generator=gen).to(dtype)
+    b = torch.randn((2, 5, 6, 7, cb), generator=gen).to(dtype)
+    go = torch.randn((2, 5, 6, 7, ca + cb), generator=gen).to(dtype)
+    for act, slope in ((1, 0.0), (2, 0.2), (0, 0.0)):
+        out = I.cat2_act_fwd(a.cuda(), b.cuda(), act, slope)
+        want = ref.cat2_act_fwd(a, b, act, slope)
+        assert torch.equal(out.cpu(), want)
+        da, db = I.cat2_act_bwd(go.cuda(), out, ca, act, slope)
+        wa, wb = ref.cat2_act_bwd(go, want, ca, act, slope)
+        assert torch.equal(da.cpu(), wa) and torch.equal(db.cpu(), wb)
+        da, db = I.cat2_act_bwd(go.cuda(), out, ca, act, slope, (False, True))
+        assert da is None and torch.equal(db.cpu(), wb)
+
+
 NSTATS = [
     # geom, in_dims (= shape of the norm's stored output), N, norm act, slope      -> kernel
     (ConvGeom(256, 256, 3, 1, 0), (10, 10, 10), 2, 1, 0.0),             # res-block conv2 dgrad: gather_halo (2D / flat tiles)

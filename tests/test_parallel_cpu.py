@@ -106,3 +106,27 @@ def test_two_rank_gradient_averaging_matches_batch_two(tmp_path, fused):
     stats = res[0][3]
     assert stats["buckets"] > 4 and stats["allreduce_calls"] == stats["buckets"]
     assert stats["late_launches"] == 0, "every bucket must go out from inside the backward pass (overlap)"
+
+
+def test_bucket_views_are_256_byte_aligned(tmp_path):
+    """Every gradient view starts on a 256-byte boundary of its flat bucket, whatever odd-sized parameters (1-element
+    biases of the heads) precede it: the fused-wgrad kernels reduce into these views with 16-byte vector atomics
+    (a 4-byte shifted view was a `misaligned address` fault on the GPU at N = 2)."""
+    from mra_gan_b200 import ops, parallel
+    m = _build(str(tmp_path))
+    try:
+        sync = parallel.attach(m, bucket_mb=0.05, fused_wgrad=True)
+        seen = 0
+        for phase in sync.phases.values():
+            for b in phase:
+                base, end = b.flat.data_ptr(), b.flat.data_ptr() + b.flat.numel() * 4
+                assert base % 64 == 0               # CPU allocator: 64 B; the CUDA caching allocator hands out 512 B blocks
+                for p in b.params:
+                    off = p.grad.data_ptr() - base
+                    assert off % 256 == 0 and p.grad.data_ptr() + p.numel() * 4 <= end
+                    assert p.grad.stride() == p.stride()
+                    seen += 1
+        assert seen == sum(1 for n in ("G_A", "G_B", "D_A", "D_B") for _ in getattr(m, "net" + n).parameters())
+        assert any(p.numel() == 1 for b in sync.phases["D"] for p in b.params)      # the case that broke alignment
+    finally:
+        ops.set_impl(None)
