@@ -108,7 +108,7 @@ def workload_config(world, per_gpu_batch, launch, workload="train"):
 
 
 def launch_mode(world, no_graphs=False):
-    use_graphs = not no_graphs and (world == 1 or os.environ.get("MRA_DP_GRAPHS", "0") == "1")
+    use_graphs = not no_graphs and (world == 1 or os.environ.get("MRA_DP_GRAPHS", "1") == "1")
     return use_graphs, ("two CUDA graphs per step" if use_graphs else "eager")
 
 
@@ -395,7 +395,7 @@ def run_gpu(args):
         "tc_error_flag": err,
     }
     if sync_stats is not None:
-        line["grad_sync"] = dict(sync_stats, fused_wgrad=os.environ.get("MRA_DP_FUSED_WGRAD", "0") == "1",
+        line["grad_sync"] = dict(sync_stats, fused_wgrad=os.environ.get("MRA_DP_FUSED_WGRAD", "1") == "1",
                                  skip_allreduce=os.environ.get("MRA_DP_SKIP_ALLREDUCE", "0") == "1")
     if world == 1 and not args.no_anchor and not args.batch and not unet:
         # the weak-scaling anchor: the SAME program the N > 1 runs execute (config 3's per-GPU batch and launch mode)

@@ -185,8 +185,10 @@ def attach(model, bucket_mb=32.0, fused_wgrad=None):
     # straight into the bucket view and autograd is handed nothing.  The engine still runs each parameter's
     # AccumulateGrad node -- and with it the post-accumulate hook the buckets listen to -- once all uses are done
     # (observed on torch 2.11; were it ever skipped, finish() launches the bucket, losing overlap, not correctness).
-    # Opt-in until it has been measured at N > 1.
-    fused = os.environ.get("MRA_DP_FUSED_WGRAD", "0") == "1" if fused_wgrad is None else bool(fused_wgrad)
+    # Default since it was measured at N = 2 (profiles/r02_dp2_variants_v2.txt: with graph replay 257.96 vs 259.77 ms on
+    # resnet_9blocks, 58.35 vs 61.32 ms on unet_128, no late bucket launches); MRA_DP_FUSED_WGRAD=0 restores the
+    # autograd accumulation.
+    fused = os.environ.get("MRA_DP_FUSED_WGRAD", "1") == "1" if fused_wgrad is None else bool(fused_wgrad)
     for name in model.model_names:
         networks3D.set_fused_wgrad(getattr(model, "net" + name), fused)
     model.grad_sync = GradSync({"G": [model.netG_A, model.netG_B], "D": [model.netD_A, model.netD_B]},
