@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 LIB = os.path.join(OUT_DIR, "libmra_b200.so")
 SOURCES = ["mra_abi.cu"]
-HEADERS = ["common.cuh", "conv_plan.h", "conv_naive.cuh", "conv_tc.cuh", "conv_tc_halo.cuh", "conv_tc_col.cuh", "conv_special.cuh", "norm.cuh", "norm_stream.cuh", "misc.cuh",
+HEADERS = ["common.cuh", "conv_plan.h", "conv_naive.cuh", "conv_tc.cuh", "conv_tc_halo.cuh", "conv_tc_phase.cuh", "conv_tc_col.cuh", "conv_special.cuh", "norm.cuh", "norm_stream.cuh", "misc.cuh",
            os.path.join("..", "..", "include", "mra_gan_b200.h")]
 
 

@@ -472,8 +472,11 @@ inline int run_gather_halo(const GatherPlan& plan, const GatherLaunch& L, HaloP&
   return 0;
 }
 
-// Run every launch of a gather plan on the tensor cores: stride-1 launches on the halo-plane kernel, the
-// rest (and anything the halo kernel cannot host) on the per-tap kernel.
+inline bool phase_try_run(const GatherPlan& plan, const GatherRun& R, cudaStream_t st, int* rc);   // conv_tc_phase.cuh
+
+// Run every launch of a gather plan on the tensor cores: the 8 parity phases of a stride-2 dgrad-form plan on the
+// phase-halo kernel, stride-1 launches on the halo-plane kernel, the rest (and anything those cannot host) on the
+// per-tap kernel.
 inline int run_gather_tc(const GatherPlan& plan, const GatherRun& R, cudaStream_t st) {
   const int n_tile = pick_n_tile(plan.cn);
   MRA_REQUIRE(n_tile > 0 && plan.ck % 64 == 0, "channel counts not eligible for the tensor-core path");
@@ -486,6 +489,8 @@ inline int run_gather_tc(const GatherPlan& plan, const GatherRun& R, cudaStream_
   const bool no_pair = gm && !strcmp(gm, "single");
   const bool no_col = gm && !strcmp(gm, "nocol");
   if (!force_v1 && gather_mergeable(plan)) {
+    int prc = 0;
+    if (!(gm && !strcmp(gm, "nophase")) && phase_try_run(plan, R, st, &prc)) return prc;
     bool slabs_ok = true;
     for (const GatherLaunch& L : plan.launches)
       for (const Tap& t : L.taps) if (t.widx >= R.slabs) slabs_ok = false;

@@ -5,6 +5,7 @@
 #include "conv_naive.cuh"
 #include "conv_plan.h"
 #include "conv_tc_halo.cuh"
+#include "conv_tc_phase.cuh"
 #include "conv_special.cuh"
 #include "misc.cuh"
 #include "norm.cuh"
