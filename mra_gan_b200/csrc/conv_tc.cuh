@@ -180,6 +180,15 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_m
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// 256-bit global stores / loads (sm_100: STG.E.ENL2.256): an epilogue thread owns 64 contiguous bytes of an output row
+// while its neighbours' rows are >= 128 B away, so every store instruction touches 32 different sectors; with 32-byte
+// pieces each of them is written whole (no partial-sector merge in L2) by half as many instructions as with 16-byte ones.
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
+                                             uint32_t a5, uint32_t a6, uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7) : "memory");
+}
+
 // Sum over the 32 lanes of each of 32 per-lane values; lane j ends up with column j's total.
 __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 #pragma unroll
@@ -363,11 +372,13 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, uint32_t t_addr,
     }
     if (valid) {
       if (E.out_bf16) {
-        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(E.out) + obase_c + c0);
+        char* o = reinterpret_cast<char*>(reinterpret_cast<bf16*>(E.out) + obase_c + c0);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          o[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                            pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+        for (int i = 0; i < 2; ++i)
+          st_global_v8(o + 32 * i, pack_bf16x2(v[16 * i], v[16 * i + 1]), pack_bf16x2(v[16 * i + 2], v[16 * i + 3]),
+                       pack_bf16x2(v[16 * i + 4], v[16 * i + 5]), pack_bf16x2(v[16 * i + 6], v[16 * i + 7]),
+                       pack_bf16x2(v[16 * i + 8], v[16 * i + 9]), pack_bf16x2(v[16 * i + 10], v[16 * i + 11]),
+                       pack_bf16x2(v[16 * i + 12], v[16 * i + 13]), pack_bf16x2(v[16 * i + 14], v[16 * i + 15]));
       } else {
         float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(E.out) + obase_c + c0);
 #pragma unroll

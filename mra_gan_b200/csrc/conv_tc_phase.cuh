@@ -113,6 +113,11 @@ gather_phase_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const bool prof = (P.debug & 2) != 0;
+  // Every CTA walks the channel chunks and the sub-items of a work item in its own ROTATED order (sums are order-free,
+  // the accumulate flags follow the iteration index): at any moment the SMs then stream different weight slabs
+  // instead of all 148 asking one L2 slice for the same 16 KB.
+  const int rot_kc = (int)(blockIdx.x % (unsigned)P.kchunks);
+  const int rot_k = (int)((blockIdx.x / (unsigned)P.kchunks) % (unsigned)kPhaseSubs);
 
   if (warp == kHaloPlaneWarp) {
     // ---- plane producer: per (work item, channel chunk) the group's halo planes
@@ -123,7 +128,9 @@ gather_phase_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int it = blockIdx.x; it < P.total_items && ok; it += gridDim.x) {
         const PhaseItem t = phase_decode(P, it);
         const int nd = P.g_nd[t.pg];
-        for (int kc = 0; kc < P.kchunks && ok; ++kc)
+        for (int kci = 0; kci < P.kchunks && ok; ++kci) {
+          int kc = kci + rot_kc;
+          if (kc >= P.kchunks) kc -= P.kchunks;
           for (int pl = 0; pl < nd; ++pl) {
             if (!mbar_wait(&p_empty[s], ph ^ 1u, P.err, 41)) { ok = false; break; }
             mbar_expect_tx(&p_full[s], (uint32_t)P.plane_tx);
@@ -131,6 +138,7 @@ gather_phase_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         t.d + (int)P.g_dd[t.pg][pl], t.n);
             if (++s == P.NP) { s = 0; ph ^= 1u; }
           }
+        }
       }
     }
   } else if (warp == kProdWarp) {
@@ -143,9 +151,12 @@ gather_phase_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int it = blockIdx.x; it < P.total_items && ok; it += gridDim.x) {
         const PhaseItem t = phase_decode(P, it);
         const int n0 = t.nt * 128;
-        const int e0 = P.s_ent0[t.pg * kPhaseSubs], e1 = P.s_ent0[(t.pg + 1) * kPhaseSubs];
-        for (int kc = 0; kc < P.kchunks && ok; ++kc)
-          for (int e = e0; e < e1; ++e) {
+        for (int kci = 0; kci < P.kchunks && ok; ++kci) {
+          int kc = kci + rot_kc;
+          if (kc >= P.kchunks) kc -= P.kchunks;
+         for (int ki = 0; ki < kPhaseSubs && ok; ++ki) {
+          const int sub = t.pg * kPhaseSubs + ((ki + rot_k) & (kPhaseSubs - 1));
+          for (int e = P.s_ent0[sub]; e < P.s_ent0[sub + 1]; ++e) {
             const long long tw0 = prof ? clock64() : 0;
             if (!mbar_wait(&b_empty[s], ph ^ 1u, P.err, 42)) { ok = false; break; }
             if (prof) t_wait += clock64() - tw0;
@@ -161,6 +172,8 @@ gather_phase_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             if (++s == P.NB) { s = 0; ph ^= 1u; }
           }
+         }
+        }
       }
       if (prof) { atomicAdd(P.dbg + 0, (unsigned long long)t_wait); atomicAdd(P.dbg + 1, (unsigned long long)(clock64() - t_begin)); }
     }
@@ -195,7 +208,8 @@ gather_phase_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (prof) t_waitp += clock64() - tp0;
           if (!ok) break;
           tc_fence_after();
-          for (int k = 0; k < kPhaseSubs && ok; ++k) {
+          for (int ki = 0; ki < kPhaseSubs && ok; ++ki) {
+            const int k = (ki + rot_k) & (kPhaseSubs - 1);
             const int sub = pg * kPhaseSubs + k;
             if (kc == 0) {
               const long long ta0 = prof ? clock64() : 0;
@@ -300,7 +314,12 @@ gather_phase_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // Eligibility + tables: 8 parity phases over one launch space (gather_mergeable), 64 or a multiple of 128 output
 // channels, the tap tables within their limits, planes + a weight ring within shared memory.
 inline bool phase_setup(const GatherPlan& plan, const GatherRun& R, PhaseP& P) {
-  if (!gather_mergeable(plan) || getenv("MRA_GATHER_NOPHASE")) return false;
+  // Opt-in (MRA_GATHER_PHASE=1): measured on B200 it loses to the per-tap merged kernel on every BASELINE layer
+  // (profiles/r02_conv_layers_phase_vs_pertap.txt: G.u2 fprop 0.475 vs 0.369 ms, G.d1 dgrad 0.457 vs 0.333 ms) -- the
+  // weight slabs, not the A tiles, dominate the L2 -> SM bytes of these layers and a single-CTA version streams
+  // them just as often; it is kept as the base for a cta_group::2 version that shares the slabs.
+  const char* on = getenv("MRA_GATHER_PHASE");
+  if (!gather_mergeable(plan) || !on || atoi(on) == 0) return false;
   if (plan.ck % 64 != 0) return false;
   const bool dual = plan.cn == 64;
   if (!dual && plan.cn % 128 != 0) return false;
