@@ -45,7 +45,17 @@ constexpr int kThreads = 192;                    // wgrad kernel: producer, MMA,
 constexpr int kEpiWarps = 8;
 constexpr int kProdWarp = kEpiWarps;             // TMA producer (A and B boxes / weight ring)
 constexpr int kMmaWarp = kEpiWarps + 1;          // gather_tc / gather_col: TMEM allocator + MMA issuer
-constexpr int kThreadsGather = 32 * (kEpiWarps + 2);
+constexpr int kThreadsGather = 32 * 12;         // 3 whole warpgroups: 0..7 epilogue, 8 producer, 9 MMA, 10..11 idle
+// Register split between the warpgroups (setmaxnreg): the kernels are compiled for 384 threads = 168 registers per
+// thread at entry; the two epilogue warpgroups then grow to kRegsEpi, the producer / MMA warpgroup shrinks to
+// kRegsOther (2 * 128 * 216 + 128 * 72 = 64 512 <= 65 536).  The epilogue with statistics keeps ~200 values live
+// (accumulator chunk, partial sums, addresses); at 168 registers it spilled loop-carried scalars, and with the L1
+// cut to a few KB by the shared-memory carve-out every reload was an L2 round trip inside the epilogue's critical path
+// (profiles/r02_col_stem_ncu.txt: 3.4 M local loads per launch, 46 % L1 hit rate, long-scoreboard stalls).
+// (The instruction sits at the head of every role branch: ptxas takes the limit of the code that follows from it.)
+constexpr int kRegsEpi = 216, kRegsOther = 72;
+__device__ __forceinline__ void regs_epilogue() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi)); }
+__device__ __forceinline__ void regs_other() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther)); }
 constexpr int kMaxTaps = 64;
 constexpr uint32_t kABytes = 128 * 128;          // 128 rows x 64 bf16
 
@@ -240,9 +250,27 @@ __device__ __noinline__ float act_slow(float v, int act) {
 // Dual-plane tiles (gather_col_kernel with 64 output channels): the accumulator is 128 columns wide, columns
 // [0, 64) belong to output plane p and [64, 128) to plane p + 1 (`dual_stride` elements further, validity
 // `valid_hi`); TMEM chunk c then maps to channel chunk c & 1 of plane c >> 1.
-template <bool kAux = false, typename Release>
+// kMode (compile time, one kernel instantiation each): 0 = no statistics -- the per-thread / per-lane partial sums do
+// not exist at all, which is what keeps the dgrad-type launches free of register spills (with the shared-memory
+// carve-out at its maximum the L1 is a few KB: a spilled loop variable costs an L2 round trip in the epilogue's
+// critical path) --, 1 = InstanceNorm statistics of the output, 2 = norm-backward statistics against E.aux.
+// Per-lane fp64 partial sums of the (at most 4) channel chunks a warp owns, slot k <-> channel chunk c_begin + k * c_step.
+// Registers with a predicated update per slot: an array indexed by the (run-time) chunk would live in local memory,
+// and with the L1 squeezed to a few KB by the shared-memory carve-out every update was an L2 round trip.
+struct EpiStats {
+  double s[4], q[4];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { s[i] = 0.0; q[i] = 0.0; }
+  }
+  __device__ __forceinline__ void add(int k, double a, double b) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (i == k) { s[i] += a; q[i] += b; }
+  }
+};
+template <int kMode, typename Release>
 __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, uint32_t t_addr, int c_begin, int c_step, int nchunks, bool valid,
-                                              long long obase, int n0, int lane, double* st_s, double* st_q, bool defer,
+                                              long long obase, int n0, int lane, EpiStats& st, int slot0, bool defer,
                                               float (&d1)[32], float (&d2)[32], Release release, bool dual = false,
                                               long long dual_stride = 0, bool valid_hi = false) {
   const bool lin_act = E.act == MRA_ACT_RELU || E.act == MRA_ACT_LRELU;
@@ -270,7 +298,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, uint32_t t_addr,
         v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
       }
     }
-    if (kAux && E.stats) {
+    if constexpr (kMode == 2) {
       // aux is consumed 8 values at a time (never more than 8 extra live registers); the deferred flavour adds straight
       // into d1 / d2, the per-tile flavour builds the two arrays of the transpose-reduce
       const float ns = E.aux_nslope;
@@ -338,10 +366,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, uint32_t t_addr,
 #pragma unroll
           for (int i = 0; i < 32; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
         }
-        st_s[c] += (double)warp_colsum32(s1, lane);
-        st_q[c] += (double)warp_colsum32(s2, lane);
+        const float a1 = warp_colsum32(s1, lane), a2 = warp_colsum32(s2, lane);
+        st.add(slot0 + (c - c_begin) / c_step, (double)a1, (double)a2);
       }
-    } else if (E.stats) {
+    } else if constexpr (kMode == 1) {
       if (defer) {
         if (valid) {
 #pragma unroll
@@ -351,8 +379,8 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, uint32_t t_addr,
         float s1[32], s2[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) { s1[i] = valid ? v[i] : 0.f; s2[i] = s1[i] * s1[i]; }
-        st_s[c] += (double)warp_colsum32(s1, lane);
-        st_q[c] += (double)warp_colsum32(s2, lane);
+        const float a1 = warp_colsum32(s1, lane), a2 = warp_colsum32(s2, lane);
+        st.add(slot0 + (c - c_begin) / c_step, (double)a1, (double)a2);
       }
     }
     if (lin_act) {
@@ -395,29 +423,32 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, uint32_t t_addr,
 typedef double EpiRed[2][4][32][2];              // [chunk group][quadrant][lane][sum, sum of squares]
 constexpr size_t kEpiRedBytes = sizeof(EpiRed);  // static shared memory of the gather kernels
 __device__ __forceinline__ void epilogue_flush_stats(double* stats, int n, int Cn, int n0, int q, int c_begin, int c_step,
-                                                     int nchunks, int lane, double* st_s, double* st_q, bool defer,
+                                                     int nchunks, int lane, EpiStats& st, bool defer,
                                                      float (&d1)[32], float (&d2)[32], EpiRed& red) {
   if (n < 0) return;
   if (defer && c_begin < nchunks) {
-    st_s[c_begin] += (double)warp_colsum32(d1, lane);
-    st_q[c_begin] += (double)warp_colsum32(d2, lane);
+    const float a1 = warp_colsum32(d1, lane), a2 = warp_colsum32(d2, lane);
+    st.add(0, (double)a1, (double)a2);
 #pragma unroll
     for (int i = 0; i < 32; ++i) { d1[i] = 0.f; d2[i] = 0.f; }
   }
-#pragma unroll 1
-  for (int c = c_begin; c < nchunks; c += c_step) {
-    red[c_begin][q][lane][0] = st_s[c];
-    red[c_begin][q][lane][1] = st_q[c];
-    st_s[c] = 0.0; st_q[c] = 0.0;
-    asm volatile("bar.sync %0, 128;" ::"r"(1 + c_begin) : "memory");
-    if (q == 0) {
-      const double a = red[c_begin][0][lane][0] + red[c_begin][1][lane][0] + red[c_begin][2][lane][0] + red[c_begin][3][lane][0];
-      const double b = red[c_begin][0][lane][1] + red[c_begin][1][lane][1] + red[c_begin][2][lane][1] + red[c_begin][3][lane][1];
-      double* st = stats + ((long long)n * Cn + n0 + c * 32 + lane) * 2;
-      atomicAdd(st, a);
-      atomicAdd(st + 1, b);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c_begin + k * c_step;
+    if (c < nchunks) {                                   // same for all 128 threads of the group
+      red[c_begin][q][lane][0] = st.s[k];
+      red[c_begin][q][lane][1] = st.q[k];
+      st.s[k] = 0.0; st.q[k] = 0.0;
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + c_begin) : "memory");
+      if (q == 0) {
+        const double a = red[c_begin][0][lane][0] + red[c_begin][1][lane][0] + red[c_begin][2][lane][0] + red[c_begin][3][lane][0];
+        const double b = red[c_begin][0][lane][1] + red[c_begin][1][lane][1] + red[c_begin][2][lane][1] + red[c_begin][3][lane][1];
+        double* sp = stats + ((long long)n * Cn + n0 + c * 32 + lane) * 2;
+        atomicAdd(sp, a);
+        atomicAdd(sp + 1, b);
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + c_begin) : "memory");
     }
-    asm volatile("bar.sync %0, 128;" ::"r"(1 + c_begin) : "memory");
   }
 }
 // per-warp epilogue state shared by the three gather kernels
@@ -493,8 +524,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GatherP& P, int tile) {
 // multi-buffered in TMEM (P.nbuf) so the epilogue of item j overlaps the MMAs of the following items; InstanceNorm
 // statistics are accumulated per CTA and flushed with one fp64 atomic per channel when the sample index changes
 // (instead of per tile).
-template <bool kAux>        // kAux: norm-backward statistics in the epilogue (EpiArgs::aux); a separate instantiation so
-                             // that the fprop / plain dgrad epilogue keeps its register budget
+template <int kMode>         // epilogue statistics mode, see epilogue_tile
 __global__ void __launch_bounds__(kThreadsGather, 1)
 gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ GatherP P) {
@@ -526,6 +556,8 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp >= kEpiWarps) {            // third warpgroup: producers, MMA issuer, idle warps -- one setmaxnreg for all of it
+  regs_other();
   if (warp == kProdWarp) {
     if (elect_one()) {
       uint32_t git = 0;                                    // global k-iteration counter (stage ring position)
@@ -610,17 +642,18 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         atomicAdd(P.dbg + 6, (unsigned long long)t_wacc); atomicAdd(P.dbg + 5, 1ull);
       }
     }
+  }
   } else {
     // epilogue warps 0..7 -> TMEM lane quadrant (warp % 4), alternate 32-column chunks
+    regs_epilogue();
     const EpiWarp W(warp);
     const int q = W.q;
     const int row = q * 32 + lane;
     const int rw = row % P.bw, rh = (row / P.bw) % P.bh, rd = row / (P.bw * P.bh);
     const int nchunks = P.n_tile / 32;
-    const bool defer = P.stats != nullptr && nchunks <= 2;
-    double st_s[8], st_q[8];                 // per-lane running sums for column (chunk*32 + lane)
-#pragma unroll
-    for (int c = 0; c < 8; ++c) { st_s[c] = 0.0; st_q[c] = 0.0; }
+    const bool defer = kMode != 0 && nchunks <= 2;
+    EpiStats st;                             // per-lane running sums of this warp's chunks
+    st.clear();
     float d1[32], d2[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) { d1[i] = 0.f; d2[i] = 0.f; }
@@ -636,8 +669,8 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const long long obase = (long long)t.n * P.osn + (long long)(ld * P.ostep + P.ph_od[t.ph]) * P.osd +
                               (long long)(lh * P.ostep + P.ph_oh[t.ph]) * P.osh +
                               (long long)(lw * P.ostep + P.ph_ow[t.ph]) * P.osw + t.n0;
-      if (P.stats && (t.n != st_n || t.n0 != st_n0)) {
-        epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, W.q, W.c_begin, 2, nchunks, lane, st_s, st_q, defer, d1, d2, epi_red);
+      if (kMode != 0 && (t.n != st_n || t.n0 != st_n0)) {
+        epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, W.q, W.c_begin, 2, nchunks, lane, st, defer, d1, d2, epi_red);
         st_n = t.n; st_n0 = t.n0;
       }
       ok = mbar_wait(&acc_full[buf], aph, P.err, 3);
@@ -646,7 +679,7 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const long long te0 = (P.debug & 2) ? clock64() : 0;
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
       uint64_t* rel_bar = &acc_empty[buf];
-      epilogue_tile<kAux>(E, t_addr, W.c_begin, 2, acc_cols / 32, valid, obase, t.n0, lane, st_s, st_q, defer, d1, d2, [&]() {
+      epilogue_tile<kMode>(E, t_addr, W.c_begin, 2, acc_cols / 32, valid, obase, t.n0, lane, st, 0, defer, d1, d2, [&]() {
         tc_fence_before();                      // accumulator fully read: hand the buffer back to the MMA warp
         __syncwarp();
         if (lane == 0) mbar_arrive(rel_bar);
@@ -654,7 +687,7 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if ((P.debug & 2) && threadIdx.x == 0) atomicAdd(P.dbg + 4, (unsigned long long)(clock64() - te0));
       if (++buf == P.nbuf) { buf = 0; aph ^= 1u; }
     }
-    if (P.stats) epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, W.q, W.c_begin, 2, nchunks, lane, st_s, st_q, defer, d1, d2, epi_red);
+    if (kMode != 0) epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, W.q, W.c_begin, 2, nchunks, lane, st, defer, d1, d2, epi_red);
   }
   tc_fence_before();
   __syncthreads();
@@ -1245,8 +1278,9 @@ inline int run_gather_v1_launch(const GatherPlan& plan, const GatherLaunch* Ls, 
                                 int n_tile, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
-    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
     attr_set = true;
   }
   const GatherLaunch& L = Ls[0];
@@ -1328,8 +1362,9 @@ inline int run_gather_v1_launch(const GatherPlan& plan, const GatherLaunch* Ls, 
                             P.astep))
     return rc;
   const int ctas = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
-  if (P.aux && P.stats) gather_tc_kernel<true><<<ctas, kThreadsGather, smem, st>>>(tmA, tmB, P);
-  else gather_tc_kernel<false><<<ctas, kThreadsGather, smem, st>>>(tmA, tmB, P);
+  if (P.aux && P.stats) gather_tc_kernel<2><<<ctas, kThreadsGather, smem, st>>>(tmA, tmB, P);
+  else if (P.stats) gather_tc_kernel<1><<<ctas, kThreadsGather, smem, st>>>(tmA, tmB, P);
+  else gather_tc_kernel<0><<<ctas, kThreadsGather, smem, st>>>(tmA, tmB, P);
   MRA_LAUNCH_CHECK();
   return 0;
 }

@@ -46,7 +46,7 @@ struct ColP {
   unsigned long long* dbg;
 };
 
-template <bool kAux>
+template <int kMode>
 __global__ void __launch_bounds__(kThreadsGather, 1)
 gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ ColP P) {
@@ -90,6 +90,8 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     len = min(P.seg_len, P.Dl - d0);
   };
 
+  if (warp >= kEpiWarps) {            // third warpgroup: producers, MMA issuer, idle warps -- one setmaxnreg for all of it
+  regs_other();
   if (warp == kProdWarp) {
     if (elect_one()) {
       // resident weights: every (tap, chunk) slab once
@@ -241,16 +243,17 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         atomicAdd(P.dbg + 7, (unsigned long long)t_wp); atomicAdd(P.dbg + 5, 1ull); atomicAdd(P.dbg + 1, (unsigned long long)jt);
       }
     }
+  }
   } else {
+    regs_epilogue();
     const EpiWarp W(warp);
     const int q = W.q;
     const int row = q * 32 + lane;
     const int nchunks = P.n_tile / 32;                    // CHANNEL chunks (dual tiles hold each of them twice)
     const int acc_cols = P.dual ? 2 * P.n_tile : P.n_tile;
-    const bool defer = P.stats != nullptr && nchunks <= 2;
-    double st_s[8], st_q[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) { st_s[c] = 0.0; st_q[c] = 0.0; }
+    const bool defer = kMode != 0 && nchunks <= 2;
+    EpiStats st;
+    st.clear();
     float d1[32], d2[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) { d1[i] = 0.f; d2[i] = 0.f; }
@@ -264,8 +267,8 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       unit_coords(u, n, h0, w0, d0, len);
       const int lh = h0 + (row >> 3), lw = w0 + (row & 7);
       const bool valid = lw < P.Wl && lh < P.Hl;
-      if (P.stats && n != st_n) {
-        epilogue_flush_stats(P.stats, st_n, P.Cn, 0, W.q, W.c_begin, 2, nchunks, lane, st_s, st_q, defer, d1, d2, epi_red);
+      if (kMode != 0 && n != st_n) {
+        epilogue_flush_stats(P.stats, st_n, P.Cn, 0, W.q, W.c_begin, 2, nchunks, lane, st, defer, d1, d2, epi_red);
         st_n = n;
       }
       const int ntiles = P.dual ? (len + 1) / 2 : len;
@@ -278,7 +281,7 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
         uint64_t* rel_bar = &acc_empty[buf];
-        epilogue_tile<kAux>(E, t_addr, W.c_begin, 2, acc_cols / 32, valid, obase, 0, lane, st_s, st_q, defer, d1, d2, [&]() {
+        epilogue_tile<kMode>(E, t_addr, W.c_begin, 2, acc_cols / 32, valid, obase, 0, lane, st, 0, defer, d1, d2, [&]() {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(rel_bar);
@@ -286,7 +289,7 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (++buf == P.nbuf) { buf = 0; aph ^= 1u; }
       }
     }
-    if (P.stats) epilogue_flush_stats(P.stats, st_n, P.Cn, 0, W.q, W.c_begin, 2, nchunks, lane, st_s, st_q, defer, d1, d2, epi_red);
+    if (kMode != 0) epilogue_flush_stats(P.stats, st_n, P.Cn, 0, W.q, W.c_begin, 2, nchunks, lane, st, defer, d1, d2, epi_red);
   }
   tc_fence_before();
   __syncthreads();
@@ -344,8 +347,9 @@ inline int run_gather_col(const GatherPlan& plan, const GatherLaunch& L, ColP& P
                           cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_col_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
-    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_col_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_col_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_col_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_col_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
     attr_set = true;
   }
   P.ostep = L.ostep; P.od0 = L.o0[0]; P.oh0 = L.o0[1]; P.ow0 = L.o0[2];
@@ -365,8 +369,9 @@ inline int run_gather_col(const GatherPlan& plan, const GatherLaunch& L, ColP& P
   if (int rc = make_act_map(&tmA, R.a, plan.n, plan.adims[0], plan.adims[1], plan.adims[2], plan.ck, 8, 16, 1, 1)) return rc;
   const size_t smem = (size_t)P.kd * P.kchunks * P.n_tile * 128 + (size_t)P.NPR * kABytes * P.kchunks + 1024 + 512;
   const int ctas = P.total_units < num_sms() ? P.total_units : num_sms();
-  if (P.aux && P.stats) gather_col_kernel<true><<<ctas, kThreadsGather, smem, st>>>(tmA, tmB, P);
-  else gather_col_kernel<false><<<ctas, kThreadsGather, smem, st>>>(tmA, tmB, P);
+  if (P.aux && P.stats) gather_col_kernel<2><<<ctas, kThreadsGather, smem, st>>>(tmA, tmB, P);
+  else if (P.stats) gather_col_kernel<1><<<ctas, kThreadsGather, smem, st>>>(tmA, tmB, P);
+  else gather_col_kernel<0><<<ctas, kThreadsGather, smem, st>>>(tmA, tmB, P);
   MRA_LAUNCH_CHECK();
   return 0;
 }

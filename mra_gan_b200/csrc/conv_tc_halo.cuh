@@ -27,7 +27,7 @@ namespace tc {
 
 constexpr int kHaloPlaneWarp = kEpiWarps + 1;
 constexpr int kHaloMmaWarp = kEpiWarps + 2;
-constexpr int kThreadsHalo = 32 * (kEpiWarps + 3);
+constexpr int kThreadsHalo = 32 * 12;             // 3 whole warpgroups (setmaxnreg is per warpgroup); warp 11 idles
 
 struct HaloP {
   int Dl, Hl, Wl;                   // launch-space (output) dims
@@ -95,7 +95,7 @@ __device__ __forceinline__ HaloTile halo_decode(const HaloP& P, int work, int pa
   return t;
 }
 
-template <bool kPair, bool kAux = false>
+template <bool kPair, int kMode>
 __global__ void __launch_bounds__(kThreadsHalo, 1)
 gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ HaloP P) {
@@ -154,6 +154,8 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   const bool dbg_nob = (P.debug & 4) != 0, dbg_nop = (P.debug & 8) != 0;     // timing experiments: no weight / plane traffic
+  if (warp >= kEpiWarps) {            // third warpgroup: producers, MMA issuer, idle warps -- one setmaxnreg for all of it
+  regs_other();
   if (warp == kHaloPlaneWarp) {
     // ---- plane producer: one halo plane per (work item, channel chunk, td); each CTA loads its own tile's planes
     if (elect_one() && !dbg_nop) {
@@ -272,17 +274,18 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         atomicAdd(P.dbg + 5, 1ull);
       }
     }
+  }
   } else {
     // ---- epilogue warps 0..7 -> TMEM lane quadrant (warp % 4), alternate 32-column chunks
+    regs_epilogue();
     const EpiWarp W(warp);
     const int q = W.q;
     const int row = q * 32 + lane;
     const int nch_full = P.n_tile / 32;
     int nchunks = nch_full;                  // of the current work item (half-width tail items: t.width < n_tile)
-    const bool defer = P.stats != nullptr && nch_full <= 2;
-    double st_s[8], st_q[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) { st_s[c] = 0.0; st_q[c] = 0.0; }
+    const bool defer = kMode != 0 && nch_full <= 2;
+    EpiStats st;
+    st.clear();
     float d1[32], d2[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) { d1[i] = 0.f; d2[i] = 0.f; }
@@ -306,8 +309,8 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       // tile's n_tile channels [tb, tb + n_tile) -- never past Cn.
       const int tb = t.n0 - (t.n0 % P.n_tile);
       const int coff = (t.n0 - tb) >> 5;        // even (n_tile >= 128 when items are split), keeps the warps' chunk parity
-      if (P.stats && (t.n != st_n || tb != st_n0)) {
-        epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, W.q, W.c_begin, 2, nch_full, lane, st_s, st_q, defer, d1, d2, epi_red);
+      if (kMode != 0 && (t.n != st_n || tb != st_n0)) {
+        epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, W.q, W.c_begin, 2, nch_full, lane, st, defer, d1, d2, epi_red);
         st_n = t.n; st_n0 = tb;
       }
       nchunks = t.width / 32;
@@ -317,14 +320,14 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const long long te0 = prof ? clock64() : 0;
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * P.n_tile);
       uint64_t* rel_bar = &acc_empty[buf];
-      epilogue_tile<kAux>(E, t_addr, W.c_begin, 2, nchunks, valid, obase, t.n0, lane, st_s + coff, st_q + coff, defer, d1, d2, [&]() {
+      epilogue_tile<kMode>(E, t_addr, W.c_begin, 2, nchunks, valid, obase, t.n0, lane, st, coff >> 1, defer, d1, d2, [&]() {
         tc_fence_before();                      // accumulator fully read: hand the buffer back to the MMA warp
         __syncwarp();
         if (lane == 0) { if constexpr (kPair) mbar_arrive_leader(rel_bar); else mbar_arrive(rel_bar); }
       });
       if (prof && threadIdx.x == 0) atomicAdd(P.dbg + 4, (unsigned long long)(clock64() - te0));
     }
-    if (P.stats) epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, W.q, W.c_begin, 2, nch_full, lane, st_s, st_q, defer, d1, d2, epi_red);
+    if (kMode != 0) epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, W.q, W.c_begin, 2, nch_full, lane, st, defer, d1, d2, epi_red);
   }
   tc_fence_before();
   if constexpr (kPair) cluster_sync_all(); else __syncthreads();
@@ -428,10 +431,12 @@ inline int run_gather_halo(const GatherPlan& plan, const GatherLaunch& L, HaloP&
     } }
   static bool attr_set = false;
   if (!attr_set) {
-    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
-    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
-    MRA_CHECK_CUDA(cudaFuncSetAttribute((gather_halo_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
-    MRA_CHECK_CUDA(cudaFuncSetAttribute((gather_halo_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute((gather_halo_kernel<false, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute((gather_halo_kernel<false, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute((gather_halo_kernel<false, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute((gather_halo_kernel<true, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute((gather_halo_kernel<true, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute((gather_halo_kernel<true, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
     attr_set = true;
   }
   P.ostep = L.ostep; P.od0 = L.o0[0]; P.oh0 = L.o0[1]; P.ow0 = L.o0[2];
@@ -450,8 +455,9 @@ inline int run_gather_halo(const GatherPlan& plan, const GatherLaunch& L, HaloP&
   const size_t smem = (size_t)P.NP * P.slot_bytes + (size_t)P.NB * P.n_tile * 128 / (P.pair ? 2 : 1) + 1024 + 256;
   if (!P.pair) {
     const int ctas = P.total_work < num_sms() ? P.total_work : num_sms();
-    if (P.aux && P.stats) gather_halo_kernel<false, true><<<ctas, kThreadsHalo, smem, st>>>(tmA, tmB, P);
-    else gather_halo_kernel<false><<<ctas, kThreadsHalo, smem, st>>>(tmA, tmB, P);
+    if (P.aux && P.stats) gather_halo_kernel<false, 2><<<ctas, kThreadsHalo, smem, st>>>(tmA, tmB, P);
+    else if (P.stats) gather_halo_kernel<false, 1><<<ctas, kThreadsHalo, smem, st>>>(tmA, tmB, P);
+    else gather_halo_kernel<false, 0><<<ctas, kThreadsHalo, smem, st>>>(tmA, tmB, P);
   } else {
     int pairs = num_sms() / 2;
     if (P.total_work < pairs) pairs = P.total_work;
@@ -465,8 +471,9 @@ inline int run_gather_halo(const GatherPlan& plan, const GatherLaunch& L, HaloP&
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (P.aux && P.stats) MRA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gather_halo_kernel<true, true>, tmA, tmB, P));
-    else MRA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gather_halo_kernel<true>, tmA, tmB, P));
+    if (P.aux && P.stats) MRA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gather_halo_kernel<true, 2>, tmA, tmB, P));
+    else if (P.stats) MRA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gather_halo_kernel<true, 1>, tmA, tmB, P));
+    else MRA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gather_halo_kernel<true, 0>, tmA, tmB, P));
   }
   MRA_LAUNCH_CHECK();
   return 0;

@@ -79,7 +79,7 @@ __device__ __forceinline__ PhaseItem phase_decode(const PhaseP& P, int item) {
   return t;
 }
 
-template <bool kAux>
+template <int kMode>
 __global__ void __launch_bounds__(kThreadsHalo, 1)
 gather_phase_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ PhaseP P) {
@@ -119,6 +119,8 @@ gather_phase_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int rot_kc = (int)(blockIdx.x % (unsigned)P.kchunks);
   const int rot_k = (int)((blockIdx.x / (unsigned)P.kchunks) % (unsigned)kPhaseSubs);
 
+  if (warp >= kEpiWarps) {            // third warpgroup: producers, MMA issuer, idle warps -- one setmaxnreg for all of it
+  regs_other();
   if (warp == kHaloPlaneWarp) {
     // ---- plane producer: per (work item, channel chunk) the group's halo planes
     if (elect_one()) {
@@ -257,16 +259,17 @@ gather_phase_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         atomicAdd(P.dbg + 5, 1ull);
       }
     }
+  }
   } else {
     // ---- epilogue warps 0..7 -> TMEM lane quadrant (warp % 4), alternate 32-column chunks of the 128-column sub-item
+    regs_epilogue();
     const EpiWarp W(warp);
     const int q = W.q;
     const int row = q * 32 + lane;
     const int nch = P.dual ? 2 : 4;                        // CHANNEL chunks of a sub-item (dual: each of them twice)
-    const bool defer = P.stats != nullptr && nch <= 2;
-    double st_s[8], st_q[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) { st_s[c] = 0.0; st_q[c] = 0.0; }
+    const bool defer = kMode != 0 && nch <= 2;
+    EpiStats st;
+    st.clear();
     float d1[32], d2[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) { d1[i] = 0.f; d2[i] = 0.f; }
@@ -280,8 +283,8 @@ gather_phase_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int lh = t.h0 + (row >> 3), lw = t.w0 + (row & 7);
       const bool valid = lw < P.Wl && lh < P.Hl;
       const int n0 = t.nt * 128;
-      if (P.stats && (t.n != st_n || n0 != st_n0)) {
-        epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, W.q, W.c_begin, 2, nch, lane, st_s, st_q, defer, d1, d2, epi_red);
+      if (kMode != 0 && (t.n != st_n || n0 != st_n0)) {
+        epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, W.q, W.c_begin, 2, nch, lane, st, defer, d1, d2, epi_red);
         st_n = t.n; st_n0 = n0;
       }
       for (int k = 0; k < kPhaseSubs && ok; ++k) {
@@ -295,7 +298,7 @@ gather_phase_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const long long te0 = prof ? clock64() : 0;
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(k * 128);
         uint64_t* rel_bar = &acc_empty[k];
-        epilogue_tile<kAux>(E, t_addr, W.c_begin, 2, 4, valid, obase, n0, lane, st_s, st_q, defer, d1, d2, [&]() {
+        epilogue_tile<kMode>(E, t_addr, W.c_begin, 2, 4, valid, obase, n0, lane, st, 0, defer, d1, d2, [&]() {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(rel_bar);
@@ -303,7 +306,7 @@ gather_phase_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (prof && threadIdx.x == 0) atomicAdd(P.dbg + 4, (unsigned long long)(clock64() - te0));
       }
     }
-    if (P.stats) epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, W.q, W.c_begin, 2, nch, lane, st_s, st_q, defer, d1, d2, epi_red);
+    if (kMode != 0) epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, W.q, W.c_begin, 2, nch, lane, st, defer, d1, d2, epi_red);
   }
   tc_fence_before();
   __syncthreads();
@@ -429,8 +432,9 @@ inline bool phase_setup(const GatherPlan& plan, const GatherRun& R, PhaseP& P) {
 inline int run_gather_phase(const GatherPlan& plan, PhaseP& P, const GatherRun& R, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_phase_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
-    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_phase_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_phase_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_phase_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
+    MRA_CHECK_CUDA(cudaFuncSetAttribute(gather_phase_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kEpiRedBytes)));
     attr_set = true;
   }
   P.osw = plan.cn;
@@ -447,8 +451,9 @@ inline int run_gather_phase(const GatherPlan& plan, PhaseP& P, const GatherRun& 
   if (int rc = make_weight_map(&tmB, R.b, (long long)R.slabs * plan.cn, plan.ck, P.dual ? 64 : 128)) return rc;
   const size_t smem = (size_t)P.NP * P.slot_bytes + (size_t)P.NB * 128 * 128 + 1024 + 512;
   const int ctas = P.total_items < num_sms() ? P.total_items : num_sms();
-  if (P.aux && P.stats) gather_phase_kernel<true><<<ctas, kThreadsHalo, smem, st>>>(tmA, tmB, P);
-  else gather_phase_kernel<false><<<ctas, kThreadsHalo, smem, st>>>(tmA, tmB, P);
+  if (P.aux && P.stats) gather_phase_kernel<2><<<ctas, kThreadsHalo, smem, st>>>(tmA, tmB, P);
+  else if (P.stats) gather_phase_kernel<1><<<ctas, kThreadsHalo, smem, st>>>(tmA, tmB, P);
+  else gather_phase_kernel<0><<<ctas, kThreadsHalo, smem, st>>>(tmA, tmB, P);
   MRA_LAUNCH_CHECK();
   return 0;
 }
