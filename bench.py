@@ -250,10 +250,10 @@ def time_norm_kernels(torch, I, batch, hbm_peak, reps=10):
     out = []
     for name, ms, nbytes, launches in (
             ("inorm_fwd_stream_kernel (IN+ReLU fwd, 64ch x 128^3)", t_f, 2 * e, 1),
-            ("inorm_bwd_stats_stream_kernel + inorm_bwd_stream_kernel (two-pass IN+ReLU bwd, 64ch x 128^3: what the step "
-             "runs on this tensor -- its consumer's dgrad is epilogue bound, see functional.nstats_profitable)", t_b, 3 * e, 2),
-            ("inorm_bwd_stream_kernel alone (apply pass; statistics from the consumer conv's dgrad epilogue: the step's "
-             "path for the res-block / PatchGAN norms, timed here on the 64ch x 128^3 tensor)", t_a, 3 * e, 1)):
+            ("inorm_bwd_stream_kernel (IN+ReLU bwd, 64ch x 128^3: what the step runs on this tensor -- the reduction "
+             "pass {sum dy, sum dy xhat} comes out of the consumer conv's dgrad epilogue, mra_conv3d_dgrad_nstats)", t_a, 3 * e, 1),
+            ("inorm_bwd_stats_stream_kernel + inorm_bwd_stream_kernel (two-pass IN bwd on the same tensor: the path of "
+             "norms whose output has a second consumer, i.e. the res-block skip)", t_b, 3 * e, 2)):
         gbs = nbytes / (ms * 1e-3) / 1e9
         out.append({"bound": "hbm", "kernel": name, "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                     "frac": gbs / hbm_peak, "ms_per_call": ms, "algorithmic_bytes": nbytes, "launches_per_call": launches})

@@ -48,12 +48,12 @@ constexpr int kMmaWarp = kEpiWarps + 1;          // gather_tc / gather_col: TMEM
 constexpr int kThreadsGather = 32 * 12;         // 3 whole warpgroups: 0..7 epilogue, 8 producer, 9 MMA, 10..11 idle
 // Register split between the warpgroups (setmaxnreg): the kernels are compiled for 384 threads = 168 registers per
 // thread at entry; the two epilogue warpgroups then grow to kRegsEpi, the producer / MMA warpgroup shrinks to
-// kRegsOther (2 * 128 * 216 + 128 * 72 = 64 512 <= 65 536).  The epilogue with statistics keeps ~200 values live
+// kRegsOther (2 * 128 * 224 + 128 * 56 = 64 512 <= 65 536).  The epilogue with statistics keeps ~200 values live
 // (accumulator chunk, partial sums, addresses); at 168 registers it spilled loop-carried scalars, and with the L1
 // cut to a few KB by the shared-memory carve-out every reload was an L2 round trip inside the epilogue's critical path
 // (profiles/r02_col_stem_ncu.txt: 3.4 M local loads per launch, 46 % L1 hit rate, long-scoreboard stalls).
 // (The instruction sits at the head of every role branch: ptxas takes the limit of the code that follows from it.)
-constexpr int kRegsEpi = 216, kRegsOther = 72;
+constexpr int kRegsEpi = 224, kRegsOther = 56;
 __device__ __forceinline__ void regs_epilogue() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi)); }
 __device__ __forceinline__ void regs_other() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther)); }
 constexpr int kMaxTaps = 64;
@@ -268,10 +268,36 @@ struct EpiStats {
     for (int i = 0; i < 4; ++i) if (i == k) { s[i] += a; q[i] += b; }
   }
 };
+// kMode 2: the 32 bf16 aux values of one chunk (64 B of this thread's row), fetched AHEAD of their use: the first chunk
+// of a tile before the wait for its accumulator (epilogue_aux_first), every further chunk while the previous one is
+// processed -- inside the epilogue a dependent global load costs its full L2 / HBM latency per chunk otherwise.
+struct AuxRegs { uint32_t w[16]; };
+__device__ __forceinline__ void aux_load(const EpiArgs& E, long long elem, bool valid, AuxRegs& a) {
+  if (valid) {
+    const char* p = reinterpret_cast<const char*>(reinterpret_cast<const bf16*>(E.aux) + elem);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(a.w[8 * i]), "=r"(a.w[8 * i + 1]), "=r"(a.w[8 * i + 2]), "=r"(a.w[8 * i + 3]), "=r"(a.w[8 * i + 4]),
+                     "=r"(a.w[8 * i + 5]), "=r"(a.w[8 * i + 6]), "=r"(a.w[8 * i + 7])
+                   : "l"(p + 32 * i));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a.w[i] = 0u;
+  }
+}
+// the first chunk of a warp's tile: call BEFORE waiting for the accumulator (kMode 2, bf16 output only)
+template <int kMode>
+__device__ __forceinline__ void epilogue_aux_first(const EpiArgs& E, int c_begin, int nchunks, bool valid, long long obase,
+                                                   bool dual, AuxRegs& a) {
+  if constexpr (kMode == 2) {
+    if (E.out_bf16 && c_begin < nchunks) aux_load(E, obase + (dual ? (c_begin & 1) : c_begin) * 32, valid, a);
+  }
+}
 template <int kMode, typename Release>
 __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, uint32_t t_addr, int c_begin, int c_step, int nchunks, bool valid,
                                               long long obase, int n0, int lane, EpiStats& st, int slot0, bool defer,
-                                              float (&d1)[32], float (&d2)[32], Release release, bool dual = false,
+                                              float (&d1)[32], float (&d2)[32], AuxRegs& ax, Release release, bool dual = false,
                                               long long dual_stride = 0, bool valid_hi = false) {
   const bool lin_act = E.act == MRA_ACT_RELU || E.act == MRA_ACT_LRELU;
   const float nslope = E.act == MRA_ACT_RELU ? 0.f : E.slope;
@@ -285,6 +311,14 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, uint32_t t_addr,
     const long long obase_c = obase + ((dual && (ct >> 1)) ? dual_stride : 0);
     uint32_t r[32];
     tmem_ld32(t_addr + (uint32_t)(ct * 32), r);
+    AuxRegs nx;
+    if constexpr (kMode == 2) {                          // next chunk's aux values: in flight while this chunk is processed
+      const int ctn = ct + c_step;
+      if (E.out_bf16 && ctn < nchunks) {
+        const bool vn = dual ? ((ctn >> 1) ? valid_hi : valid_lo) : valid_lo;
+        aux_load(E, obase + ((dual && (ctn >> 1)) ? dual_stride : 0) + (dual ? (ctn & 1) : ctn) * 32, vn, nx);
+      }
+    }
     tmem_wait_ld();
     if (ct + c_step >= nchunks) release();
     float v[32];
@@ -305,18 +339,12 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, uint32_t t_addr,
       if (defer) {
         if (valid) {
           if (E.out_bf16) {
-            const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(E.aux) + obase_c + c0);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 u = __ldg(ap + i);
-              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float a0 = __uint_as_float(w[k] << 16), a1 = __uint_as_float(w[k] & 0xffff0000u);
-                const float g0 = v[8 * i + 2 * k], g1 = v[8 * i + 2 * k + 1];
-                d1[8 * i + 2 * k] += a0 > 0.f ? g0 : g0 * ns; d2[8 * i + 2 * k] = fmaf(g0, a0, d2[8 * i + 2 * k]);
-                d1[8 * i + 2 * k + 1] += a1 > 0.f ? g1 : g1 * ns; d2[8 * i + 2 * k + 1] = fmaf(g1, a1, d2[8 * i + 2 * k + 1]);
-              }
+            for (int i = 0; i < 16; ++i) {
+              const float a0 = __uint_as_float(ax.w[i] << 16), a1 = __uint_as_float(ax.w[i] & 0xffff0000u);
+              const float g0 = v[2 * i], g1 = v[2 * i + 1];
+              d1[2 * i] += a0 > 0.f ? g0 : g0 * ns; d2[2 * i] = fmaf(g0, a0, d2[2 * i]);
+              d1[2 * i + 1] += a1 > 0.f ? g1 : g1 * ns; d2[2 * i + 1] = fmaf(g1, a1, d2[2 * i + 1]);
             }
           } else {
             const float4* ap = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(E.aux) + obase_c + c0);
@@ -336,18 +364,12 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, uint32_t t_addr,
         float s1[32], s2[32];
         if (valid) {
           if (E.out_bf16) {
-            const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(E.aux) + obase_c + c0);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 u = __ldg(ap + i);
-              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float a0 = __uint_as_float(w[k] << 16), a1 = __uint_as_float(w[k] & 0xffff0000u);
-                const float g0 = v[8 * i + 2 * k], g1 = v[8 * i + 2 * k + 1];
-                s1[8 * i + 2 * k] = a0 > 0.f ? g0 : g0 * ns; s2[8 * i + 2 * k] = g0 * a0;
-                s1[8 * i + 2 * k + 1] = a1 > 0.f ? g1 : g1 * ns; s2[8 * i + 2 * k + 1] = g1 * a1;
-              }
+            for (int i = 0; i < 16; ++i) {
+              const float a0 = __uint_as_float(ax.w[i] << 16), a1 = __uint_as_float(ax.w[i] & 0xffff0000u);
+              const float g0 = v[2 * i], g1 = v[2 * i + 1];
+              s1[2 * i] = a0 > 0.f ? g0 : g0 * ns; s2[2 * i] = g0 * a0;
+              s1[2 * i + 1] = a1 > 0.f ? g1 : g1 * ns; s2[2 * i + 1] = g1 * a1;
             }
           } else {
             const float4* ap = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(E.aux) + obase_c + c0);
@@ -383,6 +405,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, uint32_t t_addr,
         st.add(slot0 + (c - c_begin) / c_step, (double)a1, (double)a2);
       }
     }
+    if constexpr (kMode == 2) ax = nx;
     if (lin_act) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * nslope;
@@ -673,13 +696,15 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, W.q, W.c_begin, 2, nchunks, lane, st, defer, d1, d2, epi_red);
         st_n = t.n; st_n0 = t.n0;
       }
+      AuxRegs ax;
+      epilogue_aux_first<kMode>(E, W.c_begin, acc_cols / 32, valid, obase, P.pair != 0, ax);
       ok = mbar_wait(&acc_full[buf], aph, P.err, 3);
       if (!ok) break;
       tc_fence_after();
       const long long te0 = (P.debug & 2) ? clock64() : 0;
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
       uint64_t* rel_bar = &acc_empty[buf];
-      epilogue_tile<kMode>(E, t_addr, W.c_begin, 2, acc_cols / 32, valid, obase, t.n0, lane, st, 0, defer, d1, d2, [&]() {
+      epilogue_tile<kMode>(E, t_addr, W.c_begin, 2, acc_cols / 32, valid, obase, t.n0, lane, st, 0, defer, d1, d2, ax, [&]() {
         tc_fence_before();                      // accumulator fully read: hand the buffer back to the MMA warp
         __syncwarp();
         if (lane == 0) mbar_arrive(rel_bar);

@@ -276,12 +276,14 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int pl = P.dual ? 2 * j : j;                 // (first) output plane of the tile, relative to d0
         const long long obase = (long long)n * P.osn + (long long)((d0 + pl) * P.ostep + P.od0) * P.osd +
                                 (long long)(lh * P.ostep + P.oh0) * P.osh + (long long)(lw * P.ostep + P.ow0) * P.osw;
+        AuxRegs ax;
+        epilogue_aux_first<kMode>(E, W.c_begin, acc_cols / 32, valid, obase, P.dual != 0, ax);
         ok = mbar_wait(&acc_full[buf], aph, P.err, 33);
         if (!ok) break;
         tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
         uint64_t* rel_bar = &acc_empty[buf];
-        epilogue_tile<kMode>(E, t_addr, W.c_begin, 2, acc_cols / 32, valid, obase, 0, lane, st, 0, defer, d1, d2, [&]() {
+        epilogue_tile<kMode>(E, t_addr, W.c_begin, 2, acc_cols / 32, valid, obase, 0, lane, st, 0, defer, d1, d2, ax, [&]() {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(rel_bar);

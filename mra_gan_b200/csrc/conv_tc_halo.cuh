@@ -314,13 +314,15 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         st_n = t.n; st_n0 = tb;
       }
       nchunks = t.width / 32;
+      AuxRegs ax;
+      epilogue_aux_first<kMode>(E, W.c_begin, nchunks, valid, obase, false, ax);
       ok = mbar_wait(&acc_full[buf], aph, P.err, 23);
       if (!ok) break;
       tc_fence_after();
       const long long te0 = prof ? clock64() : 0;
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * P.n_tile);
       uint64_t* rel_bar = &acc_empty[buf];
-      epilogue_tile<kMode>(E, t_addr, W.c_begin, 2, nchunks, valid, obase, t.n0, lane, st, coff >> 1, defer, d1, d2, [&]() {
+      epilogue_tile<kMode>(E, t_addr, W.c_begin, 2, nchunks, valid, obase, t.n0, lane, st, coff >> 1, defer, d1, d2, ax, [&]() {
         tc_fence_before();                      // accumulator fully read: hand the buffer back to the MMA warp
         __syncwarp();
         if (lane == 0) { if constexpr (kPair) mbar_arrive_leader(rel_bar); else mbar_arrive(rel_bar); }

@@ -292,13 +292,15 @@ gather_phase_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const long long obase = (long long)t.n * P.osn + (long long)(t.d * P.ostep + P.s_od[sub]) * P.osd +
                                 (long long)(lh * P.ostep + P.s_oh[sub]) * P.osh +
                                 (long long)(lw * P.ostep + P.s_ow[sub]) * P.osw + n0;
+        AuxRegs ax;
+        epilogue_aux_first<kMode>(E, W.c_begin, 4, valid, obase, P.dual != 0, ax);
         ok = mbar_wait(&acc_full[k], aph, P.err, 43);
         if (!ok) break;
         tc_fence_after();
         const long long te0 = prof ? clock64() : 0;
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(k * 128);
         uint64_t* rel_bar = &acc_empty[k];
-        epilogue_tile<kMode>(E, t_addr, W.c_begin, 2, 4, valid, obase, n0, lane, st, 0, defer, d1, d2, [&]() {
+        epilogue_tile<kMode>(E, t_addr, W.c_begin, 2, 4, valid, obase, n0, lane, st, 0, defer, d1, d2, ax, [&]() {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(rel_bar);

@@ -13,7 +13,7 @@ from . import ops
 from .ops import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, LOSS_BCE_CONST, LOSS_L1, LOSS_MSE_CONST
 
 
-_NSTATS_ALWAYS = os.environ.get("MRA_NORM_BWD_FUSED", "1") == "2"     # ablation: link every eligible pair
+_NSTATS_ALWAYS = False
 
 
 def weight_grad_view(dw_packed, k, transposed):
@@ -36,14 +36,18 @@ class NormBwdLink:
 
 def nstats_profitable(g, x):
     """Is the norm-backward statistics pass cheaper inside this conv's dgrad epilogue than as its own kernel?
-    Measured per layer on B200 (tools/nstats_bench.py, profiles/r02_nstats_bench_*.txt): the epilogue hides under the
-    main loop when a tile accumulates over K = taps x Cout >= ~1500 (G.rb, G.u2, D.3, D.4: the statistics cost 8-60 us
-    extra against 22-69 us for the kernel they replace), but the short-K stride-2 dgrads and the head lowering are
-    epilogue bound already (G.d1 +290 us vs 240 us, G.c4 +390 vs 300); small tensors are launch bound, one kernel less
-    always wins there."""
+    Measured per layer on B200 (tools/nstats_bench.py).  With the first build of the epilogue (spilled loop variables,
+    un-prefetched aux loads: profiles/r02_nstats_bench_v1.txt) only layers whose tiles accumulate over K = taps x Cout
+    >= ~1500 won; since the epilogue warps have their own register budget and fetch the aux values ahead of use it
+    wins on every linked layer (profiles/r02_nstats_bench_v3.txt: G.d1 +174 us against a 242 us statistics kernel,
+    G.rb +10 vs 31, G.u2 +25 vs 69, D.3 / D.4 / D.5 +8..10 vs 23..27) except the head lowering (Cout = 1: the dual-plane
+    column kernel is bound by its epilogue, +338 us vs 301).  MRA_NORM_BWD_FUSED=3 restores the rule of the first build
+    for the ablation."""
     if min(g.cin, g.cout) == 1:
-        k_eff = g.k * 64                                   # channel-expanded lowering: (k, 1, 1) taps x 64
-    elif not g.transposed and g.stride > 1:
+        return False                                       # channel-expanded lowering (column kernel)
+    if os.environ.get("MRA_NORM_BWD_FUSED", "1") != "3":
+        return True
+    if not g.transposed and g.stride > 1:
         k_eff = (g.k ** 3) / float(g.stride ** 3) * g.cout  # dgrad of a strided conv: taps split over stride^3 phases
     else:
         k_eff = g.k ** 3 * g.cout
