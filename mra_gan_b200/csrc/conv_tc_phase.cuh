@@ -420,10 +420,11 @@ inline bool phase_setup(const GatherPlan& plan, const GatherRun& R, PhaseP& P) {
   // ---- shared memory: a plane ring of up to 3 chunks' worth, the rest for the weight ring (>= 3 stages)
   const size_t budget = kSmemLimit - 2048 - kEpiRedBytes;
   int NP = 3 * max_nd;
+  { const char* e = getenv("MRA_PHASE_NP"); if (e && atoi(e) >= max_nd && atoi(e) <= 4 * max_nd) NP = atoi(e); }
   while (NP > max_nd + 1 && (size_t)NP * P.slot_bytes + 3 * (size_t)(128 * 128) > budget) --NP;
   if ((size_t)NP * P.slot_bytes + 3 * (size_t)(128 * 128) > budget) return false;
   int NB = (int)((budget - (size_t)NP * P.slot_bytes) / (128 * 128));
-  if (NB > 8) NB = 8;
+  if (NB > 10) NB = 10;
   P.NP = NP; P.NB = NB;
   const long long total = (long long)plan.n * P.n_tiles * P.Dl * P.tiles_hw * P.ngroups;
   if (total >= (1ll << 31)) return false;
