@@ -9,6 +9,7 @@
 #include <string.h>
 #include <atomic>
 #include <string>
+#include <utility>
 
 #include "../../include/mra_gan_b200.h"
 
@@ -45,6 +46,50 @@ extern std::atomic<long long> g_launch_count;
     ::mra::g_launch_count.fetch_add(1, std::memory_order_relaxed);                        \
     MRA_CHECK_CUDA(cudaGetLastError());                                                   \
   } while (0)
+
+// ---- programmatic dependent launch (PDL) ----
+// A step is ~1100 launches of persistent, one-CTA-per-SM kernels; between two dependent kernels the stream (or graph)
+// pays the launch / dependency latency and the successor's prologue (barrier init, tensor-map prefetch, TMEM
+// allocation) in series: ~5 us per boundary, ~5 % of the step (sum of kernel durations 116 ms vs a 122 ms step).
+// The hot kernels therefore (a) let their successor launch at once (griddepcontrol.launch_dependents as their first
+// instruction: its CTAs become resident SM by SM as ours retire and run their prologue), (b) wait for their
+// predecessors (griddepcontrol.wait: full completion + memory visibility) after the prologue and BEFORE the first
+// global-memory access -- reads of anything a predecessor wrote, and writes, which could hit a buffer a predecessor
+// still reads.  Every PDL-launched kernel executes the wait, so ordering stays transitive.
+// MEASURED (profiles/r02_pdl_ab.txt, driver command, A/B/A/B on one box): 123.15 / 123.39 ms with the attribute,
+// 122.83 / 122.93 ms without -- no gain: a persistent one-CTA-per-SM kernel with ~200 KB of shared memory cannot
+// become resident before its predecessor's CTA on that SM has retired, so there is no prologue to overlap.  The
+// attribute is therefore OFF by default (MRA_PDL=1 switches it on; without it the device instructions are no-ops).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("MRA_PDL"); on = (e && atoi(e) != 0) ? 1 : 0; }
+  return on != 0;
+}
+// kernel<<<grid, block, smem, st>>>(args...) with the programmatic-stream-serialization attribute (+ an optional
+// cluster dimension)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster_x > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)cluster_x; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = (unsigned)na;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 inline int num_sms() {
   static int n = 0;

@@ -551,6 +551,7 @@ template <int kMode>         // epilogue statistics mode, see epilogue_tile
 __global__ void __launch_bounds__(kThreadsGather, 1)
 gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ GatherP P) {
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t slab_bytes = (uint32_t)P.n_tile * 128u;
@@ -578,6 +579,7 @@ gather_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                  // prologue done: from here on global memory is touched
 
   if (warp >= kEpiWarps) {            // third warpgroup: producers, MMA issuer, idle warps -- one setmaxnreg for all of it
   regs_other();
@@ -899,6 +901,7 @@ template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ WMaps tmN,
                 const __grid_constant__ WgradP P) {
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -949,6 +952,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
   if constexpr (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                  // prologue done: from here on global memory is touched
   const bool prof = (P.debug & 2) != 0;
 
   if (warp == 0) {
@@ -1387,9 +1391,9 @@ inline int run_gather_v1_launch(const GatherPlan& plan, const GatherLaunch* Ls, 
                             P.astep))
     return rc;
   const int ctas = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
-  if (P.aux && P.stats) gather_tc_kernel<2><<<ctas, kThreadsGather, smem, st>>>(tmA, tmB, P);
-  else if (P.stats) gather_tc_kernel<1><<<ctas, kThreadsGather, smem, st>>>(tmA, tmB, P);
-  else gather_tc_kernel<0><<<ctas, kThreadsGather, smem, st>>>(tmA, tmB, P);
+  if (P.aux && P.stats) MRA_CHECK_CUDA(launch_pdl(gather_tc_kernel<2>, dim3(ctas), dim3(kThreadsGather), smem, st, 1, tmA, tmB, P));
+  else if (P.stats) MRA_CHECK_CUDA(launch_pdl(gather_tc_kernel<1>, dim3(ctas), dim3(kThreadsGather), smem, st, 1, tmA, tmB, P));
+  else MRA_CHECK_CUDA(launch_pdl(gather_tc_kernel<0>, dim3(ctas), dim3(kThreadsGather), smem, st, 1, tmA, tmB, P));
   MRA_LAUNCH_CHECK();
   return 0;
 }
@@ -1484,17 +1488,7 @@ inline int run_wgrad_tc(const WgradPlan& plan, const void* x, const void* dy, fl
   P.tmem_cols = pow2_cols(max_cols);
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
   if (pair) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)(num_sms() & ~1), 1, 1);
-    cfg.blockDim = dim3(kThreads, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    MRA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<true>, tmM, maps, P));
+    MRA_CHECK_CUDA(launch_pdl(wgrad_tc_kernel<true>, dim3((unsigned)(num_sms() & ~1)), dim3(kThreads), smem, st, 2, tmM, maps, P));
     MRA_LAUNCH_CHECK();
     return 0;
   }
@@ -1502,7 +1496,7 @@ inline int run_wgrad_tc(const WgradPlan& plan, const void* x, const void* dy, fl
   long long ctas = num_sms();
   if (P.total_cost < ctas * 4) ctas = (P.total_cost + 3) / 4;
   if (ctas < 1) ctas = 1;
-  wgrad_tc_kernel<false><<<(unsigned)ctas, kThreads, smem, st>>>(tmM, maps, P);
+  MRA_CHECK_CUDA(launch_pdl(wgrad_tc_kernel<false>, dim3((unsigned)ctas), dim3(kThreads), smem, st, 1, tmM, maps, P));
   MRA_LAUNCH_CHECK();
   return 0;
 }

@@ -50,6 +50,7 @@ template <int kMode>
 __global__ void __launch_bounds__(kThreadsGather, 1)
 gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ ColP P) {
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t slab_bytes = (uint32_t)P.n_tile * 128u;                 // one (tap, channel chunk) weight slab
@@ -79,6 +80,7 @@ gather_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                  // prologue done: from here on global memory is touched
 
   // unit -> (n, hw tile, first plane, number of planes)
   auto unit_coords = [&](int u, int& n, int& h0, int& w0, int& d0, int& len) {
@@ -371,9 +373,9 @@ inline int run_gather_col(const GatherPlan& plan, const GatherLaunch& L, ColP& P
   if (int rc = make_act_map(&tmA, R.a, plan.n, plan.adims[0], plan.adims[1], plan.adims[2], plan.ck, 8, 16, 1, 1)) return rc;
   const size_t smem = (size_t)P.kd * P.kchunks * P.n_tile * 128 + (size_t)P.NPR * kABytes * P.kchunks + 1024 + 512;
   const int ctas = P.total_units < num_sms() ? P.total_units : num_sms();
-  if (P.aux && P.stats) gather_col_kernel<2><<<ctas, kThreadsGather, smem, st>>>(tmA, tmB, P);
-  else if (P.stats) gather_col_kernel<1><<<ctas, kThreadsGather, smem, st>>>(tmA, tmB, P);
-  else gather_col_kernel<0><<<ctas, kThreadsGather, smem, st>>>(tmA, tmB, P);
+  if (P.aux && P.stats) MRA_CHECK_CUDA(launch_pdl(gather_col_kernel<2>, dim3(ctas), dim3(kThreadsGather), smem, st, 1, tmA, tmB, P));
+  else if (P.stats) MRA_CHECK_CUDA(launch_pdl(gather_col_kernel<1>, dim3(ctas), dim3(kThreadsGather), smem, st, 1, tmA, tmB, P));
+  else MRA_CHECK_CUDA(launch_pdl(gather_col_kernel<0>, dim3(ctas), dim3(kThreadsGather), smem, st, 1, tmA, tmB, P));
   MRA_LAUNCH_CHECK();
   return 0;
 }

@@ -99,6 +99,7 @@ template <bool kPair, int kMode>
 __global__ void __launch_bounds__(kThreadsHalo, 1)
 gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ HaloP P) {
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kCtas = kPair ? 2 : 1;
@@ -152,6 +153,7 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if constexpr (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                  // prologue done: from here on global memory is touched
 
   const bool dbg_nob = (P.debug & 4) != 0, dbg_nop = (P.debug & 8) != 0;     // timing experiments: no weight / plane traffic
   if (warp >= kEpiWarps) {            // third warpgroup: producers, MMA issuer, idle warps -- one setmaxnreg for all of it
@@ -457,25 +459,16 @@ inline int run_gather_halo(const GatherPlan& plan, const GatherLaunch& L, HaloP&
   const size_t smem = (size_t)P.NP * P.slot_bytes + (size_t)P.NB * P.n_tile * 128 / (P.pair ? 2 : 1) + 1024 + 256;
   if (!P.pair) {
     const int ctas = P.total_work < num_sms() ? P.total_work : num_sms();
-    if (P.aux && P.stats) gather_halo_kernel<false, 2><<<ctas, kThreadsHalo, smem, st>>>(tmA, tmB, P);
-    else if (P.stats) gather_halo_kernel<false, 1><<<ctas, kThreadsHalo, smem, st>>>(tmA, tmB, P);
-    else gather_halo_kernel<false, 0><<<ctas, kThreadsHalo, smem, st>>>(tmA, tmB, P);
+    if (P.aux && P.stats) MRA_CHECK_CUDA(launch_pdl(gather_halo_kernel<false, 2>, dim3(ctas), dim3(kThreadsHalo), smem, st, 1, tmA, tmB, P));
+    else if (P.stats) MRA_CHECK_CUDA(launch_pdl(gather_halo_kernel<false, 1>, dim3(ctas), dim3(kThreadsHalo), smem, st, 1, tmA, tmB, P));
+    else MRA_CHECK_CUDA(launch_pdl(gather_halo_kernel<false, 0>, dim3(ctas), dim3(kThreadsHalo), smem, st, 1, tmA, tmB, P));
   } else {
     int pairs = num_sms() / 2;
     if (P.total_work < pairs) pairs = P.total_work;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)(2 * pairs), 1, 1);
-    cfg.blockDim = dim3(kThreadsHalo, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    if (P.aux && P.stats) MRA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gather_halo_kernel<true, 2>, tmA, tmB, P));
-    else if (P.stats) MRA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gather_halo_kernel<true, 1>, tmA, tmB, P));
-    else MRA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gather_halo_kernel<true, 0>, tmA, tmB, P));
+    const dim3 grid((unsigned)(2 * pairs));
+    if (P.aux && P.stats) MRA_CHECK_CUDA(launch_pdl(gather_halo_kernel<true, 2>, grid, dim3(kThreadsHalo), smem, st, 2, tmA, tmB, P));
+    else if (P.stats) MRA_CHECK_CUDA(launch_pdl(gather_halo_kernel<true, 1>, grid, dim3(kThreadsHalo), smem, st, 2, tmA, tmB, P));
+    else MRA_CHECK_CUDA(launch_pdl(gather_halo_kernel<true, 0>, grid, dim3(kThreadsHalo), smem, st, 2, tmA, tmB, P));
   }
   MRA_LAUNCH_CHECK();
   return 0;

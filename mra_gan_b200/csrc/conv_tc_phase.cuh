@@ -83,6 +83,7 @@ template <int kMode>
 __global__ void __launch_bounds__(kThreadsHalo, 1)
 gather_phase_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ PhaseP P) {
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr uint32_t kBStage = 128 * 128;                      // one weight stage: up to 128 rows x 64 channels
@@ -112,6 +113,7 @@ gather_phase_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
   const bool prof = (P.debug & 2) != 0;
   // Every CTA walks the channel chunks and the sub-items of a work item in its own ROTATED order (sums are order-free,
   // the accumulate flags follow the iteration index): at any moment the SMs then stream different weight slabs
@@ -454,9 +456,9 @@ inline int run_gather_phase(const GatherPlan& plan, PhaseP& P, const GatherRun& 
   if (int rc = make_weight_map(&tmB, R.b, (long long)R.slabs * plan.cn, plan.ck, P.dual ? 64 : 128)) return rc;
   const size_t smem = (size_t)P.NP * P.slot_bytes + (size_t)P.NB * 128 * 128 + 1024 + 512;
   const int ctas = P.total_items < num_sms() ? P.total_items : num_sms();
-  if (P.aux && P.stats) gather_phase_kernel<2><<<ctas, kThreadsHalo, smem, st>>>(tmA, tmB, P);
-  else if (P.stats) gather_phase_kernel<1><<<ctas, kThreadsHalo, smem, st>>>(tmA, tmB, P);
-  else gather_phase_kernel<0><<<ctas, kThreadsHalo, smem, st>>>(tmA, tmB, P);
+  if (P.aux && P.stats) MRA_CHECK_CUDA(launch_pdl(gather_phase_kernel<2>, dim3(ctas), dim3(kThreadsHalo), smem, st, 1, tmA, tmB, P));
+  else if (P.stats) MRA_CHECK_CUDA(launch_pdl(gather_phase_kernel<1>, dim3(ctas), dim3(kThreadsHalo), smem, st, 1, tmA, tmB, P));
+  else MRA_CHECK_CUDA(launch_pdl(gather_phase_kernel<0>, dim3(ctas), dim3(kThreadsHalo), smem, st, 1, tmA, tmB, P));
   MRA_LAUNCH_CHECK();
   return 0;
 }

@@ -169,9 +169,11 @@ __global__ void __launch_bounds__(CONS + 32, 1) inorm_fwd_stream_kernel(const T*
                                                                          float* running_mean, float* running_var,
                                                                          const T* __restrict__ res, T* __restrict__ y,
                                                                          const StreamP S) {
+  pdl_launch_dependents();
   extern __shared__ __align__(128) unsigned char smem[];
   const NormP& P = S.P;
   Ring R = ring_setup<CONS>(smem, S);
+  pdl_wait();                                  // barriers are set up: from here on global memory is touched
   const int n = blockIdx.y, t = threadIdx.x;
   const int p = P.pad, rp = P.res_pad;
   const int Hp = P.H + 2 * p, Wp = P.W + 2 * p, Dp = P.D + 2 * p;
@@ -340,9 +342,11 @@ __global__ void __launch_bounds__(CONS + 32, 1) inorm_bwd_stats_stream_kernel(co
                                                                                const float* __restrict__ mean,
                                                                                const float* __restrict__ rstd,
                                                                                double* __restrict__ sums, const StreamP S) {
+  pdl_launch_dependents();
   extern __shared__ __align__(128) unsigned char smem[];
   const NormP& P = S.P;
   Ring R = ring_setup<CONS>(smem, S);
+  pdl_wait();                                  // barriers are set up: from here on global memory is touched
   const int n = blockIdx.y, t = threadIdx.x;
   const int G = P.G, cg = t & (G - 1), wl = t >> S.lgG, wpp = CONS >> S.lgG, lane = t & 31;
   F8 s, ss;
@@ -408,9 +412,11 @@ __global__ void __launch_bounds__(CONS + 32, 1) inorm_bwd_stream_kernel(const T*
                                                                          const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                          const double* __restrict__ sums, T* __restrict__ dx,
                                                                          T* __restrict__ dres, const StreamP S) {
+  pdl_launch_dependents();
   extern __shared__ __align__(128) unsigned char smem[];
   const NormP& P = S.P;
   Ring R = ring_setup<CONS>(smem, S);
+  pdl_wait();                                  // barriers are set up: from here on global memory is touched
   const int n = blockIdx.y, t = threadIdx.x;
   if (t >= CONS) {
     if (t == CONS) bwd_producer<T>(R, S, gy, x, n);
@@ -557,8 +563,9 @@ int norm_fwd_stream_launch(const StreamP& S, const void* x, const double* stats,
                            float* rstd, float* rm, float* rv, cudaStream_t st) {
   static bool attr = false;
   if (!attr) { if (int rc = stream_attr(inorm_fwd_stream_kernel<T, CONS>)) return rc; attr = true; }
-  inorm_fwd_stream_kernel<T, CONS><<<stream_grid(S), CONS + 32, stream_smem(S), st>>>(
-      reinterpret_cast<const T*>(x), stats, mean, rstd, rm, rv, reinterpret_cast<const T*>(res), reinterpret_cast<T*>(y), S);
+  MRA_CHECK_CUDA(launch_pdl(inorm_fwd_stream_kernel<T, CONS>, stream_grid(S), dim3(CONS + 32), stream_smem(S), st, 1,
+                            reinterpret_cast<const T*>(x), stats, mean, rstd, rm, rv, reinterpret_cast<const T*>(res),
+                            reinterpret_cast<T*>(y), S));
   MRA_LAUNCH_CHECK();
   return 0;
 }
@@ -583,14 +590,14 @@ int norm_bwd_stream_launch(const mra_norm_desc& d, const StreamP& S, const void*
   }
   if (d.use_running != 1 && (phases & 1)) {
     MRA_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * d.n * d.c, st));
-    inorm_bwd_stats_stream_kernel<T, CONS, U><<<stream_grid(S), CONS + 32, stream_smem(S), st>>>(
-        reinterpret_cast<const T*>(gy), reinterpret_cast<const T*>(x), mean, rstd, sums, S);
+    MRA_CHECK_CUDA(launch_pdl(inorm_bwd_stats_stream_kernel<T, CONS, U>, stream_grid(S), dim3(CONS + 32), stream_smem(S), st, 1,
+                              reinterpret_cast<const T*>(gy), reinterpret_cast<const T*>(x), mean, rstd, sums, S));
     MRA_LAUNCH_CHECK();
   }
   if (!(phases & 2)) return 0;
-  inorm_bwd_stream_kernel<T, CONS, U><<<stream_grid(S), CONS + 32, stream_smem(S), st>>>(
-      reinterpret_cast<const T*>(gy), reinterpret_cast<const T*>(x), mean, rstd, sums, reinterpret_cast<T*>(dx),
-      reinterpret_cast<T*>(dres), S);
+  MRA_CHECK_CUDA(launch_pdl(inorm_bwd_stream_kernel<T, CONS, U>, stream_grid(S), dim3(CONS + 32), stream_smem(S), st, 1,
+                            reinterpret_cast<const T*>(gy), reinterpret_cast<const T*>(x), mean, rstd,
+                            static_cast<const double*>(sums), reinterpret_cast<T*>(dx), reinterpret_cast<T*>(dres), S));
   MRA_LAUNCH_CHECK();
   return 0;
 }
