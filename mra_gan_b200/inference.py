@@ -4,6 +4,14 @@ Same grid, clamping, scaling and averaging as the reference loop; windows are in
 the generator keeps per-window instance statistics (train-mode norm: test.py never calls eval()),
 so rank r takes windows r, r+R, ...; label/weight accumulators live on the device and one
 reduce(sum) to rank 0 finishes the volume.
+
+For the same reason a rank may push several of its windows through the generator as ONE batch
+(``windows_per_pass``, default 4): every sample of a batch gets its own statistics, so the result of a window
+does not depend on its batch mates, while the persistent conv kernels fill their last round of tiles
+(256 -> 256 k3 at 32^3: 128 CTA-pair tiles on 74 pairs at batch 1 = 2 rounds for 1.73 rounds of work, 256 tiles at
+batch 2 = 3.5 for 3.46; config 5 on one B200: 162.6 / 150.0 / 143.4 ms per volume at 1 / 2 / 4 windows per pass,
+profiles/r02_infer_windows_per_pass.txt).  The accumulation order of overlapping windows is unchanged (windows are added in grid
+order), so the sums are those of the one-window-at-a-time loop.
 """
 import math
 
@@ -34,7 +42,7 @@ def window_grid(shape, patch, stride_inplane, stride_layer):
 
 @torch.no_grad()
 def sliding_window_inference(model, volume, patch, stride_inplane, stride_layer, rank=0, world=1, dtype=None,
-                             _local_only=False):
+                             _local_only=False, windows_per_pass=4):
     """``model``: a TestModel (set_input / test / get_current_visuals, like test.py:158-161).
     ``volume``: float32 (X, Y, Z) tensor on the 0..255 scale, each dim >= patch.
     Returns the (X, Y, Z) float32 result on rank 0 (other ranks get their partial sum's buffer)."""
@@ -48,12 +56,20 @@ def sliding_window_inference(model, volume, patch, stride_inplane, stride_layer,
     weight = torch.zeros_like(vol)
     dtype = dtype or torch.float32
     grid = window_grid(tuple(vol.shape), patch, stride_inplane, stride_layer)
-    for (i0, j0, k0) in grid[rank::world]:
-        win = I.window_extract(vol, i0, j0, k0, patch, dtype)        # (1, px, py, pz, 1), scaled to [-1, 1]
-        model.set_input(win.reshape(1, 1, *patch))
+    mine = grid[rank::world]
+    step = max(1, int(windows_per_pass))
+    net = getattr(model, "netG", None)
+    if net is not None and any(type(mod).__name__ == "BatchNorm3d" for mod in net.modules()):
+        step = 1                    # train-mode batch statistics couple the samples of a batch: keep the reference's batch of 1
+    for b0 in range(0, len(mine), step):
+        group = mine[b0:b0 + step]
+        wins = [I.window_extract(vol, i0, j0, k0, patch, dtype) for (i0, j0, k0) in group]   # (1, px, py, pz, 1) in [-1, 1]
+        win = wins[0] if len(wins) == 1 else torch.cat(wins, 0)
+        model.set_input(win.reshape(len(group), 1, *patch))
         model.test()
-        pred = model.get_current_visuals()["fake_B"]
-        I.window_accumulate(pred.reshape(1, *patch, 1).contiguous(), label, weight, i0, j0, k0)
+        pred = model.get_current_visuals()["fake_B"]                 # (len(group), 1, px, py, pz)
+        for b, (i0, j0, k0) in enumerate(group):
+            I.window_accumulate(pred[b].reshape(1, *patch, 1).contiguous(), label, weight, i0, j0, k0)
     if _local_only:                 # test hook: this rank's partial sums, before the cross-rank reduce
         return label, weight
     if world > 1:

@@ -50,7 +50,9 @@ def test_sliding_window_matches_reference_fixture(golden_dir, tmp_path):
     vol = np.random.RandomState(r["vol_seed"]).uniform(0, 255, size=r["shape"]).astype(np.float32)
     out = inference.sliding_window_inference(model, torch.from_numpy(vol), r["patch"], *r["stride"])
     assert tuple(out.shape) == tuple(r["shape"])
-    assert float((out - r["label"]).abs().max()) < 2e-3            # 0..255 scale
+    # 0..255 scale.  5e-3 = 4e-5 on the generator's [-1, 1] output: the default loop sends two windows per pass, and the
+    # CPU oracle's batched fp32 convolution sums in another order than its batch-1 call (2.1e-3 measured here)
+    assert float((out - r["label"]).abs().max()) < 5e-3
     # sharding: the union of the ranks' partial sums equals the single-rank result
     parts = []
     for rank in range(3):
@@ -60,4 +62,19 @@ def test_sliding_window_matches_reference_fixture(golden_dir, tmp_path):
     label = sum(p[0] for p in parts)
     weight = sum(p[1] for p in parts)
     merged = (label / weight + 0.01)[:, :, :r["shape"][2]]
-    assert float((merged - r["label"]).abs().max()) < 2e-3
+    assert float((merged - r["label"]).abs().max()) < 5e-3
+
+
+def test_windows_per_pass_does_not_change_the_result(golden_dir, tmp_path):
+    """Several windows through the generator as one batch (per-sample instance statistics) == one window at a time."""
+    r = torch.load(os.path.join(golden_dir, "sliding_window_small.pt"), weights_only=False)
+    sd = OF.make_weights(OF.resnet_g_spec(1, 1, 8, 9), r["weight_seed"], scale=r["weight_scale"])
+    model = _test_model(tmp_path, sd)
+    vol = torch.from_numpy(np.random.RandomState(r["vol_seed"]).uniform(0, 255, size=r["shape"]).astype(np.float32))
+    one = inference.sliding_window_inference(model, vol, r["patch"], *r["stride"], windows_per_pass=1)
+    for wpp in (2, 3):
+        many = inference.sliding_window_inference(model, vol, r["patch"], *r["stride"], windows_per_pass=wpp)
+        # 0..255 scale; the CPU oracle's fp32 convolution sums in a batch-dependent order (1.6e-3 measured), the CUDA
+        # kernels do not (tests/test_options_gpu.py holds the tight version of this check)
+        assert float((many - one).abs().max()) < 5e-3
+    assert float((one - r["label"]).abs().max()) < 2e-3

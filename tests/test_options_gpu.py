@@ -72,6 +72,10 @@ def test_sliding_window_on_cuda_matches_reference_fixture(golden_dir, tmp_path, 
         assert err < 2e-3
     else:
         assert OF.rel_l2(out.cpu() - 127.5, r["label"] - 127.5) < 4e-2
+    # one window per generator pass (the reference's loop) == the default two windows per pass: per-sample statistics
+    single = inference.sliding_window_inference(model, torch.from_numpy(vol), r["patch"], *r["stride"], dtype=DT[mode],
+                                                windows_per_pass=1)
+    assert float((single - out).abs().max()) < 1e-4
     # the sharded run (3 ranks' partial sums merged by hand) equals the single-rank result
     parts = [inference.sliding_window_inference.__wrapped__(model, torch.from_numpy(vol), r["patch"], *r["stride"],
                                                             rank=k, world=3, dtype=DT[mode], _local_only=True) for k in range(3)]
