@@ -91,7 +91,7 @@ class CycleGANModel(BaseModel):
             for net in (self.netG_A, self.netG_B, self.netD_A, self.netD_B):
                 for m in net.conv_modules():
                     m.make_shadow(net.compute_dtype)
-                networks3D.set_fused_wgrad(net, True)       # parallel.attach() turns it off again (bucket hooks)
+                networks3D.set_fused_wgrad(net, True)       # parallel.attach() keeps it unless MRA_DP_FUSED_WGRAD=0
         self.grad_sync = None        # set by parallel.DataParallelTrainer
         self._graphs = None          # CUDA-graph replay of the step (enable_cuda_graphs)
 

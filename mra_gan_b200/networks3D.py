@@ -52,8 +52,9 @@ class _WeightsEpoch:
 
 def set_fused_wgrad(net, flag=True):
     """Let the wgrad kernels of ``net`` accumulate straight into ``weight.grad`` when a weight is used several times
-    per step (functional.ConvFn.backward).  Off under data parallelism: the gradient-bucket hooks need autograd's
-    AccumulateGrad to fire for every parameter."""
+    per step (functional.ConvFn.backward).  Under data parallelism (parallel.attach) it stays on by default -- the
+    kernels add into the gradient-bucket views and the bucket hooks still fire once per parameter (measured: 0 late
+    bucket launches); MRA_DP_FUSED_WGRAD=0 / attach(fused_wgrad=False) hands every gradient to autograd instead."""
     for m in net.modules():
         if isinstance(m, _ConvNd):
             m.fuse_wgrad = bool(flag)
