@@ -67,7 +67,7 @@ __device__ __forceinline__ uint64_t desc_kmajor_sw128_sbo(uint32_t saddr, uint32
          (2ull << 61);
 }
 
-struct HaloTile { int n, d, n0, h0, w0, f0, hs, roff, width; };
+struct HaloTile { int n, d, n0, h0, w0, f0, hs, roff, width; int rot_kc0, rot_td0, rot_th0, rot_tw0, rot_t; };
 // work index -> coordinates.  Order: n_tile fastest, then the tiles of a plane, then d (pair mode: pairs of
 // planes, CTA rank r takes d = 2 * dp + r so both tiles share the weight slab and the in-plane geometry), then n.
 __device__ __forceinline__ HaloTile halo_decode(const HaloP& P, int work, int pair, int rank) {
@@ -84,6 +84,19 @@ __device__ __forceinline__ HaloTile halo_decode(const HaloP& P, int work, int pa
   const int dq = tile % dsteps;
   t.d = pair ? 2 * dq + rank : dq;            // may be == Dl for the odd plane's partner: loads hit zero fill, nothing is stored
   t.n = tile / dsteps;
+  // The (channel chunk, td) planes and the (th, tw) taps of a plane are walked in a ROTATED order (the sum over taps is
+  // order-free): CTAs that run side by side work on consecutive tiles, so at any moment the SMs stream different weight
+  // slabs instead of all 148 hammering the same 32 KB of L2.  The rotation is a function of the tile's position INSIDE
+  // ITS SAMPLE -- not of the CTA that happens to run it -- so the fp32 accumulation order of an output element, and with
+  // it every bit of a sample's result, is independent of the batch size and of how the schedule deals tiles to CTAs.
+  {
+    const int key = dq * P.tiles_hw + j;
+    const int nplanes = P.kchunks * P.kd, taps_hw = P.kh * P.kw;
+    const int rot_p = key % nplanes;
+    t.rot_t = (key / nplanes) % taps_hw;
+    t.rot_kc0 = rot_p / P.kd; t.rot_td0 = rot_p - t.rot_kc0 * P.kd;
+    t.rot_th0 = t.rot_t / P.kw; t.rot_tw0 = t.rot_t - t.rot_th0 * P.kw;
+  }
   t.n0 = nt * P.n_tile + half * t.width;
   if (P.mode == 0) {
     t.h0 = (j / P.tiles_w) * 16; t.w0 = (j % P.tiles_w) * 8;
@@ -123,14 +136,7 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int wstride = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int taps_hw = P.kh * P.kw;
   const bool prof = (P.debug & 2) != 0;
-  // Every CTA walks the (channel chunk, td) planes and the (th, tw) taps of a plane in its own ROTATED order
-  // (the sum over taps is order-free): at any moment the SMs then stream different weight slabs, instead of
-  // all 148 hammering the same 32 KB of L2 at once.
-  const int nplanes = P.kchunks * P.kd;
-  const int rot_p = work0 % nplanes;
-  const int rot_t = (work0 / nplanes) % taps_hw;
-  const int rot_kc0 = rot_p / P.kd, rot_td0 = rot_p - rot_kc0 * P.kd;
-  const int rot_th0 = rot_t / P.kw, rot_tw0 = rot_t - rot_th0 * P.kw;
+  const int nplanes = P.kchunks * P.kd;        // walked in a per-tile rotated order: HaloTile::rot_* (halo_decode)
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
@@ -166,7 +172,7 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       bool ok = true;
       for (int w = work0; w < P.total_work && ok; w += wstride) {
         const HaloTile t = halo_decode(P, w, kPair, rank);
-        int kc = rot_kc0, td = rot_td0;
+        int kc = t.rot_kc0, td = t.rot_td0;
         for (int pi = 0; pi < nplanes; ++pi) {
           if (!mbar_wait(&p_empty[s], ph ^ 1u, P.err, 21)) { ok = false; break; }
           if (leader) mbar_expect_tx(&p_full[s], (uint32_t)P.plane_tx * kCtas);
@@ -187,9 +193,9 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int w = work0; w < P.total_work && ok; w += wstride) {
         const HaloTile t = halo_decode(P, w, kPair, 0);
         const int n0 = t.n0 + rank * (t.width / kCtas);      // half-width items use the first rows of the (full-size) box
-        int kc = rot_kc0, td = rot_td0;
+        int kc = t.rot_kc0, td = t.rot_td0;
         for (int pi = 0; pi < nplanes && ok; ++pi) {
-          int tap = rot_t;                                   // (th, tw) index inside the plane, rotated start
+          int tap = t.rot_t;                                 // (th, tw) index inside the plane, rotated start
           for (int i = 0; i < taps_hw; ++i) {
             const long long tw0 = prof ? clock64() : 0;
             if (!((P.debug & 64) ? mbar_wait_poll(&b_empty[s], ph ^ 1u, P.err, 22) : mbar_wait(&b_empty[s], ph ^ 1u, P.err, 22))) { ok = false; break; }
@@ -217,7 +223,6 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const uint32_t row_u = 128u >> 4;                                        // one plane row, in 16-byte units
       const int kh = P.kh, kw = P.kw, NP = P.NP, NB = P.NB;
       const uint32_t line_step = (uint32_t)(P.Wb - (kw - 1)) * row_u;          // from the last tap of a line to the next line's first
-      const uint32_t rot_a_u = (uint32_t)(rot_th0 * P.Wb + rot_tw0) * row_u;
       int ps = 0, bs = 0;
       uint32_t pph = 0, bph = 0;
       bool ok = true, b_ready = false;
@@ -229,6 +234,8 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const HaloTile t = halo_decode(P, w, kPair, 0);
         const uint32_t roff_u = (uint32_t)t.roff * row_u;      // flat tiles start inside their first plane line
         const uint32_t idesc = t.width == P.n_tile ? idesc_full : idesc_half;
+        const uint32_t rot_a_u = (uint32_t)(t.rot_th0 * P.Wb + t.rot_tw0) * row_u;
+        const int rot_th0 = t.rot_th0, rot_tw0 = t.rot_tw0;
         const long long ta0 = prof ? clock64() : 0;
         if (!mbar_wait(&acc_empty[buf], aph ^ 1u, P.err, 24)) { ok = false; break; }
         if (prof) t_wacc += clock64() - ta0;
