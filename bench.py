@@ -503,10 +503,19 @@ def run_infer(args):
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if sampler else None
     err = I.tc_error()
-    check = None
-    if rank == 0 and world > 1:                                # the sharded result against this rank running every window
-        ref = sliding_window_inference(tm, dev_vol, patch, stride, stride, 0, 1, dtype=torch.bfloat16, windows_per_pass=1)
-        check = float((out["v"] - ref).abs().max())
+    check = batched = None
+    if world > 1:
+        # (1) the sharding logic: the reference's one-window-per-pass loop sharded over the ranks against this rank running
+        # every window -- same kernels on the same batches of 1, so only the order of the fp32 accumulation differs
+        sh1 = sliding_window_inference(tm, dev_vol, patch, stride, stride, rank, world, dtype=torch.bfloat16, windows_per_pass=1)
+        if rank == 0:
+            ref = sliding_window_inference(tm, dev_vol, patch, stride, stride, 0, 1, dtype=torch.bfloat16, windows_per_pass=1)
+            check = float((sh1 - ref).abs().max())
+            # (2) the timed run groups windows into batches: a sample's convolution results do not depend on its batch
+            # mates, but the fp32 partial sums of its InstanceNorm statistics are grouped by the persistent schedule, and
+            # this UNTRAINED N(0, 0.02) generator amplifies such last-bit differences
+            d = (out["v"] - ref).double()
+            batched = {"rel_l2": float(d.norm() / (ref.double() - 127.5).norm()), "max_abs": float(d.abs().max())}
     if world > 1:
         barrier()
         dist.destroy_process_group()
@@ -527,7 +536,7 @@ def run_infer(args):
         "e2e": {"value": nvox / (ms_e2e * 1e-3), "unit": "voxels/s", "h2d_bytes_per_step": nvox * 4,
                 "d2h_bytes_per_step": nvox * 4, "ms_per_step": ms_e2e},
         "gpu_launches": int(launches), "clocks": clocks, "tc_error_flag": err,
-        "sharded_vs_single_max_abs": check,
+        "sharded_vs_single_max_abs": check, "batched_vs_one_window_per_pass": batched,
     }
     print(json.dumps(line), flush=True)
     return 0
