@@ -531,12 +531,109 @@ inline int run_gather_tc(const GatherPlan& plan, const GatherRun& R, cudaStream_
   return 0;
 }
 
+// ------------------------------------------------------------------ split-K for launches that cannot fill the GPU
+// The deep layers of the 7-down UNet (512 -> 512 k4 s2 at 8^3 -> 4^3 ... 2^3 -> 1^3, and the dgrads of the matching
+// transposed convs) have a handful of output tiles but K = 64 taps x 8..16 channel chunks: two to eight CTAs each streamed
+// the whole 33 - 67 MB weight tensor through one TMA producer (0.157 ms per launch whatever the spatial size, 1 - 55
+// TFLOP/s).  Such a launch is split into 8 tap ranges that run as the 8 "phases" of the merged launch of gather_tc_kernel
+// -- (tile, range) work items, each range writing its fp32 partial sums to its own slice of a scratch tensor shaped
+// [N][8 * Do][Ho][Wo][Cn] (the output d offset of range s is s * Do) -- and ksplit_finish_kernel adds the 8 slices, the
+// bias and the activation and writes the bf16 result.  8x the CTAs stream the weights in parallel.
+constexpr int kSplitParts = 8;
+inline bool ksplit_eligible(const GatherPlan& plan) {
+  if (getenv("MRA_GATHER_NOKSPLIT") != nullptr || plan.launches.size() != 1) return false;
+  const GatherLaunch& L = plan.launches[0];
+  const int n_tile = pick_n_tile(plan.cn);
+  if (L.astep != 2 || L.ostep != 1 || n_tile == 0 || plan.ck % 64 != 0) return false;
+  const int taps = (int)L.taps.size();
+  if (taps < 2 * kSplitParts || taps > kMaxTaps || (long long)taps * (plan.ck / 64) < 64) return false;
+  if (L.o0[0] != 0 || L.o0[1] != 0 || L.o0[2] != 0 || (kSplitParts - 1) * plan.odims[0] > 127) return false;
+  long long tiles = (long long)plan.n * (plan.cn / n_tile);
+  for (int i = 0; i < 3; ++i) tiles *= (L.dims[i] + L.box[i] - 1) / L.box[i];
+  return tiles * 4 <= num_sms();                 // under a quarter of a wave
+}
+inline size_t ksplit_workspace_bytes(const mra_conv_desc& d, int which) {
+  if (d.dtype != MRA_BF16 || (d.flags & MRA_CONV_FORCE_NAIVE) || !gather_eligible(d, which)) return 0;
+  GatherPlan plan;
+  if (!build_gather_plan(d, which, plan) || !ksplit_eligible(plan)) return 0;
+  return (size_t)plan.n * kSplitParts * plan.odims[0] * plan.odims[1] * plan.odims[2] * plan.cn * sizeof(float);
+}
+// out[n][pos][c] = act(sum_s part[n][s][pos][c] + bias[c]);  4 channels per thread
+__global__ void __launch_bounds__(256) ksplit_finish_kernel(const float* __restrict__ part, bf16* __restrict__ out, int N,
+                                                             long long npos, int Cn, const float* __restrict__ bias, int act,
+                                                             float slope) {
+  const long long c4n = Cn / 4;
+  const long long total = (long long)N * npos * c4n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long c4 = i % c4n, r = i / c4n;
+    const long long n = r / npos, pos = r - n * npos;
+    const float4* p = reinterpret_cast<const float4*>(part + ((n * kSplitParts) * npos + pos) * Cn) + c4;
+    float4 a = __ldg(p);
+#pragma unroll
+    for (int s = 1; s < kSplitParts; ++s) {
+      const float4 b = __ldg(p + (long long)s * npos * c4n);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (bias) { const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + c4); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+    float v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (act == MRA_ACT_RELU) v[k] = fmaxf(v[k], 0.f);
+      else if (act == MRA_ACT_LRELU) v[k] = v[k] > 0.f ? v[k] : v[k] * slope;
+      else if (act == MRA_ACT_TANH) v[k] = tanhf(v[k]);
+      else if (act == MRA_ACT_SIGMOID) v[k] = 1.f / (1.f + expf(-v[k]));
+    }
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&lo); o.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(out + (r * Cn + c4 * 4)) = o;
+  }
+}
+inline int run_gather_ksplit(const GatherPlan& plan, const GatherRun& R, float* scratch, cudaStream_t st) {
+  const GatherLaunch& L0 = plan.launches[0];
+  GatherPlan sp = plan;
+  sp.launches.clear();
+  sp.odims[0] = plan.odims[0] * kSplitParts;
+  const int taps = (int)L0.taps.size();
+  for (int s = 0; s < kSplitParts; ++s) {
+    GatherLaunch L = L0;
+    L.taps.assign(L0.taps.begin() + (long long)taps * s / kSplitParts, L0.taps.begin() + (long long)taps * (s + 1) / kSplitParts);
+    L.o0[0] = s * plan.odims[0];
+    sp.launches.push_back(L);
+  }
+  const int n_tile = pick_n_tile(plan.cn);
+  CUtensorMap tmB;
+  if (int rc = make_weight_map(&tmB, R.b, (long long)R.slabs * plan.cn, plan.ck, n_tile)) return rc;
+  GatherRun P{R.a, R.b, R.slabs, nullptr, scratch, 0, MRA_ACT_NONE, 0.f, nullptr};
+  if (int rc = run_gather_v1_launch(sp, sp.launches.data(), kSplitParts, P, tmB, n_tile, st)) return rc;
+  const long long npos = (long long)plan.odims[0] * plan.odims[1] * plan.odims[2];
+  const long long total = (long long)plan.n * npos * (plan.cn / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+  ksplit_finish_kernel<<<(unsigned)blocks, 256, 0, st>>>(scratch, reinterpret_cast<bf16*>(R.out), plan.n, npos, plan.cn, R.bias, R.act,
+                                                         R.slope);
+  MRA_LAUNCH_CHECK();
+  return 0;
+}
+
+// `split_done` (optional) tells the caller that the split-K path ran: it does not produce InstanceNorm statistics.
 inline int run_gather_tc(const mra_conv_desc& d, int which, const void* a, const void* b, const float* bias, void* out,
-                         double* stats, cudaStream_t st, const void* aux = nullptr, float aux_nslope = 0.f) {
+                         double* stats, cudaStream_t st, const void* aux = nullptr, float aux_nslope = 0.f,
+                         void* workspace = nullptr, size_t workspace_bytes = 0, bool* split_done = nullptr) {
   GatherPlan plan;
   MRA_REQUIRE(build_gather_plan(d, which, plan), "unsupported conv geometry");
   GatherRun R{a, b, d.k * d.k * d.k, bias, out, 1, which == 0 ? d.act : MRA_ACT_NONE, d.slope, stats};
   R.aux = aux; R.aux_nslope = aux_nslope;
+  if (split_done) *split_done = false;
+  if (aux == nullptr && split_done != nullptr && workspace != nullptr && ksplit_eligible(plan)) {
+    const size_t need = (size_t)plan.n * kSplitParts * plan.odims[0] * plan.odims[1] * plan.odims[2] * plan.cn * sizeof(float);
+    bool slabs_ok = true;
+    for (const Tap& t : plan.launches[0].taps) if (t.widx >= R.slabs) slabs_ok = false;
+    if (slabs_ok && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0) {
+      *split_done = true;
+      return run_gather_ksplit(plan, R, reinterpret_cast<float*>(workspace), st);
+    }
+  }
   return run_gather_tc(plan, R, st);
 }
 

@@ -65,7 +65,11 @@ long long mra_debug_launch_count(void) { return g_launch_count.load(); }
 const char* mra_last_error(void) { return g_last_error.c_str(); }
 
 size_t mra_conv3d_workspace_size(const mra_conv_desc* d, int which) {
-  return d ? special::workspace_bytes(*d, which) : 0;
+  if (!d) return 0;
+  if (special::stem_eligible(*d) || special::head_eligible(*d) || special::im2col_eligible(*d) || special::convT1_eligible(*d))
+    return special::workspace_bytes(*d, which);
+  if (which == 0 || which == 1) return tc::ksplit_workspace_bytes(*d, which);     // fp32 partial sums of the split-K gather
+  return 0;
 }
 
 int mra_conv3d_lowering(const mra_conv_desc* d) {
@@ -95,7 +99,18 @@ int mra_conv3d_fprop(const mra_conv_desc* d, const void* x, const void* w, const
     return special::im2col_dgrad(special::convT1_mirror(*d), x, w, y, workspace, workspace_bytes, st, bias, d->act, d->slope);
   if (special::stem_eligible(*d)) return special::stem_fprop(*d, x, w, bias, y, stats, workspace, workspace_bytes, st);
   if (special::head_eligible(*d) && !stats) return special::head_fprop(*d, x, w, bias, y, workspace, workspace_bytes, st);
-  if (tc::gather_eligible(*d, 0)) return tc::run_gather_tc(*d, 0, x, w, bias, y, stats, st);
+  if (tc::gather_eligible(*d, 0)) {
+    bool split = false;
+    if (int rc = tc::run_gather_tc(*d, 0, x, w, bias, y, stats, st, nullptr, 0.f, workspace, workspace_bytes, &split)) return rc;
+    if (split && stats) {                          // the split-K path leaves the statistics to the exact pass over y
+      MRA_REQUIRE(d->act == MRA_ACT_NONE, "stats are defined on the pre-activation output only");
+      mra_norm_desc nd;
+      memset(&nd, 0, sizeof(nd));
+      nd.n = d->n; nd.c = d->cout; nd.d = d->dout; nd.h = d->hout; nd.w = d->wout; nd.res_pad = -1; nd.dtype = d->dtype;
+      return mra_inorm_stats(&nd, y, stats, stream);
+    }
+    return 0;
+  }
   NaiveGatherP P = naive_params(*d, 0, x, w, bias, y);
   DISPATCH_DTYPE(d->dtype, { if (int rc = launch_naive_gather<T>(P, st)) return rc; });
   if (stats) {
@@ -117,7 +132,10 @@ int mra_conv3d_dgrad(const mra_conv_desc* d, const void* dy, const void* wT, voi
     return special::im2col_fprop(special::convT1_mirror(*d), dy, wT, nullptr, dx, nullptr, workspace, workspace_bytes, st);
   if (special::stem_eligible(*d)) return special::stem_dgrad(*d, dy, wT, dx, workspace, workspace_bytes, st);
   if (special::head_eligible(*d)) return special::head_dgrad(*d, dy, wT, dx, workspace, workspace_bytes, st);
-  if (tc::gather_eligible(*d, 1)) return tc::run_gather_tc(*d, 1, dy, wT, nullptr, dx, nullptr, st);
+  if (tc::gather_eligible(*d, 1)) {
+    bool split = false;
+    return tc::run_gather_tc(*d, 1, dy, wT, nullptr, dx, nullptr, st, nullptr, 0.f, workspace, workspace_bytes, &split);
+  }
   NaiveGatherP P = naive_params(*d, 1, dy, wT, nullptr, dx);
   DISPATCH_DTYPE(d->dtype, { if (int rc = launch_naive_gather<T>(P, st)) return rc; });
   return 0;

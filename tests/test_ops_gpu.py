@@ -481,3 +481,49 @@ def test_sliding_window_helpers():
     ref.window_finalize(lab, wt)
     I.window_finalize(labd, wtd)
     assert torch.allclose(labd.cpu(), lab, atol=1e-4)
+
+
+KSPLIT = [
+    (ConvGeom(512, 512, 4, 2, 1), (8, 8, 8), 4),               # UNet-7 d5 at config 4's per-GPU batch
+    (ConvGeom(512, 512, 4, 2, 1), (2, 2, 2), 4),               # d7: 2^3 -> 1^3, four output positions
+    (ConvGeom(1024, 512, 4, 2, 1, True, 0), (2, 2, 2), 2),     # u6 (its dgrad is the direct stride-2 form)
+    (ConvGeom(256, 512, 4, 2, 1), (16, 16, 16), 2),            # d4
+    (ConvGeom(256, 128, 3, 2, 1), (8, 8, 8), 1),               # 27 taps: uneven tap ranges (3,3,4,3,3,4,3,4)
+]
+
+
+@pytest.mark.parametrize("case", KSPLIT, ids=gid)
+def test_split_k_gather_matches_unsplit_and_oracle(case, monkeypatch):
+    """Launches with a handful of output tiles and a long reduction run as 8 tap ranges with fp32 partial sums in the
+    caller's workspace (conv_tc_halo.cuh: run_gather_ksplit).  Against the unsplit kernel (MRA_GATHER_NOKSPLIT) and the fp64
+    oracle, for the op whose plan is the direct stride-2 form: fprop of a Conv3d, dgrad of a ConvTranspose3d."""
+    import ctypes as C
+    g, dims, n = case
+    I = ops.impl()
+    ref = R.RefImpl(torch.float64)
+    x, w, b, dy = _conv_case(g, dims, n, torch.bfloat16, seed=5)
+    xd, wd, bd, dyd = x.cuda(), w.cuda(), b.cuda(), dy.cuda()
+    which = 1 if g.transposed else 0
+    d = I._conv_desc(g, n, dims, g.out_dims(dims), ops.MRA_BF16)
+    assert int(I.L.mra_conv3d_workspace_size(C.byref(d), which)) > 0, "case is expected to take the split-K path"
+    if not g.transposed:
+        y, st = I.conv_fprop(xd, wd, bd, g, want_stats=True)
+        y3, _ = I.conv_fprop(xd, wd, None, g, act=ops.ACT_LRELU, slope=0.2)
+        monkeypatch.setenv("MRA_GATHER_NOKSPLIT", "1")
+        assert int(I.L.mra_conv3d_workspace_size(C.byref(d), which)) == 0
+        y2, st2 = I.conv_fprop(xd, wd, bd, g, want_stats=True)
+        y_ref, st_ref = ref.conv_fprop(x.double(), w.double(), b.double(), g, want_stats=True)
+        y3_ref, _ = ref.conv_fprop(x.double(), w.double(), None, g, act=R.ACT_LRELU, slope=0.2)
+        assert rel_l2(y.cpu(), y_ref) < 1e-2 and rel_l2(y2.cpu(), y_ref) < 1e-2
+        assert rel_l2(y.float().cpu(), y2.float().cpu()) < 4e-3          # two roundings of fp32 sums in another order
+        assert rel_l2(st.cpu(), st_ref) < 1e-1 and rel_l2(st.cpu(), st2.cpu()) < 2e-2
+        assert rel_l2(y3.cpu(), y3_ref) < 1e-2
+    else:
+        wT = I.pack_weight_t(wd, torch.bfloat16)
+        dx = I.conv_dgrad(dyd, wT, g, dims)
+        monkeypatch.setenv("MRA_GATHER_NOKSPLIT", "1")
+        dx2 = I.conv_dgrad(dyd, wT, g, dims)
+        dx_ref = ref.conv_dgrad(dy.double(), w.double().transpose(1, 2).contiguous(), g, dims)
+        assert rel_l2(dx.cpu(), dx_ref) < 1e-2 and rel_l2(dx2.cpu(), dx_ref) < 1e-2
+        assert rel_l2(dx.float().cpu(), dx2.float().cpu()) < 4e-3
+    assert I.tc_error() == 0
