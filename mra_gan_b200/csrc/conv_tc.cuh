@@ -840,6 +840,7 @@ struct WgradP {
 struct WMaps { CUtensorMap m[kMaxWGroups]; };
 
 constexpr uint32_t kChunkBytes = 64 * 128;       // 64 positions x 64 bf16
+constexpr size_t kWgradFlushBytes = 4 * 4096;    // transposing buffers of the 4 epilogue warps (see the flush)
 
 // One contiguous piece of a CTA's stream-K range that lies inside a single work item.
 struct WSeg { int item, mt, nt, g, tap0, ntap, kb0, kb1; };
@@ -919,6 +920,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
   uint64_t* acc_full = empty_bar + P.stages;
   uint64_t* acc_empty = acc_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+  uint8_t* flush_stage = smem + (size_t)P.stages * stage_bytes + 256;      // 4 epilogue warps x 4 KB (kWgradFlushBytes)
 
   const int boxes_per_sample = P.tilesW * P.tilesH * P.tilesD;
   const long long kblocks = (long long)boxes_per_sample * P.N;
@@ -1104,14 +1106,34 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
           uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * ncols + c0), r);
           tmem_wait_ld();
-          if (!valid) continue;
           if (P.n_stride == 1) {
-            float* o = obase + n0 + c0;
+            // A thread owns accumulator ROW ml and 32 consecutive columns = 128 B of one dw row; its neighbours' rows are
+            // m_stride floats away, so a red.v4 straight from the registers touched 32 half-used sectors per warp
+            // instruction (tools/red_probe.cu: 2.1 TB/s device-wide against 3.9 TB/s for contiguous lanes, and the flush
+            // is the tail of every wgrad launch: nothing overlaps it).  The 32 x 32 block is therefore transposed
+            // through 4 KB of shared memory per warp (16-byte pieces, XOR-swizzled by the row: conflict-free both ways)
+            // and leaves as 8 instructions that each cover four whole 128-byte lines.
+            float4* stg = reinterpret_cast<float4*>(flush_stage) + q * 256;
+            __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(__uint_as_float(r[j])),
-                           "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
-                           : "memory");
+            for (int j = 0; j < 8; ++j)
+              stg[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                             __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            __syncwarp();
+            const int ch = lane & 7;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row = i * 4 + (lane >> 3);                     // row of this warp's 32-row quadrant
+              const int mr = q * 32 + row;
+              const float4 v = stg[row * 8 + (ch ^ (row & 7))];
+              if (mr < 64 * P.m_chunks && m - ml + mr < P.Km && !(P.debug & 1)) {
+                float* o = obase + (long long)(mr - ml) * P.m_stride + n0 + c0 + ch * 4;
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                             : "memory");
+              }
+            }
+          } else if (!valid) {
+            continue;
           } else {
 #pragma unroll 8
             for (int j = 0; j < 32; ++j)
@@ -1481,12 +1503,12 @@ inline int run_wgrad_tc(const WgradPlan& plan, const void* x, const void* dy, fl
   MRA_REQUIRE(tapc <= kMaxTaps, "wgrad plan: too many taps");
   P.n_items = itemc;
   const size_t stage_bytes = 2 * kChunkBytes + (size_t)P.sets_max * (P.ncc / (pair ? 2 : 1)) * P.box_bytes;
-  int stages = (int)((kSmemLimit - 2048) / stage_bytes);
+  int stages = (int)((kSmemLimit - 2048 - kWgradFlushBytes) / stage_bytes);
   MRA_REQUIRE(stages >= 2, "wgrad plan: stage does not fit shared memory");
   if (stages > 6) stages = 6;
   P.stages = stages;
   P.tmem_cols = pow2_cols(max_cols);
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + kWgradFlushBytes;
   if (pair) {
     MRA_CHECK_CUDA(launch_pdl(wgrad_tc_kernel<true>, dim3((unsigned)(num_sms() & ~1)), dim3(kThreads), smem, st, 2, tmM, maps, P));
     MRA_LAUNCH_CHECK();

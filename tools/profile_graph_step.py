@@ -1,7 +1,7 @@
 """GPU: where does a GRAPH-REPLAYED step spend its time?  CUPTI kernel/memset records of one replayed
 optimize_parameters() (two CUDA graphs): sum of device durations, number of nodes by kind, and the idle time
 between consecutive records on the stream (the launch / dependency gaps the kernels cannot see).
-Usage: python tools/profile_graph_step.py [batch]   ->  gpurun_out/graph_step_profile.txt"""
+Usage: python tools/profile_graph_step.py [batch] [netG]   ->  gpurun_out/graph_step_profile_*.txt"""
 import contextlib
 import io
 import os
@@ -15,10 +15,11 @@ from mra_gan_b200 import networks3D as N3  # noqa: E402
 from mra_gan_b200.models import create_model  # noqa: E402
 
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+netG = sys.argv[2] if len(sys.argv) > 2 else "resnet_9blocks"
 N3.set_default_compute_dtype(torch.bfloat16)
 with contextlib.redirect_stdout(io.StringIO()):
-    m = create_model(bench.make_opt())
-    m.setup(bench.make_opt())
+    m = create_model(bench.make_opt(netG=netG))
+    m.setup(bench.make_opt(netG=netG))
 m.enable_cuda_graphs(warmup_steps=2)
 A = torch.rand(batch, 1, 128, 128, 128, device="cuda") * 2 - 1
 B = torch.rand(batch, 1, 128, 128, 128, device="cuda") * 2 - 1
@@ -66,5 +67,5 @@ for k, (n, d) in sorted(by.items(), key=lambda kv: -kv[1][1]):
     out.append("%-62s %6d %10.3f %10.3f" % (k, n, d / 1e3, gby.get(k, [0, 0.0])[1] / 1e3))
 txt = "\n".join(out)
 os.makedirs("gpurun_out", exist_ok=True)
-open("gpurun_out/graph_step_profile_b%d.txt" % batch, "w").write(txt + "\n")
+open("gpurun_out/graph_step_profile_%sb%d.txt" % ("" if netG == "resnet_9blocks" else netG + "_", batch), "w").write(txt + "\n")
 print(txt)
