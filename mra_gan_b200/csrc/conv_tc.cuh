@@ -812,6 +812,7 @@ struct WGroup {
   int gpi, share;                   // taps per item, taps per box set
   int pitch_w, pitch_h;             // rows per h line / per d plane of a shifted-operand box
   int box_tx;                       // bytes one 64-channel box delivers
+  long long cost0;                  // stream-K cost of all work items of the groups before this one
 };
 struct WgradP {
   int tilesW, tilesH, tilesD;       // K-block boxes per dim of the dense position space
@@ -861,15 +862,31 @@ __device__ __forceinline__ void wseg_begin(const WgradP& P, long long kblocks, W
   const long long share = (P.total_cost + nunits - 1) / nunits;
   it.pos = (long long)unit * share;
   it.end = min(it.pos + share, P.total_cost);
-  it.work = 0; it.woff = 0;
   const int per_item = P.m_tiles * P.n_tiles;
   const int n_work = P.n_items * per_item;
-  while (it.work < n_work) {                       // skip the work items that end before this CTA's range
-    const int item = it.work / per_item;
-    const long long span = (long long)wg_item_ntap(P, wg_item_group(P, item), item) * kblocks;
-    if (it.woff + span > it.pos) break;
-    it.woff += span; ++it.work;
+  // First work item that ends after it.pos, in O(groups): inside a group every item carries gpi taps except possibly the
+  // last one, so the cumulative cost is piecewise linear.  (A linear walk over the work items cost the last CTAs of the
+  // deep UNet layers -- 512 to 2048 items of 4 K-blocks -- ~100 us of single-thread integer code before their first load:
+  // those launches took 0.11 - 0.26 ms whatever their size.)
+  int g = 0;
+  while (g + 1 < P.n_groups && P.grp[g + 1].cost0 <= it.pos) ++g;
+  const WGroup& G = P.grp[g];
+  const long long span_full = (long long)G.gpi * kblocks;
+  const int items_full = G.ntaps / G.gpi;                          // items with gpi taps
+  const long long works_full = (long long)items_full * per_item;
+  const long long off = it.pos - G.cost0;
+  long long wl;                                                    // work index inside the group
+  if (off < works_full * span_full) {
+    wl = off / span_full;
+    it.woff = G.cost0 + wl * span_full;
+  } else {
+    const long long span_part = (long long)(G.ntaps - items_full * G.gpi) * kblocks;
+    const long long rem = off - works_full * span_full;
+    wl = works_full + (span_part > 0 ? rem / span_part : 0);
+    it.woff = G.cost0 + works_full * span_full + (wl - works_full) * span_part;
   }
+  it.work = G.item0 * per_item + (int)wl;
+  if (it.work > n_work) it.work = n_work;
 }
 __device__ __forceinline__ bool wseg_next(const WgradP& P, long long kblocks, WSegIter& it, WSeg& sg) {
   const int per_item = P.m_tiles * P.n_tiles;
@@ -1493,6 +1510,7 @@ inline int run_wgrad_tc(const WgradPlan& plan, const void* x, const void* dy, fl
       P.rshift[tapc + i] = (int16_t)r;
       P.twi[tapc + i] = (int16_t)t.widx;
     }
+    G.cost0 = P.total_cost;
     for (int it = 0; it < G.n_items; ++it) {
       const int nt = G.ntaps - it * G.gpi < G.gpi ? G.ntaps - it * G.gpi : G.gpi;
       P.total_cost += (long long)nt * kblocks * P.m_tiles * P.n_tiles;
