@@ -340,7 +340,8 @@ def run_gpu(args):
             model.optimize_parameters()
             model.get_current_losses()                  # device -> host read of the 8 losses (one transfer)
 
-        for _ in range(max(warmup, 3)):                 # >= 3: two eager steps + the capture step of the graph replay
+        for _ in range(max(warmup, int(os.environ.get("MRA_BENCH_MIN_WARMUP", "3")))):   # >= 3: two eager steps + the capture step of
+                                                        # the graph replay (the env hook shortens ncu launch-list runs only)
             step_resident()
         launches0 = I.launch_count()
         ms_step = timed(step_resident, steps)
