@@ -104,6 +104,15 @@ struct AdamBatch {
 };
 #define MRA_ADAM_ELEMS_PER_BLOCK 4096
 
+// one element of torch.optim.Adam: exp_avg.lerp_(grad, 1-b1) with ATen's two-branch lerp; exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
+__device__ __forceinline__ void adam_elem(float gi, float& mi, float& vi, float& pi, float b1, float b2, float eps, float step_size,
+                                          float bc2_sqrt) {
+  const float wl = 1.f - b1, diff = gi - mi;
+  mi = (wl < 0.5f) ? mi + wl * diff : gi - diff * (1.f - wl);
+  vi = b2 * vi + (1.f - b2) * gi * gi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  pi = pi - step_size * (mi / denom);
+}
 __global__ void __launch_bounds__(256) adam_kernel(const AdamBatch B) {
   // locate this block's tensor (count <= 48: linear scan)
   int ti = 0;
@@ -117,17 +126,46 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamBatch B) {
   const long long n = B.numel[ti];
   float b1 = B.b1, b2 = B.b2, eps = B.eps, step_size = B.step_size, bc2_sqrt = B.bc2_sqrt;
   if (B.hyper) { b1 = B.hyper[1]; b2 = B.hyper[2]; eps = B.hyper[3]; step_size = B.hyper[4]; bc2_sqrt = B.hyper[5]; }
+  // 16-byte accesses (4 elements per thread and iteration) when all arrays of the tensor are 16-byte aligned -- they are
+  // for the packed parameters, their Adam moments and the gradient-bucket views (256-byte slots); the 4-byte path measured
+  // 4.0 TB/s on the UNet's 334 M parameters (28 + 2 bytes each)
+  const bool vec = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0 && (sh == nullptr || ((uintptr_t)sh & 7) == 0);
+  if (vec) {
+#pragma unroll
+    for (int k = 0; k < MRA_ADAM_ELEMS_PER_BLOCK / 1024; ++k) {
+      const long long i = base + ((long long)k * 256 + threadIdx.x) * 4;
+      if (i + 3 < n) {
+        const float4 g4 = *reinterpret_cast<const float4*>(g + i);
+        float4 m4 = *reinterpret_cast<const float4*>(m + i), v4 = *reinterpret_cast<const float4*>(v + i),
+               p4 = *reinterpret_cast<const float4*>(p + i);
+        adam_elem(g4.x, m4.x, v4.x, p4.x, b1, b2, eps, step_size, bc2_sqrt);
+        adam_elem(g4.y, m4.y, v4.y, p4.y, b1, b2, eps, step_size, bc2_sqrt);
+        adam_elem(g4.z, m4.z, v4.z, p4.z, b1, b2, eps, step_size, bc2_sqrt);
+        adam_elem(g4.w, m4.w, v4.w, p4.w, b1, b2, eps, step_size, bc2_sqrt);
+        *reinterpret_cast<float4*>(m + i) = m4; *reinterpret_cast<float4*>(v + i) = v4; *reinterpret_cast<float4*>(p + i) = p4;
+        if (sh) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(p4.x, p4.y), hi = __floats2bfloat162_rn(p4.z, p4.w);
+          uint2 o;
+          o.x = *reinterpret_cast<uint32_t*>(&lo); o.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(sh + i) = o;
+        }
+      } else {
+        for (long long j = i; j < n && j < i + 4; ++j) {
+          float mi = m[j], vi = v[j], pi = p[j];
+          adam_elem(g[j], mi, vi, pi, b1, b2, eps, step_size, bc2_sqrt);
+          m[j] = mi; v[j] = vi; p[j] = pi;
+          if (sh) sh[j] = __float2bfloat16_rn(pi);
+        }
+      }
+    }
+    return;
+  }
 #pragma unroll 4
   for (int k = 0; k < MRA_ADAM_ELEMS_PER_BLOCK / 256; ++k) {
     const long long i = base + k * 256 + threadIdx.x;
     if (i >= n) break;
-    const float gi = g[i];
-    // exp_avg.lerp_(grad, 1-b1) with ATen's two-branch lerp; exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
-    const float wl = 1.f - b1, diff = gi - m[i];
-    const float mi = (wl < 0.5f) ? m[i] + wl * diff : gi - diff * (1.f - wl);
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    const float pi = p[i] - step_size * (mi / denom);
+    float mi = m[i], vi = v[i], pi = p[i];
+    adam_elem(g[i], mi, vi, pi, b1, b2, eps, step_size, bc2_sqrt);
     m[i] = mi; v[i] = vi; p[i] = pi;
     if (sh) sh[i] = __float2bfloat16_rn(pi);
   }
