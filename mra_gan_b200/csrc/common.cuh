@@ -9,6 +9,8 @@
 #include <string.h>
 #include <atomic>
 #include <string>
+#include <map>
+#include <mutex>
 #include <utility>
 
 #include "../../include/mra_gan_b200.h"

@@ -94,29 +94,37 @@ __global__ void __launch_bounds__(256) expand_hw_kernel(const bf16* __restrict__
 
 // out[n,d,ho,wo] = act(bias + sum_{kh,kw<k} Z[n,d,ho+sgn*kh+off,wo+sgn*kw+off,kh*8+kw])
 // One block = a band of output lines of one (n, d) plane.  Every Z line of the band is read from global memory ONCE
-// (coalesced 16-byte loads) into a padded shared-memory line (position pitch 33 words: conflict-free column reads);
+// (coalesced cp.async) into a padded shared-memory line (position pitch 33 words: conflict-free column reads);
 // thread wo then adds the line's k*k contributions to the <= 8 output lines that are still open, which it keeps in
 // registers (a statically rotated window of 8 partial sums).
-template <typename TZ, typename TO>
-__global__ void __launch_bounds__(256) shift_sum_kernel(const TZ* __restrict__ Z, TO* __restrict__ out, long long rows, int Hz,
-                                                         int Wz, int Ho, int Wo, int k, int sgn, int off,
-                                                         const float* __restrict__ bias, int act, float slope, int band) {
-  extern __shared__ uint32_t s_z[];                  // [Wz][33] words: 64 bf16 of one position + 1 pad word
+// SGN and K are COMPILE-TIME parameters: the window slot of an output line is ((u - SGN*kh) mod 8) with u, kh unrolled,
+// i.e. a constant only when the sign is one -- the first version took sgn and k as kernel arguments, which made acc[] a
+// run-time indexed array in LOCAL memory (146 LDL/STL in its SASS, 80 registers, ~800 predicate instructions) and the
+// kernel ran at 2.1 TB/s.  CHECKW = false when the host has shown that every wo + SGN*kw + off lies inside the Z line.
+template <typename TO, int SGN, int K, bool CHECKW>
+__global__ void __launch_bounds__(256) shift_sum_kernel(const bf16* __restrict__ Z, TO* __restrict__ out, long long rows, int Hz,
+                                                         int Wz, int Ho, int Wo, int off, const float* __restrict__ bias, int act,
+                                                         float slope, int band) {
+  static_assert(K >= 1 && K <= 8 && (SGN == 1 || SGN == -1), "shift_sum: window of 8 lines");
+  extern __shared__ uint32_t s_z[];                  // 2 x [Wz][33] words: 64 bf16 of one position + 1 pad word
   const float b = bias ? bias[0] : 0.f;
   const int nbands = (Ho + band - 1) / band;
   const long long nwork = rows * nbands;
+  const int wo = threadIdx.x;                        // Wo <= blockDim.x (host)
+  const int buf_words = Wz * 33;
   for (long long wk = blockIdx.x; wk < nwork; wk += gridDim.x) {
     const int bi = (int)(wk % nbands);
     const long long r = wk / nbands;
     const int ho0 = bi * band, ho1 = min(Ho, ho0 + band);
-    // Z lines that feed output lines [ho0, ho1): hz = ho + sgn*kh + off, kh in [0, k)
-    const int hz_lo = sgn > 0 ? ho0 + off : ho0 - (k - 1) + off;
-    const int hz_hi = sgn > 0 ? ho1 - 1 + (k - 1) + off : ho1 - 1 + off;       // inclusive
+    // Z lines that feed output lines [ho0, ho1): hz = ho + SGN*kh + off, kh in [0, K)
+    const int hz_lo = SGN > 0 ? ho0 + off : ho0 - (K - 1) + off;
+    const int hz_hi = SGN > 0 ? ho1 - 1 + (K - 1) + off : ho1 - 1 + off;       // inclusive
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
     // Z lines are double-buffered: while line hz is being added up, line hz + 1 streams into the other buffer with
-    // cp.async (4-byte pieces: the 33-word pitch that makes the column reads conflict-free is not 16-byte aligned)
+    // cp.async (4-byte pieces: the 33-word pitch that makes the column reads conflict-free is not 16-byte aligned; a
+    // warp moves the 128 contiguous bytes of one position per instruction)
     auto stage = [&](int hz, uint32_t* dst) {
       if (hz >= 0 && hz < Hz && hz <= hz_hi) {
         const uint32_t* gl = reinterpret_cast<const uint32_t*>(Z + ((r * Hz + hz) * (long long)Wz) * 64);
@@ -127,11 +135,10 @@ __global__ void __launch_bounds__(256) shift_sum_kernel(const TZ* __restrict__ Z
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    const int buf_words = Wz * 33;
     __syncthreads();                                 // the previous band is done with both buffers
     stage(hz_lo, s_z);
     int cur = 0;
-    // process the lines in groups of 8 so that the rotating window index is static
+    // the lines are processed in groups of 8 so that the rotating window index is static
     for (int hz0 = hz_lo; hz0 <= hz_hi; hz0 += 8) {
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
@@ -141,36 +148,31 @@ __global__ void __launch_bounds__(256) shift_sum_kernel(const TZ* __restrict__ Z
         stage(hz + 1, s_z + (cur ^ 1) * buf_words);   // that buffer was last read before the barrier closing line hz - 1
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncthreads();
-        const bool in_range = hz >= 0 && hz < Hz;
-        // contributions of line hz: to output line ho = hz - off - sgn*kh  for kh in [0, k)
-        const int wo = threadIdx.x;                                        // Wo <= blockDim.x (checked on host)
         if (wo < Wo) {
+          if (hz >= 0 && hz < Hz) {                  // (block-uniform) a line outside Z contributes zeros
+            // contributions of line hz: to output line ho = hz - off - SGN*kh, kept in slot (u - SGN*kh) mod 8
 #pragma unroll
-          for (int kh = 0; kh < 8; ++kh) {
-            if (kh >= k) break;
-            // window slot of output line ho: lines are visited in increasing hz; slot = (u - sgn*kh) mod 8 is static
-            const int slot = ((u - sgn * kh) % 8 + 8) % 8;
-            float s = 0.f;
-            if (in_range) {
+            for (int kh = 0; kh < K; ++kh) {
+              float s = 0.f;
 #pragma unroll
-              for (int kw = 0; kw < 8; ++kw) {
-                if (kw >= k) break;
-                const int wz = wo + sgn * kw + off;
-                if (wz >= 0 && wz < Wz) {
+              for (int kw = 0; kw < K; ++kw) {
+                const int wz = wo + SGN * kw + off;
+                if (!CHECKW || (unsigned)wz < (unsigned)Wz) {
                   const uint32_t wrd = s_cur[wz * 33 + ((kh * 8 + kw) >> 1)];
                   s += __uint_as_float((kw & 1) ? (wrd & 0xffff0000u) : (wrd << 16));
                 }
               }
+              acc[((u - SGN * kh) % 8 + 8) % 8] += s;
             }
-            acc[slot] += s;
           }
-          // the output line completed by this Z line: for sgn > 0 it is ho = hz - off - (k-1) (its last contributor is
-          // kh = k-1); for sgn < 0 it is ho = hz - off (last contributor kh = 0)
-          const int ho_done = sgn > 0 ? hz - off - (k - 1) : hz - off;
-          const int slot_done = sgn > 0 ? ((u - (k - 1)) % 8 + 8) % 8 : u;
+          // the output line completed by this Z line: for SGN > 0 it is ho = hz - off - (K-1) (its last contributor is
+          // kh = K-1); for SGN < 0 it is ho = hz - off (last contributor kh = 0)
+          const int ho_done = SGN > 0 ? hz - off - (K - 1) : hz - off;
+          constexpr int kDoneShift = SGN > 0 ? K - 1 : 0;
+          float& a_done = acc[((u - kDoneShift) % 8 + 8) % 8];
           if (ho_done >= ho0 && ho_done < ho1)
-            out[(r * Ho + ho_done) * (long long)Wo + wo] = from_f<TO>(apply_act(acc[slot_done] + b, act, slope));
-          acc[slot_done] = 0.f;
+            out[(r * Ho + ho_done) * (long long)Wo + wo] = from_f<TO>(apply_act(a_done + b, act, slope));
+          a_done = 0.f;
         }
         __syncthreads();                             // line hz fully consumed: its buffer may be refilled
         cur ^= 1;
@@ -305,18 +307,72 @@ inline int launch_expand_hw(const bf16* src, bf16* out, long long rows, int Hs, 
   MRA_LAUNCH_CHECK();
   return 0;
 }
-inline int launch_shift_sum(const bf16* Z, bf16* out, long long rows, int Hz, int Wz, int Ho, int Wo, int k, int sgn, int off,
-                            const float* bias, int act, float slope, cudaStream_t st) {
-  MRA_REQUIRE(Wo <= 256 && k <= 8, "shift_sum: line longer than a block (Wo = %d)", Wo);
-  const int band = 32;
-  const long long nwork = rows * ((Ho + band - 1) / band);
-  long long grid = nwork < (long long)num_sms() * 8 ? nwork : (long long)num_sms() * 8;
-  if (grid < 1) grid = 1;
+// Launch geometry of shift_sum: blocks of round_up(Wo, 32) threads (one thread per output column -- the first version
+// always ran 256, half of them idle for a 128-wide line, and its 80 registers x 256 threads allowed 3 blocks per SM);
+// bands sized to the resident block count: rows = 256 planes (batch 2 x 128) on 148 x 6 slots -> 3 bands of 43 lines =
+// 768 items in one wave, instead of 1024 items of 32 lines in 2.3 waves.  A band re-reads the K - 1 Z lines it shares
+// with its neighbour (L2 hits).
+template <typename TO, int SGN, int K, bool CHECKW>
+inline int launch_shift_sum_t(const bf16* Z, TO* out, long long rows, int Hz, int Wz, int Ho, int Wo, int off, const float* bias,
+                              int act, float slope, cudaStream_t st) {
+  auto kern = shift_sum_kernel<TO, SGN, K, CHECKW>;
+  int threads = ((Wo + 31) / 32) * 32;
+  if (threads < 64) threads = 64;
   const size_t smem = (size_t)2 * Wz * 33 * sizeof(uint32_t);          // two line buffers
   MRA_REQUIRE(smem <= 48 * 1024, "shift_sum: Z line does not fit shared memory (Wz = %d)", Wz);
-  shift_sum_kernel<bf16, bf16><<<(unsigned)grid, 256, smem, st>>>(Z, out, rows, Hz, Wz, Ho, Wo, k, sgn, off, bias, act, slope, band);
+  // resident blocks per SM for this (kernel, block size, shared memory): asked once per configuration (host-side query,
+  // no stream work; the first call of a configuration happens in the eager warm-up steps, before any graph capture)
+  static std::mutex mu;
+  static std::map<std::pair<int, size_t>, int> occ_cache;
+  int occ = 0;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_pair(threads, smem);
+    auto it = occ_cache.find(key);
+    if (it == occ_cache.end()) {
+      MRA_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+      if (occ < 1) occ = 1;
+      occ_cache[key] = occ;
+    } else {
+      occ = it->second;
+    }
+  }
+  const long long slots = (long long)num_sms() * occ;
+  // bands per plane: minimise (rounds of the block-cyclic schedule) x (Z lines per band, K - 1 of them re-read)
+  int band = Ho;
+  long long best = -1;
+  for (int nb = 1; nb <= (Ho + 7) / 8; ++nb) {
+    const int bd = (Ho + nb - 1) / nb;
+    const long long items = rows * ((Ho + bd - 1) / bd);
+    const long long cost = ((items + slots - 1) / slots) * (bd + K - 1);
+    if (best < 0 || cost < best) { best = cost; band = bd; }
+  }
+  const long long nwork = rows * ((Ho + band - 1) / band);
+  long long grid = nwork < slots ? nwork : slots;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, threads, smem, st>>>(Z, out, rows, Hz, Wz, Ho, Wo, off, bias, act, slope, band);
   MRA_LAUNCH_CHECK();
   return 0;
+}
+inline int launch_shift_sum(const bf16* Z, bf16* out, long long rows, int Hz, int Wz, int Ho, int Wo, int k, int sgn, int off,
+                            const float* bias, int act, float slope, cudaStream_t st) {
+  MRA_REQUIRE(Wo <= 256 && k >= 1 && k <= 8 && (sgn == 1 || sgn == -1), "shift_sum: line longer than a block (Wo = %d) or k = %d", Wo, k);
+  // does any (wo, kw) fall outside the Z line?
+  const int wlo = sgn > 0 ? off : off - (k - 1), whi = sgn > 0 ? Wo - 1 + (k - 1) + off : Wo - 1 + off;
+  const bool check_w = wlo < 0 || whi >= Wz;
+#define MRA_SS_CASE(KK)                                                                                                          \
+  case KK:                                                                                                                       \
+    if (sgn > 0) {                                                                                                               \
+      if (check_w) return launch_shift_sum_t<bf16, 1, KK, true>(Z, out, rows, Hz, Wz, Ho, Wo, off, bias, act, slope, st);        \
+      return launch_shift_sum_t<bf16, 1, KK, false>(Z, out, rows, Hz, Wz, Ho, Wo, off, bias, act, slope, st);                    \
+    }                                                                                                                            \
+    if (check_w) return launch_shift_sum_t<bf16, -1, KK, true>(Z, out, rows, Hz, Wz, Ho, Wo, off, bias, act, slope, st);         \
+    return launch_shift_sum_t<bf16, -1, KK, false>(Z, out, rows, Hz, Wz, Ho, Wo, off, bias, act, slope, st);
+  switch (k) {
+    MRA_SS_CASE(1) MRA_SS_CASE(2) MRA_SS_CASE(3) MRA_SS_CASE(4) MRA_SS_CASE(5) MRA_SS_CASE(6) MRA_SS_CASE(7) MRA_SS_CASE(8)
+  }
+#undef MRA_SS_CASE
+  return ::mra::fail(-1, "shift_sum: unsupported k = %d", k);
 }
 
 struct Workspace {

@@ -1152,7 +1152,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
           } else if (!valid) {
             continue;
           } else {
-#pragma unroll 8
+            // fully unrolled: with a partial unroll r[] is indexed at run time, which puts the whole chunk into LOCAL memory --
+            // eight STL.128 per chunk and thread ahead of the branch, i.e. also on the n_stride == 1 path above
+#pragma unroll
             for (int j = 0; j < 32; ++j)
               asm volatile("red.global.add.f32 [%0], %1;" ::"l"(obase + (long long)(n0 + c0 + j) * P.n_stride),
                            "f"(__uint_as_float(r[j]))

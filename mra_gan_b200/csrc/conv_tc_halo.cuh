@@ -59,6 +59,9 @@ struct HaloP {
   int debug;
   unsigned long long* dbg;
   int pair;                         // 1: cta_group::2 pairs (host-side choice of the kernel instantiation)
+  int Da;                           // d extent of the A tensor
+  int skip;                         // 1: input planes that lie outside A for every tile of a work item are not loaded and
+                                    // their MMAs not issued (halo_plane_live); host-checked: every item keeps >= 1 plane
   int b_tx_dbg;                     // timing experiments: bytes per weight box when the box was shrunk (debug bit 5)
 };
 
@@ -67,7 +70,7 @@ __device__ __forceinline__ uint64_t desc_kmajor_sw128_sbo(uint32_t saddr, uint32
          (2ull << 61);
 }
 
-struct HaloTile { int n, d, n0, h0, w0, f0, hs, roff, width; int rot_kc0, rot_td0, rot_th0, rot_tw0, rot_t; };
+struct HaloTile { int n, d, d0, n0, h0, w0, f0, hs, roff, width; int rot_kc0, rot_td0, rot_th0, rot_tw0, rot_t; };
 // work index -> coordinates.  Order: n_tile fastest, then the tiles of a plane, then d (pair mode: pairs of
 // planes, CTA rank r takes d = 2 * dp + r so both tiles share the weight slab and the in-plane geometry), then n.
 __device__ __forceinline__ HaloTile halo_decode(const HaloP& P, int work, int pair, int rank) {
@@ -83,6 +86,7 @@ __device__ __forceinline__ HaloTile halo_decode(const HaloP& P, int work, int pa
   const int dsteps = pair ? (P.Dl + 1) / 2 : P.Dl;
   const int dq = tile % dsteps;
   t.d = pair ? 2 * dq + rank : dq;            // may be == Dl for the odd plane's partner: loads hit zero fill, nothing is stored
+  t.d0 = pair ? 2 * dq : dq;                  // the work item's first plane (the same for both CTAs of a pair)
   t.n = tile / dsteps;
   // The (channel chunk, td) planes and the (th, tw) taps of a plane are walked in a ROTATED order (the sum over taps is
   // order-free): CTAs that run side by side work on consecutive tiles, so at any moment the SMs stream different weight
@@ -106,6 +110,17 @@ __device__ __forceinline__ HaloTile halo_decode(const HaloP& P, int work, int pa
     t.h0 = 0; t.w0 = 0;
   }
   return t;
+}
+
+// Does input plane td of the work item whose first output plane is d0 touch the A tensor at all?  A dgrad computes the
+// gradient of the PADDED input (34^3 outputs from a 32^3 gradient for the residual blocks): the outermost output planes
+// see kd - 1 (or, for the second and second-to-last, kd - 2) input planes that are pure zero fill.  Such a plane is
+// skipped by all three roles -- no plane load, no weight slabs, no MMAs -- when it is dead for EVERY tile of the item
+// (both planes of a CTA pair): 2 of the 51 (pair, td) steps of the G.rb dgrad, 6 of 102 without pairs.
+__device__ __forceinline__ bool halo_plane_live(const HaloP& P, int d0, int td, int pair) {
+  if (!P.skip) return true;
+  const int a0 = d0 + P.dmin + td;
+  return pair ? (a0 + 1 >= 0 && a0 < P.Da) : (a0 >= 0 && a0 < P.Da);
 }
 
 template <bool kPair, int kMode>
@@ -174,11 +189,13 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const HaloTile t = halo_decode(P, w, kPair, rank);
         int kc = t.rot_kc0, td = t.rot_td0;
         for (int pi = 0; pi < nplanes; ++pi) {
-          if (!mbar_wait(&p_empty[s], ph ^ 1u, P.err, 21)) { ok = false; break; }
-          if (leader) mbar_expect_tx(&p_full[s], (uint32_t)P.plane_tx * kCtas);
-          tma_load_5d_g<kPair>(planes + (size_t)s * P.slot_bytes, &tmA, &p_full[s], kc * 64, t.w0 + P.wmin, t.hs + P.hmin,
-                               t.d + P.dmin + td, t.n);
-          if (++s == P.NP) { s = 0; ph ^= 1u; }
+          if (halo_plane_live(P, t.d0, td, kPair)) {
+            if (!mbar_wait(&p_empty[s], ph ^ 1u, P.err, 21)) { ok = false; break; }
+            if (leader) mbar_expect_tx(&p_full[s], (uint32_t)P.plane_tx * kCtas);
+            tma_load_5d_g<kPair>(planes + (size_t)s * P.slot_bytes, &tmA, &p_full[s], kc * 64, t.w0 + P.wmin, t.hs + P.hmin,
+                                 t.d + P.dmin + td, t.n);
+            if (++s == P.NP) { s = 0; ph ^= 1u; }
+          }
           if (++td == P.kd) { td = 0; if (++kc == P.kchunks) kc = 0; }
         }
       }
@@ -196,7 +213,8 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         int kc = t.rot_kc0, td = t.rot_td0;
         for (int pi = 0; pi < nplanes && ok; ++pi) {
           int tap = t.rot_t;                                 // (th, tw) index inside the plane, rotated start
-          for (int i = 0; i < taps_hw; ++i) {
+          const int ntap_p = halo_plane_live(P, t.d0, td, kPair) ? taps_hw : 0;
+          for (int i = 0; i < ntap_p; ++i) {
             const long long tw0 = prof ? clock64() : 0;
             if (!((P.debug & 64) ? mbar_wait_poll(&b_empty[s], ph ^ 1u, P.err, 22) : mbar_wait(&b_empty[s], ph ^ 1u, P.err, 22))) { ok = false; break; }
             if (prof) t_wait += clock64() - tw0;
@@ -242,7 +260,11 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * P.n_tile);
         uint32_t acc = 0;
+        int td_p = t.rot_td0;                                  // td of plane pi (the producers' walk)
         for (int pi = 0; pi < nplanes && ok; ++pi) {
+          const bool live = halo_plane_live(P, t.d0, td_p, kPair);
+          if (++td_p == P.kd) td_p = 0;
+          if (!live) continue;
           const long long tp0 = prof ? clock64() : 0;
           if (!dbg_nop && !mbar_wait(&p_full[ps], pph, P.err, 25)) { ok = false; break; }
           if (prof) t_waitp += clock64() - tp0;
@@ -461,6 +483,23 @@ inline int run_gather_halo(const GatherPlan& plan, const GatherLaunch& L, HaloP&
   { const char* e = getenv("MRA_GATHER_DEBUG"); P.debug = e ? atoi(e) : 0; }
   P.dbg = tc_dbg_counters();
   P.tmem_cols = pow2_cols(2 * P.n_tile);
+  // dead-plane skipping (halo_plane_live): on when some (item, td) lies outside A and every item keeps a live plane
+  P.Da = plan.adims[0];
+  P.skip = 0;
+  if (getenv("MRA_HALO_NOSKIP") == nullptr) {
+    const int dsteps = P.pair ? (P.Dl + 1) / 2 : P.Dl;
+    bool any_dead = false, all_items_live = true;
+    for (int dq = 0; dq < dsteps; ++dq) {
+      int live = 0;
+      for (int td = 0; td < P.kd; ++td) {
+        const int a0 = (P.pair ? 2 * dq : dq) + P.dmin + td;
+        const bool lv = P.pair ? (a0 + 1 >= 0 && a0 < P.Da) : (a0 >= 0 && a0 < P.Da);
+        if (lv) ++live; else any_dead = true;
+      }
+      if (live == 0) all_items_live = false;
+    }
+    P.skip = (any_dead && all_items_live) ? 1 : 0;
+  }
   CUtensorMap tmA;
   if (int rc = make_act_map(&tmA, R.a, plan.n, plan.adims[0], plan.adims[1], plan.adims[2], plan.ck, P.Wb, P.Hb, 1, 1)) return rc;
   const size_t smem = (size_t)P.NP * P.slot_bytes + (size_t)P.NB * P.n_tile * 128 / (P.pair ? 2 : 1) + 1024 + 256;

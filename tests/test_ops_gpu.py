@@ -533,3 +533,39 @@ def test_split_k_gather_matches_unsplit_and_oracle(case, monkeypatch):
         assert rel_l2(dx.cpu(), dx_ref) < 1e-2 and rel_l2(dx2.cpu(), dx_ref) < 1e-2
         assert rel_l2(dx.float().cpu(), dx2.float().cpu()) < 4e-3
     assert I.tc_error() == 0
+
+
+DEAD_PLANES = [
+    (ConvGeom(256, 256, 3, 1, 0), (14, 12, 10), 2),            # G.rb dgrad: 14^3-ish padded gradient, flat tiles, CTA pairs
+    (ConvGeom(256, 256, 3, 1, 0), (9, 10, 10), 1),             # odd plane count: the last pair's partner plane does not exist
+    (ConvGeom(256, 512, 4, 1, 1), (9, 9, 9), 2),               # D.4: zero padding, dead planes in fprop AND dgrad
+    (ConvGeom(64, 64, 3, 1, 1), (9, 7, 5), 1),
+]
+
+
+@pytest.mark.parametrize("mode", ["pair", "single"])
+@pytest.mark.parametrize("case", DEAD_PLANES, ids=gid)
+def test_halo_dead_plane_skipping_is_bit_identical(case, mode, monkeypatch):
+    """gather_halo_kernel skips input planes that lie outside the A tensor for every tile of a work item (conv_tc_halo.cuh:
+    halo_plane_live): no plane load, no weight slabs, no MMAs.  The skipped MMAs multiply TMA zero fill, so the result
+    must be the same bits as with MRA_HALO_NOSKIP=1 (epilogue statistics: up to the order of fp64 atomics) and match the
+    fp64 oracle."""
+    g, dims, n = case
+    I = ops.impl()
+    ref = R.RefImpl(torch.float64)
+    if mode == "single":
+        monkeypatch.setenv("MRA_GATHER_MODE", "single")
+    x, w, b, dy = _conv_case(g, dims, n, torch.bfloat16, seed=11)
+    xd, wd, bd, dyd = x.cuda(), w.cuda(), b.cuda(), dy.cuda()
+    wT = I.pack_weight_t(wd, torch.bfloat16)
+    y, st = I.conv_fprop(xd, wd, bd, g, want_stats=True)
+    dx = I.conv_dgrad(dyd, wT, g, dims)
+    monkeypatch.setenv("MRA_HALO_NOSKIP", "1")
+    y0, st0 = I.conv_fprop(xd, wd, bd, g, want_stats=True)
+    dx0 = I.conv_dgrad(dyd, wT, g, dims)
+    assert I.tc_error() == 0
+    assert bool((y.float() == y0.float()).all()) and bool((dx.float() == dx0.float()).all())
+    assert torch.allclose(st, st0, rtol=1e-9, atol=1e-9)        # fp64 atomics: the order of the CTAs' adds is free
+    y_ref, _ = ref.conv_fprop(x.double(), w.double(), b.double(), g, want_stats=True)
+    dx_ref = ref.conv_dgrad(dy.double(), w.double().transpose(1, 2).contiguous(), g, dims)
+    assert rel_l2(y.cpu(), y_ref) < 1e-2 and rel_l2(dx.cpu(), dx_ref) < 1e-2
