@@ -81,6 +81,9 @@ class ConvFn(torch.autograd.Function):
         ctx.link = link
         ctx.in_dims = tuple(x.shape[1:4])
         ctx.save_for_backward(x, y if act != ACT_NONE else None)
+        # the statistics output never receives a gradient: without this autograd hands backward() a freshly zero-filled
+        # fp64 tensor for it on every call (168 fill kernels per step)
+        ctx.set_materialize_grads(False)
         if stats is not None:
             ctx.mark_non_differentiable(stats)
             return y, stats
@@ -88,6 +91,8 @@ class ConvFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gy, _gstats):
+        if gy is None:                                   # (materialize_grads is off) no gradient reached the output
+            return (None,) * 9
         I = ops.impl()
         x, y = ctx.saved_tensors
         mod, g = ctx.mod, ctx.mod.geom
