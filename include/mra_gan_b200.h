@@ -219,6 +219,20 @@ int mra_debug_tc_error(int reset);
  * with the MRA_WGRAD_DEBUG / MRA_GATHER_DEBUG environment bit 1 set (pipeline diagnosis; synchronises). */
 int mra_debug_counters(unsigned long long* out, int reset);
 
+/* Host-side walk of the PERSISTENT SCHEDULES of the tensor-core kernels for one op (which: 0 fprop, 1 dgrad, 2 wgrad), run
+ * on the CPU with the very functions the kernels execute (halo_decode / halo_stats_key / halo_plane_live for
+ * gather_halo_kernel, wseg_begin / wseg_next for wgrad_tc_kernel's stream-K ranges).  No device work: usable without a
+ * GPU; tests/test_schedule_cpu.py checks coverage, channel bounds of the statistics flushes and the stream-K partition.
+ * units: CTAs (or CTA pairs) of the persistent grid, 0 = what the launch would use (148 SMs without a device).
+ * single != 0: gather_halo_kernel without CTA pairs.  Layout of out[] (int32 words):
+ *   which 0/1: {1, n_launches} then per halo-capable launch {li, pair, mode, N, Dl, Hl, Wl, Wb, Cn, n_tile, n_tiles,
+ *     total_tiles, split_from, total_work, units, skip, kd, n_records} + n_records x {unit, rank, work, n, d, n0, width,
+ *     h0, w0, f0, tb, coff, live_mask}
+ *   which 2:   {2, pair, m_tiles, n_tiles, n_groups, n_items, kblocks, units, cost_lo, cost_hi} + n_groups x {tap0, ntaps,
+ *     gpi, item0, n_items} + {n_segments} + n_segments x {unit, item, mt, nt, g, tap0, ntap, kb0, kb1}
+ * Returns the number of words written, or a negative error code (cap too small, unsupported geometry). */
+int mra_debug_schedule(const mra_conv_desc* d, int which, int units, int single, int32_t* out, int cap);
+
 /* Number of kernels this library has launched in this process (host-side counter). */
 long long mra_debug_launch_count(void);
 

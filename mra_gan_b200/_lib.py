@@ -72,6 +72,7 @@ _SIGNATURES = {
     "mra_window_accumulate": ([_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "mra_window_finalize": ([_P, _P, _L, _P], C.c_int),
     "mra_conv_plan_describe": ([C.POINTER(ConvDesc), _I, C.POINTER(C.c_int32), _I], C.c_int),
+    "mra_debug_schedule": ([C.POINTER(ConvDesc), _I, _I, _I, C.POINTER(C.c_int32), _I], C.c_int),
 }
 
 _lock = threading.Lock()

@@ -849,16 +849,16 @@ struct WSegIter {
   long long pos, end, woff;
   int work;
 };
-__device__ __forceinline__ int wg_item_group(const WgradP& P, int item) {
+__host__ __device__ __forceinline__ int wg_item_group(const WgradP& P, int item) {
   int g = 0;
   while (g + 1 < P.n_groups && item >= P.grp[g + 1].item0) ++g;
   return g;
 }
-__device__ __forceinline__ int wg_item_ntap(const WgradP& P, int g, int item) {
+__host__ __device__ __forceinline__ int wg_item_ntap(const WgradP& P, int g, int item) {
   const WGroup& G = P.grp[g];
   return min(G.gpi, G.ntaps - (item - G.item0) * G.gpi);
 }
-__device__ __forceinline__ void wseg_begin(const WgradP& P, long long kblocks, WSegIter& it, int unit, int nunits) {
+__host__ __device__ __forceinline__ void wseg_begin(const WgradP& P, long long kblocks, WSegIter& it, int unit, int nunits) {
   const long long share = (P.total_cost + nunits - 1) / nunits;
   it.pos = (long long)unit * share;
   it.end = min(it.pos + share, P.total_cost);
@@ -888,7 +888,7 @@ __device__ __forceinline__ void wseg_begin(const WgradP& P, long long kblocks, W
   it.work = G.item0 * per_item + (int)wl;
   if (it.work > n_work) it.work = n_work;
 }
-__device__ __forceinline__ bool wseg_next(const WgradP& P, long long kblocks, WSegIter& it, WSeg& sg) {
+__host__ __device__ __forceinline__ bool wseg_next(const WgradP& P, long long kblocks, WSegIter& it, WSeg& sg) {
   const int per_item = P.m_tiles * P.n_tiles;
   const int n_work = P.n_items * per_item;
   while (it.pos < it.end && it.work < n_work) {
@@ -1439,6 +1439,50 @@ inline int run_gather_v1_launch(const GatherPlan& plan, const GatherLaunch* Ls, 
   return 0;
 }
 
+// Tile geometry of a wgrad launch (K-block boxes, m / n tiles) and the CTA-pair decision; returns pair.
+inline bool wgrad_fill_geometry(const WgradPlan& plan, WgradP& P) {
+  const bool sw = plan.m_is_shifted != 0;
+  const int Km = sw ? plan.cn : plan.cm, Kn = sw ? plan.cm : plan.cn;
+  P.bd = plan.box[0]; P.bh = plan.box[1]; P.bw = plan.box[2];
+  P.tilesD = (plan.qdims[0] + P.bd - 1) / P.bd; P.tilesH = (plan.qdims[1] + P.bh - 1) / P.bh;
+  P.tilesW = (plan.qdims[2] + P.bw - 1) / P.bw;
+  P.N = plan.n; P.sstep = plan.sstep;
+  P.Km = Km; P.Kn = Kn;
+  P.m_chunks = Km >= 128 ? 2 : 1;
+  P.ncc = plan.ncc;
+  // CTA pairs (cta_group::2): 256 dense channels per unit, each CTA loads half of the shifted chunks.  Needs whole
+  // 256-channel m tiles and one tap per MMA (ncc == 4), and enough K-blocks to feed 74 pairs.
+  long long pair_min = 64ll * 64 * 8;                       // K positions (MRA_WGRAD_PAIR_MIN: test hook)
+  { const char* e = getenv("MRA_WGRAD_PAIR_MIN"); if (e) pair_min = atoll(e); }
+  const bool pair = Km % 256 == 0 && plan.ncc == 4 && (num_sms() % 2) == 0 && getenv("MRA_WGRAD_NOPAIR") == nullptr &&
+                    (long long)plan.qdims[0] * plan.qdims[1] * plan.qdims[2] * plan.n >= pair_min;
+  P.m_tiles = pair ? Km / 256 : (Km + 127) / 128;
+  P.n_tiles = Kn / (64 * P.ncc);
+  return pair;
+}
+// The stream-K side of a wgrad launch: tap groups -> work items -> cost prefixes (needs P.m_tiles / P.n_tiles).  Kept apart
+// from the tensor maps so that mra_debug_schedule can walk the schedule on the CPU with the code the kernel runs.
+inline bool wgrad_fill_schedule(const WgradPlan& plan, long long kblocks, WgradP& P) {
+  P.n_groups = (int)plan.launches.size();
+  if (P.n_groups > kMaxWGroups) return false;
+  int tapc = 0, itemc = 0;
+  P.total_cost = 0;
+  for (int gi = 0; gi < P.n_groups; ++gi) {
+    const WgradLaunch& L = plan.launches[gi];
+    WGroup& G = P.grp[gi];
+    G.tap0 = tapc; G.ntaps = (int)L.taps.size();
+    G.gpi = L.gpi; G.share = L.share;
+    G.item0 = itemc; G.n_items = (G.ntaps + G.gpi - 1) / G.gpi;
+    G.cost0 = P.total_cost;
+    for (int it = 0; it < G.n_items; ++it) {
+      const int nt = G.ntaps - it * G.gpi < G.gpi ? G.ntaps - it * G.gpi : G.gpi;
+      P.total_cost += (long long)nt * kblocks * P.m_tiles * P.n_tiles;
+    }
+    tapc += G.ntaps; itemc += G.n_items;
+  }
+  P.n_items = itemc;
+  return tapc <= kMaxTaps;
+}
 inline int run_wgrad_tc(const WgradPlan& plan, const void* x, const void* dy, float* dw, cudaStream_t st) {
   int* err = tc_err_flag();
   MRA_REQUIRE(plan.cm % 64 == 0 && plan.cn % 64 == 0 && (int)plan.taps.size() <= kMaxTaps,
@@ -1464,21 +1508,7 @@ inline int run_wgrad_tc(const WgradPlan& plan, const void* x, const void* dy, fl
   memset(&maps, 0, sizeof(maps));
   WgradP P;
   memset(&P, 0, sizeof(P));
-  P.bd = plan.box[0]; P.bh = plan.box[1]; P.bw = plan.box[2];
-  P.tilesD = (plan.qdims[0] + P.bd - 1) / P.bd; P.tilesH = (plan.qdims[1] + P.bh - 1) / P.bh;
-  P.tilesW = (plan.qdims[2] + P.bw - 1) / P.bw;
-  P.N = plan.n; P.sstep = plan.sstep;
-  P.Km = Km; P.Kn = Kn;
-  P.m_chunks = Km >= 128 ? 2 : 1;
-  P.ncc = plan.ncc;
-  // CTA pairs (cta_group::2): 256 dense channels per unit, each CTA loads half of the shifted chunks.  Needs whole
-  // 256-channel m tiles and one tap per MMA (ncc == 4), and enough K-blocks to feed 74 pairs.
-  long long pair_min = 64ll * 64 * 8;                       // K positions (MRA_WGRAD_PAIR_MIN: test hook)
-  { const char* e = getenv("MRA_WGRAD_PAIR_MIN"); if (e) pair_min = atoll(e); }
-  const bool pair = Km % 256 == 0 && plan.ncc == 4 && (num_sms() % 2) == 0 && getenv("MRA_WGRAD_NOPAIR") == nullptr &&
-                    (long long)plan.qdims[0] * plan.qdims[1] * plan.qdims[2] * plan.n >= pair_min;
-  P.m_tiles = pair ? Km / 256 : (Km + 127) / 128;
-  P.n_tiles = Kn / (64 * P.ncc);
+  const bool pair = wgrad_fill_geometry(plan, P);
   P.dw = dw; P.err = err;
   { const char* e = getenv("MRA_WGRAD_DEBUG"); P.debug = e ? atoi(e) : 0; }
   P.dbg = tc_dbg_counters();
@@ -1487,15 +1517,13 @@ inline int run_wgrad_tc(const WgradPlan& plan, const void* x, const void* dy, fl
   if (!sw) { P.m_stride = plan.cn; P.n_stride = 1; }
   else     { P.m_stride = 1; P.n_stride = plan.cn; }
   const long long kblocks = (long long)P.tilesW * P.tilesH * P.tilesD * plan.n;
-  P.n_groups = (int)plan.launches.size();
-  int tapc = 0, itemc = 0, max_cols = 0;
+  MRA_REQUIRE(wgrad_fill_schedule(plan, kblocks, P), "wgrad plan: too many taps or tap groups");
+  int max_cols = 0;
   for (int gi = 0; gi < P.n_groups; ++gi) {
     const WgradLaunch& L = plan.launches[gi];
     WGroup& G = P.grp[gi];
     const int xd = P.bd + L.ext[0], xh = P.bh + L.ext[1], xw = P.bw + L.ext[2];
-    G.tap0 = tapc; G.ntaps = (int)L.taps.size();
-    G.gpi = L.gpi; G.share = L.share;
-    G.item0 = itemc; G.n_items = (G.ntaps + G.gpi - 1) / G.gpi;
+    const int tapc = G.tap0;
     G.pitch_w = xw; G.pitch_h = xh * xw;
     G.box_tx = xd * xh * xw * 128;
     const int slot = (G.box_tx + 1023) / 1024 * 1024;
@@ -1512,16 +1540,8 @@ inline int run_wgrad_tc(const WgradPlan& plan, const void* x, const void* dy, fl
       P.rshift[tapc + i] = (int16_t)r;
       P.twi[tapc + i] = (int16_t)t.widx;
     }
-    G.cost0 = P.total_cost;
-    for (int it = 0; it < G.n_items; ++it) {
-      const int nt = G.ntaps - it * G.gpi < G.gpi ? G.ntaps - it * G.gpi : G.gpi;
-      P.total_cost += (long long)nt * kblocks * P.m_tiles * P.n_tiles;
-    }
-    tapc += G.ntaps; itemc += G.n_items;
     if (int rc = make_act_map(&maps.m[gi], shifted, plan.n, sdims[0], sdims[1], sdims[2], Kn, xw, xh, xd, plan.sstep)) return rc;
   }
-  MRA_REQUIRE(tapc <= kMaxTaps, "wgrad plan: too many taps");
-  P.n_items = itemc;
   const size_t stage_bytes = 2 * kChunkBytes + (size_t)P.sets_max * (P.ncc / (pair ? 2 : 1)) * P.box_bytes;
   int stages = (int)((kSmemLimit - 2048 - kWgradFlushBytes) / stage_bytes);
   MRA_REQUIRE(stages >= 2, "wgrad plan: stage does not fit shared memory");

@@ -73,7 +73,7 @@ __device__ __forceinline__ uint64_t desc_kmajor_sw128_sbo(uint32_t saddr, uint32
 struct HaloTile { int n, d, d0, n0, h0, w0, f0, hs, roff, width; int rot_kc0, rot_td0, rot_th0, rot_tw0, rot_t; };
 // work index -> coordinates.  Order: n_tile fastest, then the tiles of a plane, then d (pair mode: pairs of
 // planes, CTA rank r takes d = 2 * dp + r so both tiles share the weight slab and the in-plane geometry), then n.
-__device__ __forceinline__ HaloTile halo_decode(const HaloP& P, int work, int pair, int rank) {
+__host__ __device__ __forceinline__ HaloTile halo_decode(const HaloP& P, int work, int pair, int rank) {
   HaloTile t;
   int tile = work, half = 0;
   t.width = P.n_tile;
@@ -112,12 +112,21 @@ __device__ __forceinline__ HaloTile halo_decode(const HaloP& P, int work, int pa
   return t;
 }
 
+// Statistics are kept per TILE (channel base tb = nt * n_tile), indexed by the chunk's position inside the full tile: a
+// half-width tail item (t.n0 = tb or tb + n_tile / 2) adds into chunks coff .. coff + width / 32 - 1 of the same partials
+// as the full-width tiles of that (sample, tile) before it, and a flush covers exactly the tile's n_tile channels
+// [tb, tb + n_tile) -- never past Cn.  (Host-callable: mra_debug_schedule walks the same code on the CPU.)
+__host__ __device__ __forceinline__ void halo_stats_key(const HaloP& P, const HaloTile& t, int& tb, int& coff) {
+  tb = t.n0 - (t.n0 % P.n_tile);
+  coff = (t.n0 - tb) >> 5;            // even (n_tile >= 128 when items are split), keeps the warps' chunk parity
+}
+
 // Does input plane td of the work item whose first output plane is d0 touch the A tensor at all?  A dgrad computes the
 // gradient of the PADDED input (34^3 outputs from a 32^3 gradient for the residual blocks): the outermost output planes
 // see kd - 1 (or, for the second and second-to-last, kd - 2) input planes that are pure zero fill.  Such a plane is
 // skipped by all three roles -- no plane load, no weight slabs, no MMAs -- when it is dead for EVERY tile of the item
 // (both planes of a CTA pair): 2 of the 51 (pair, td) steps of the G.rb dgrad, 6 of 102 without pairs.
-__device__ __forceinline__ bool halo_plane_live(const HaloP& P, int d0, int td, int pair) {
+__host__ __device__ __forceinline__ bool halo_plane_live(const HaloP& P, int d0, int td, int pair) {
   if (!P.skip) return true;
   const int a0 = d0 + P.dmin + td;
   return pair ? (a0 + 1 >= 0 && a0 < P.Da) : (a0 >= 0 && a0 < P.Da);
@@ -334,12 +343,8 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const bool valid = lw < P.Wl && lh < P.Hl && t.d < P.Dl;
       const long long obase = (long long)t.n * P.osn + (long long)(t.d * P.ostep + P.od0) * P.osd +
                               (long long)(lh * P.ostep + P.oh0) * P.osh + (long long)(lw * P.ostep + P.ow0) * P.osw + t.n0;
-      // Statistics are kept per TILE (channel base tb = nt * n_tile), indexed by the chunk's position inside the full
-      // tile: a half-width tail item (t.n0 = tb or tb + n_tile / 2) adds into chunks coff .. coff + width / 32 - 1 of
-      // the same partials as the full-width tiles of that (sample, tile) before it, and a flush covers exactly the
-      // tile's n_tile channels [tb, tb + n_tile) -- never past Cn.
-      const int tb = t.n0 - (t.n0 % P.n_tile);
-      const int coff = (t.n0 - tb) >> 5;        // even (n_tile >= 128 when items are split), keeps the warps' chunk parity
+      int tb, coff;                             // statistics key of the item (halo_stats_key)
+      halo_stats_key(P, t, tb, coff);
       if (kMode != 0 && (t.n != st_n || tb != st_n0)) {
         epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, W.q, W.c_begin, 2, nch_full, lane, st, defer, d1, d2, epi_red);
         st_n = t.n; st_n0 = tb;
@@ -375,7 +380,7 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // ------------------------------------------------------------------ host side
 // Can this launch run on the halo kernel?  Needs unit A step, taps forming a full (kd, kh, kw) box and a plane
 // that fits the shared-memory budget.  Fills P's geometry fields on success.
-inline bool halo_setup(const GatherLaunch& L, int n, int ck, int cn, bool pair, HaloP& P) {
+inline bool halo_setup(const GatherLaunch& L, int n, int ck, int cn, bool pair, HaloP& P, int units_override = 0) {
   if (L.astep != 1 || L.taps.empty()) return false;
   int lo[3] = {1 << 30, 1 << 30, 1 << 30}, hi[3] = {-(1 << 30), -(1 << 30), -(1 << 30)};
   for (const Tap& t : L.taps) {
@@ -441,7 +446,7 @@ inline bool halo_setup(const GatherLaunch& L, int n, int ck, int cn, bool pair, 
   P.total_tiles = (int)total;
   // persistent schedule: `units` CTAs (or pairs) take work items round-robin.  When the last round is at most
   // half full, its tiles are split into two half-width items each.
-  const int units = pair ? num_sms() / 2 : num_sms();
+  const int units = units_override > 0 ? units_override : (pair ? num_sms() / 2 : num_sms());
   const int rem = (int)(total % units);
   P.split_from = P.total_tiles; P.total_work = P.total_tiles;
   if (total > units && rem > 0 && 2 * rem <= units && n_tile >= 128 && getenv("MRA_GATHER_NOSPLIT") == nullptr) {
@@ -449,6 +454,25 @@ inline bool halo_setup(const GatherLaunch& L, int n, int ck, int cn, bool pair, 
     P.total_work = P.total_tiles + rem;
   }
   return true;
+}
+
+// dead-plane skipping (halo_plane_live): on when some (item, td) lies outside A and every item keeps a live plane
+inline void halo_fill_skip(HaloP& P, int Da) {
+  P.Da = Da;
+  P.skip = 0;
+  if (getenv("MRA_HALO_NOSKIP") != nullptr) return;
+  const int dsteps = P.pair ? (P.Dl + 1) / 2 : P.Dl;
+  bool any_dead = false, all_items_live = true;
+  for (int dq = 0; dq < dsteps; ++dq) {
+    int live = 0;
+    for (int td = 0; td < P.kd; ++td) {
+      const int a0 = (P.pair ? 2 * dq : dq) + P.dmin + td;
+      const bool lv = P.pair ? (a0 + 1 >= 0 && a0 < Da) : (a0 >= 0 && a0 < Da);
+      if (lv) ++live; else any_dead = true;
+    }
+    if (live == 0) all_items_live = false;
+  }
+  P.skip = (any_dead && all_items_live) ? 1 : 0;
 }
 
 inline int run_gather_halo(const GatherPlan& plan, const GatherLaunch& L, HaloP& P, const GatherRun& R, const CUtensorMap& tmB_in,
@@ -483,23 +507,7 @@ inline int run_gather_halo(const GatherPlan& plan, const GatherLaunch& L, HaloP&
   { const char* e = getenv("MRA_GATHER_DEBUG"); P.debug = e ? atoi(e) : 0; }
   P.dbg = tc_dbg_counters();
   P.tmem_cols = pow2_cols(2 * P.n_tile);
-  // dead-plane skipping (halo_plane_live): on when some (item, td) lies outside A and every item keeps a live plane
-  P.Da = plan.adims[0];
-  P.skip = 0;
-  if (getenv("MRA_HALO_NOSKIP") == nullptr) {
-    const int dsteps = P.pair ? (P.Dl + 1) / 2 : P.Dl;
-    bool any_dead = false, all_items_live = true;
-    for (int dq = 0; dq < dsteps; ++dq) {
-      int live = 0;
-      for (int td = 0; td < P.kd; ++td) {
-        const int a0 = (P.pair ? 2 * dq : dq) + P.dmin + td;
-        const bool lv = P.pair ? (a0 + 1 >= 0 && a0 < P.Da) : (a0 >= 0 && a0 < P.Da);
-        if (lv) ++live; else any_dead = true;
-      }
-      if (live == 0) all_items_live = false;
-    }
-    P.skip = (any_dead && all_items_live) ? 1 : 0;
-  }
+  halo_fill_skip(P, plan.adims[0]);
   CUtensorMap tmA;
   if (int rc = make_act_map(&tmA, R.a, plan.n, plan.adims[0], plan.adims[1], plan.adims[2], plan.ck, P.Wb, P.Hb, 1, 1)) return rc;
   const size_t smem = (size_t)P.NP * P.slot_bytes + (size_t)P.NB * P.n_tile * 128 / (P.pair ? 2 : 1) + 1024 + 256;

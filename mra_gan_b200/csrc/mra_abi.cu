@@ -487,6 +487,87 @@ int mra_conv_plan_describe(const mra_conv_desc* d, int which, int32_t* out, int 
   return describe(P, out, cap);
 }
 
+// CPU walk of the persistent schedules (see include/mra_gan_b200.h).
+int mra_debug_schedule(const mra_conv_desc* d, int which, int units, int single, int32_t* out, int cap) {
+  if (int rc = check_conv(d)) return rc;
+  MRA_REQUIRE(out != nullptr && cap >= 16, "mra_debug_schedule: no output buffer");
+  int n = 0;
+  auto put = [&](long long v) { if (n < cap) out[n] = (int32_t)v; ++n; };
+  if (which == 2) {
+    WgradPlan plan;
+    MRA_REQUIRE(build_wgrad_plan(*d, plan), "unsupported geometry");
+    MRA_REQUIRE(plan.cm % 64 == 0 && plan.cn % 64 == 0 && !plan.launches.empty(), "shape not eligible for the tensor-core wgrad path");
+    tc::WgradP P;
+    memset(&P, 0, sizeof(P));
+    const bool pair = tc::wgrad_fill_geometry(plan, P);
+    const long long kblocks = (long long)P.tilesW * P.tilesH * P.tilesD * plan.n;
+    MRA_REQUIRE(tc::wgrad_fill_schedule(plan, kblocks, P), "wgrad plan: too many taps or tap groups");
+    long long nunits = units;
+    if (nunits <= 0) {
+      if (pair) nunits = (num_sms() & ~1) / 2;
+      else { nunits = num_sms(); if (P.total_cost < nunits * 4) nunits = (P.total_cost + 3) / 4; if (nunits < 1) nunits = 1; }
+    }
+    put(2); put(pair); put(P.m_tiles); put(P.n_tiles); put(P.n_groups); put(P.n_items); put(kblocks); put(nunits);
+    put(P.total_cost & 0x7fffffff); put(P.total_cost >> 31);
+    for (int g = 0; g < P.n_groups; ++g) {
+      put(P.grp[g].tap0); put(P.grp[g].ntaps); put(P.grp[g].gpi); put(P.grp[g].item0); put(P.grp[g].n_items);
+    }
+    const int at = n;
+    put(0);
+    int nseg = 0;
+    for (int u = 0; u < (int)nunits; ++u) {
+      tc::WSegIter it; tc::WSeg sg;
+      tc::wseg_begin(P, kblocks, it, u, (int)nunits);
+      while (tc::wseg_next(P, kblocks, it, sg)) {
+        put(u); put(sg.item); put(sg.mt); put(sg.nt); put(sg.g); put(sg.tap0); put(sg.ntap); put(sg.kb0); put(sg.kb1);
+        ++nseg;
+      }
+    }
+    if (at < cap) out[at] = nseg;
+    MRA_REQUIRE(n <= cap, "mra_debug_schedule: %d words needed, cap %d", n, cap);
+    return n;
+  }
+  MRA_REQUIRE(which == 0 || which == 1, "which must be 0, 1 or 2");
+  GatherPlan plan;
+  MRA_REQUIRE(build_gather_plan(*d, which, plan), "unsupported geometry");
+  put(1);
+  const int at_nl = n;
+  put(0);
+  int nl = 0;
+  for (size_t li = 0; li < plan.launches.size(); ++li) {
+    const GatherLaunch& L = plan.launches[li];
+    tc::HaloP P;
+    memset(&P, 0, sizeof(P));
+    if (!tc::halo_setup(L, plan.n, plan.ck, plan.cn, single == 0, P, units)) continue;
+    tc::halo_fill_skip(P, plan.adims[0]);
+    const int pair = P.pair;
+    int nu = units > 0 ? units : (pair ? num_sms() / 2 : num_sms());
+    if (P.total_work < nu) nu = P.total_work;
+    put((int)li); put(pair); put(P.mode); put(P.N); put(P.Dl); put(P.Hl); put(P.Wl); put(P.Wb); put(P.Cn); put(P.n_tile);
+    put(P.n_tiles); put(P.total_tiles); put(P.split_from); put(P.total_work); put(nu); put(P.skip); put(P.kd);
+    const int at = n;
+    put(0);
+    int nrec = 0;
+    for (int u = 0; u < nu; ++u)
+      for (int r = 0; r < (pair ? 2 : 1); ++r)
+        for (int w = u; w < P.total_work; w += nu) {
+          const tc::HaloTile t = tc::halo_decode(P, w, pair, r);
+          int tb, coff;
+          tc::halo_stats_key(P, t, tb, coff);
+          int live = 0;
+          for (int td = 0; td < P.kd && td < 31; ++td) if (tc::halo_plane_live(P, t.d0, td, pair)) live |= 1 << td;
+          put(u); put(r); put(w); put(t.n); put(t.d); put(t.n0); put(t.width); put(t.h0); put(t.w0); put(t.f0); put(tb); put(coff);
+          put(live);
+          ++nrec;
+        }
+    if (at < cap) out[at] = nrec;
+    ++nl;
+  }
+  if (at_nl < cap) out[at_nl] = nl;
+  MRA_REQUIRE(n <= cap, "mra_debug_schedule: %d words needed, cap %d", n, cap);
+  return n;
+}
+
 // Reads (and optionally clears) the tensor-core kernels' device error flag.  Synchronises the
 // device: debugging / test use only.  0 = no error, else the code of the first timed-out wait.
 int mra_debug_tc_error(int reset) {

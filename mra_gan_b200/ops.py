@@ -455,3 +455,19 @@ def plan_describe(g, n, in_dims, which, dtype=MRA_BF16):
     if nwords < 0:
         _lib.check(nwords, "mra_conv_plan_describe")
     return list(buf[:nwords])
+
+
+def schedule_describe(g, n, in_dims, which, units=0, single=False, dtype=MRA_BF16, cap=1 << 22):
+    """Host-only: the persistent schedule of the tensor-core kernel(s) of a conv op as int32 words, walked on the CPU by
+    the functions the kernels run (mra_debug_schedule; layout in include/mra_gan_b200.h)."""
+    L = _lib.lib()
+    d = _lib.ConvDesc()
+    d.n, d.cin, d.cout = n, g.cin, g.cout
+    d.din, d.hin, d.win = in_dims
+    d.dout, d.hout, d.wout = g.out_dims(tuple(in_dims))
+    d.k, d.stride, d.pad, d.transposed, d.dtype = g.k, g.stride, g.pad, int(g.transposed), dtype
+    buf = (C.c_int32 * cap)()
+    nwords = L.mra_debug_schedule(C.byref(d), which, units, int(single), buf, cap)
+    if nwords < 0:
+        _lib.check(nwords, "mra_debug_schedule")
+    return list(buf[:nwords])
