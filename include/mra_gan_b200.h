@@ -226,8 +226,8 @@ int mra_debug_counters(unsigned long long* out, int reset);
  * units: CTAs (or CTA pairs) of the persistent grid, 0 = what the launch would use (148 SMs without a device).
  * single != 0: gather_halo_kernel without CTA pairs.  Layout of out[] (int32 words):
  *   which 0/1: {1, n_launches} then per halo-capable launch {li, pair, mode, N, Dl, Hl, Wl, Wb, Cn, n_tile, n_tiles,
- *     total_tiles, split_from, total_work, units, skip, kd, n_records} + n_records x {unit, rank, work, n, d, n0, width,
- *     h0, w0, f0, tb, coff, live_mask}
+ *     total_tiles, split_from, total_work, units, skip, kd, nsub, n_records} + n_records x {unit, rank, work, n, d, n0,
+ *     width, h0, w0, f0, tb, coff, live_mask, sub, rotation}
  *   which 2:   {2, pair, m_tiles, n_tiles, n_groups, n_items, kblocks, units, cost_lo, cost_hi} + n_groups x {tap0, ntaps,
  *     gpi, item0, n_items} + {n_segments} + n_segments x {unit, item, mt, nt, g, tap0, ntap, kb0, kb1}
  * Returns the number of words written, or a negative error code (cap too small, unsupported geometry). */

@@ -59,6 +59,8 @@ struct HaloP {
   int debug;
   unsigned long long* dbg;
   int pair;                         // 1: cta_group::2 pairs (host-side choice of the kernel instantiation)
+  int nsub;                         // position tiles per work item: 1, or 2 = DUAL items (two tiles of one plane, neighbours in
+                                    // the tile order, share every weight slab; n_tile = 128, the two accumulators side by side)
   int Da;                           // d extent of the A tensor
   int skip;                         // 1: input planes that lie outside A for every tile of a work item are not loaded and
                                     // their MMAs not issued (halo_plane_live); host-checked: every item keeps >= 1 plane
@@ -73,7 +75,7 @@ __device__ __forceinline__ uint64_t desc_kmajor_sw128_sbo(uint32_t saddr, uint32
 struct HaloTile { int n, d, d0, n0, h0, w0, f0, hs, roff, width; int rot_kc0, rot_td0, rot_th0, rot_tw0, rot_t; };
 // work index -> coordinates.  Order: n_tile fastest, then the tiles of a plane, then d (pair mode: pairs of
 // planes, CTA rank r takes d = 2 * dp + r so both tiles share the weight slab and the in-plane geometry), then n.
-__host__ __device__ __forceinline__ HaloTile halo_decode(const HaloP& P, int work, int pair, int rank) {
+__host__ __device__ __forceinline__ HaloTile halo_decode(const HaloP& P, int work, int pair, int rank, int sub = 0) {
   HaloTile t;
   int tile = work, half = 0;
   t.width = P.n_tile;
@@ -82,7 +84,10 @@ __host__ __device__ __forceinline__ HaloTile halo_decode(const HaloP& P, int wor
     tile = P.split_from + (k >> 1); half = k & 1; t.width = P.n_tile >> 1;
   }
   const int nt = tile % P.n_tiles; tile /= P.n_tiles;
-  const int j = tile % P.tiles_hw; tile /= P.tiles_hw;
+  const int items_hw = P.tiles_hw / P.nsub;       // (dual items: tiles_hw is even)
+  const int j0 = (tile % items_hw) * P.nsub;      // first tile of the item: the rotation key, the same for both tiles
+  const int j = j0 + sub;
+  tile /= items_hw;
   const int dsteps = pair ? (P.Dl + 1) / 2 : P.Dl;
   const int dq = tile % dsteps;
   t.d = pair ? 2 * dq + rank : dq;            // may be == Dl for the odd plane's partner: loads hit zero fill, nothing is stored
@@ -94,7 +99,7 @@ __host__ __device__ __forceinline__ HaloTile halo_decode(const HaloP& P, int wor
   // ITS SAMPLE -- not of the CTA that happens to run it -- so the fp32 accumulation order of an output element, and with
   // it every bit of a sample's result, is independent of the batch size and of how the schedule deals tiles to CTAs.
   {
-    const int key = dq * P.tiles_hw + j;
+    const int key = dq * P.tiles_hw + j0;
     const int nplanes = P.kchunks * P.kd, taps_hw = P.kh * P.kw;
     const int rot_p = key % nplanes;
     t.rot_t = (key / nplanes) % taps_hw;
@@ -196,14 +201,18 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       bool ok = true;
       for (int w = work0; w < P.total_work && ok; w += wstride) {
         const HaloTile t = halo_decode(P, w, kPair, rank);
+        const HaloTile t1 = halo_decode(P, w, kPair, rank, P.nsub - 1);      // dual items: the second tile (else == t)
         int kc = t.rot_kc0, td = t.rot_td0;
-        for (int pi = 0; pi < nplanes; ++pi) {
+        for (int pi = 0; pi < nplanes && ok; ++pi) {
           if (halo_plane_live(P, t.d0, td, kPair)) {
-            if (!mbar_wait(&p_empty[s], ph ^ 1u, P.err, 21)) { ok = false; break; }
-            if (leader) mbar_expect_tx(&p_full[s], (uint32_t)P.plane_tx * kCtas);
-            tma_load_5d_g<kPair>(planes + (size_t)s * P.slot_bytes, &tmA, &p_full[s], kc * 64, t.w0 + P.wmin, t.hs + P.hmin,
-                                 t.d + P.dmin + td, t.n);
-            if (++s == P.NP) { s = 0; ph ^= 1u; }
+            for (int sub = 0; sub < P.nsub; ++sub) {                         // one ring slot per tile of the item
+              const HaloTile& ts = sub ? t1 : t;
+              if (!mbar_wait(&p_empty[s], ph ^ 1u, P.err, 21)) { ok = false; break; }
+              if (leader) mbar_expect_tx(&p_full[s], (uint32_t)P.plane_tx * kCtas);
+              tma_load_5d_g<kPair>(planes + (size_t)s * P.slot_bytes, &tmA, &p_full[s], kc * 64, ts.w0 + P.wmin, ts.hs + P.hmin,
+                                   ts.d + P.dmin + td, ts.n);
+              if (++s == P.NP) { s = 0; ph ^= 1u; }
+            }
           }
           if (++td == P.kd) { td = 0; if (++kc == P.kchunks) kc = 0; }
         }
@@ -249,6 +258,8 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const uint32_t slot_u = (uint32_t)P.slot_bytes >> 4, bst_u = b_bytes >> 4;
       const uint32_t row_u = 128u >> 4;                                        // one plane row, in 16-byte units
       const int kh = P.kh, kw = P.kw, NP = P.NP, NB = P.NB;
+      const bool dual = P.nsub == 2;
+      const int acc_cols = P.n_tile * P.nsub;                                  // TMEM columns of one accumulator buffer
       const uint32_t line_step = (uint32_t)(P.Wb - (kw - 1)) * row_u;          // from the last tap of a line to the next line's first
       int ps = 0, bs = 0;
       uint32_t pph = 0, bph = 0;
@@ -260,6 +271,7 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const uint32_t aph = ((uint32_t)j >> 1) & 1u;
         const HaloTile t = halo_decode(P, w, kPair, 0);
         const uint32_t roff_u = (uint32_t)t.roff * row_u;      // flat tiles start inside their first plane line
+        const uint32_t roff1_u = dual ? (uint32_t)halo_decode(P, w, kPair, 0, 1).roff * row_u : 0u;   // second tile of a dual item
         const uint32_t idesc = t.width == P.n_tile ? idesc_full : idesc_half;
         const uint32_t rot_a_u = (uint32_t)(t.rot_th0 * P.Wb + t.rot_tw0) * row_u;
         const int rot_th0 = t.rot_th0, rot_tw0 = t.rot_tw0;
@@ -267,7 +279,8 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (!mbar_wait(&acc_empty[buf], aph ^ 1u, P.err, 24)) { ok = false; break; }
         if (prof) t_wacc += clock64() - ta0;
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * P.n_tile);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * acc_cols);
+        const uint32_t d_tmem1 = d_tmem + (uint32_t)P.n_tile;  // dual items: the second tile's accumulator
         uint32_t acc = 0;
         int td_p = t.rot_td0;                                  // td of plane pi (the producers' walk)
         for (int pi = 0; pi < nplanes && ok; ++pi) {
@@ -276,8 +289,16 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (!live) continue;
           const long long tp0 = prof ? clock64() : 0;
           if (!dbg_nop && !mbar_wait(&p_full[ps], pph, P.err, 25)) { ok = false; break; }
+          // dual items: the second tile's plane sits in the next ring slot
+          int ps1 = ps;
+          uint32_t pph1 = pph;
+          if (dual) {
+            if (++ps1 == NP) { ps1 = 0; pph1 ^= 1u; }
+            if (!dbg_nop && !mbar_wait(&p_full[ps1], pph1, P.err, 25)) { ok = false; break; }
+          }
           if (prof) t_waitp += clock64() - tp0;
           const uint32_t base_u = planes_u + (uint32_t)ps * slot_u + roff_u;
+          const uint32_t sub1_u = planes_u + (uint32_t)ps1 * slot_u + roff1_u - base_u;   // second tile's plane relative to the first's
           uint32_t a_u = base_u + rot_a_u;
           int th = rot_th0, tw = rot_tw0;
           for (int i = 0; i < taps_hw; ++i) {
@@ -294,6 +315,13 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             umma_f16_g<kPair>(d_tmem, ad + 2, bd + 2, idesc, 1u);
             umma_f16_g<kPair>(d_tmem, ad + 4, bd + 4, idesc, 1u);
             umma_f16_g<kPair>(d_tmem, ad + 6, bd + 6, idesc, 1u);
+            if (dual) {                                          // the same weight slab against the second tile's plane
+              const uint64_t ad1 = a_desc0 | (uint64_t)((a_u + sub1_u) & 0x3FFFu);
+              umma_f16_g<kPair>(d_tmem1, ad1, bd, idesc, acc);
+              umma_f16_g<kPair>(d_tmem1, ad1 + 2, bd + 2, idesc, 1u);
+              umma_f16_g<kPair>(d_tmem1, ad1 + 4, bd + 4, idesc, 1u);
+              umma_f16_g<kPair>(d_tmem1, ad1 + 6, bd + 6, idesc, 1u);
+            }
             acc = 1u;
             umma_commit_g<kPair>(done_bar);
             if (++tw == kw) {
@@ -305,6 +333,10 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
           if (ok) umma_commit_g<kPair>(&p_empty[ps]);
           if (++ps == NP) { ps = 0; pph ^= 1u; }
+          if (dual) {
+            if (ok) umma_commit_g<kPair>(&p_empty[ps]);
+            if (++ps == NP) { ps = 0; pph ^= 1u; }
+          }
         }
         if (ok) umma_commit_g<kPair>(&acc_full[buf]);
       }
@@ -333,10 +365,13 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const EpiArgs E{P.out, P.out_bf16, P.bias, P.act, P.slope, P.stats != nullptr, P.aux, P.aux_nslope};
     int j = 0;
     bool ok = true;
+    const int acc_cols = P.n_tile * P.nsub;      // TMEM columns of one accumulator buffer (dual items: two tiles side by side)
     for (int w = work0; w < P.total_work && ok; w += wstride, ++j) {
-      const HaloTile t = halo_decode(P, w, kPair, rank);
       const int buf = j & 1;
       const uint32_t aph = ((uint32_t)j >> 1) & 1u;
+      for (int sub = 0; sub < P.nsub && ok; ++sub) {
+      const HaloTile t = halo_decode(P, w, kPair, rank, sub);
+      const bool last_sub = sub == P.nsub - 1;
       int lh, lw;
       if (P.mode == 0) { lh = t.h0 + (row >> 3); lw = t.w0 + (row & 7); }
       else { const int f = t.roff + row; const int hh = f / P.Wb; lh = t.hs + hh; lw = f - hh * P.Wb; }
@@ -352,18 +387,22 @@ gather_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       nchunks = t.width / 32;
       AuxRegs ax;
       epilogue_aux_first<kMode>(E, W.c_begin, nchunks, valid, obase, false, ax);
-      ok = mbar_wait(&acc_full[buf], aph, P.err, 23);
-      if (!ok) break;
-      tc_fence_after();
+      if (sub == 0) {                           // one accumulator barrier per work item
+        ok = mbar_wait(&acc_full[buf], aph, P.err, 23);
+        if (!ok) break;
+        tc_fence_after();
+      }
       const long long te0 = prof ? clock64() : 0;
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * P.n_tile);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols + sub * P.n_tile);
       uint64_t* rel_bar = &acc_empty[buf];
       epilogue_tile<kMode>(E, t_addr, W.c_begin, 2, nchunks, valid, obase, t.n0, lane, st, coff >> 1, defer, d1, d2, ax, [&]() {
+        if (!last_sub) return;                  // dual items: the buffer is free once the SECOND tile has been read
         tc_fence_before();                      // accumulator fully read: hand the buffer back to the MMA warp
         __syncwarp();
         if (lane == 0) { if constexpr (kPair) mbar_arrive_leader(rel_bar); else mbar_arrive(rel_bar); }
       });
       if (prof && threadIdx.x == 0) atomicAdd(P.dbg + 4, (unsigned long long)(clock64() - te0));
+      }
     }
     if (kMode != 0) epilogue_flush_stats(P.stats, st_n, P.Cn, st_n0, W.q, W.c_begin, 2, nch_full, lane, st, defer, d1, d2, epi_red);
   }
@@ -397,9 +436,10 @@ inline bool halo_setup(const GatherLaunch& L, int n, int ck, int cn, bool pair, 
     P.twi[idx] = (int16_t)t.widx;
   }
   P.Dl = L.dims[0]; P.Hl = L.dims[1]; P.Wl = L.dims[2]; P.N = n;
-  const int n_tile = pick_n_tile(cn);
+  int n_tile = pick_n_tile(cn);
   if (n_tile == 0 || ck % 64 != 0) return false;
   P.Cn = cn; P.n_tile = n_tile; P.n_tiles = cn / n_tile; P.kchunks = ck / 64;
+  P.nsub = 1;
   // tile shape: 2D (16 x 8) or flat, whichever wastes fewer MMA rows (and fits)
   const long long hw = (long long)P.Hl * P.Wl;
   const int t2h = (P.Hl + 15) / 16, t2w = (P.Wl + 7) / 8;
@@ -427,21 +467,41 @@ inline bool halo_setup(const GatherLaunch& L, int n, int ck, int cn, bool pair, 
   }
   P.plane_tx = P.Wb * P.Hb * 128;
   P.slot_bytes = (P.plane_tx + 1023) / 1024 * 1024;
+  P.pair = pair ? 1 : 0;
+  // DUAL items (MRA_HALO_DUAL=1): with 256 output channels per tile the kernel is bound by L2 -> SM bytes, three quarters
+  // of them weight slabs (G.rb fprop: 1.19 GB per launch at 7.7 TB/s, tensor pipe 79 %; every CTA pair streams all 3.5 MB
+  // of weights for each 256-position tile pair).  A dual item is TWO position tiles x 128 channels instead of one tile x
+  // 256: the same MMA work and the same 256 TMEM columns per accumulator buffer, but each weight slab (now half as
+  // large) feeds two tiles -- weights 1.77 -> 0.89 MB, planes 0.28 -> 0.55 MB per item and CTA: -30 % of the bytes.
+  {
+    const char* e = getenv("MRA_HALO_DUAL");
+    const size_t bB2 = (size_t)128 * 128 / 2;
+    if (e && atoi(e) != 0 && pair && n_tile == 256 && P.tiles_hw % 2 == 0 && 4 * (size_t)P.slot_bytes + 4 * bB2 <= budget) {
+      n_tile = 128;
+      P.n_tile = 128; P.n_tiles = cn / 128; P.nsub = 2;
+    }
+  }
   // ring depths: weights get what the planes leave (>= 2 each)
   const size_t bB = (size_t)n_tile * 128 / (pair ? 2 : 1);
-  P.pair = pair ? 1 : 0;
-  int NP = kd >= 3 ? 3 : 2;
-  if (kd * P.kchunks == 1) NP = 2;
-  int NB = (int)((budget - (size_t)NP * P.slot_bytes) / bB);
-  while (NB < 3 && NP > 2) { --NP; NB = (int)((budget - (size_t)NP * P.slot_bytes) / bB); }
-  if (NB < 2) return false;
-  if (NB > 8) NB = 8;
-  // spare room goes to a deeper plane ring (up to 4)
-  while (NP < 4 && (size_t)(NP + 1) * P.slot_bytes + (size_t)NB * bB <= budget) ++NP;
-  { const char* e = getenv("MRA_HALO_NB"); if (e && atoi(e) >= 2 && atoi(e) <= NB) NB = atoi(e); }
-  { const char* e = getenv("MRA_HALO_NP"); if (e && atoi(e) >= 2 && atoi(e) <= NP) NP = atoi(e); }
+  int NP, NB;
+  if (P.nsub == 2) {
+    NP = 4;                                      // two tiles per (chunk, td) step, two steps in flight (a step is 72 MMAs)
+    NB = (int)((budget - (size_t)NP * P.slot_bytes) / bB);
+    if (NB > 8) NB = 8;                          // (2 NP + 2 NB + 4 mbarriers must fit the 256 bytes behind the rings)
+  } else {
+    NP = kd >= 3 ? 3 : 2;
+    if (kd * P.kchunks == 1) NP = 2;
+    NB = (int)((budget - (size_t)NP * P.slot_bytes) / bB);
+    while (NB < 3 && NP > 2) { --NP; NB = (int)((budget - (size_t)NP * P.slot_bytes) / bB); }
+    if (NB < 2) return false;
+    if (NB > 8) NB = 8;
+    // spare room goes to a deeper plane ring (up to 4)
+    while (NP < 4 && (size_t)(NP + 1) * P.slot_bytes + (size_t)NB * bB <= budget) ++NP;
+    { const char* e = getenv("MRA_HALO_NB"); if (e && atoi(e) >= 2 && atoi(e) <= NB) NB = atoi(e); }
+    { const char* e = getenv("MRA_HALO_NP"); if (e && atoi(e) >= 2 && atoi(e) <= NP) NP = atoi(e); }
+  }
   P.NP = NP; P.NB = NB;
-  const long long total = (long long)n * (pair ? (P.Dl + 1) / 2 : P.Dl) * P.tiles_hw * P.n_tiles;
+  const long long total = (long long)n * (pair ? (P.Dl + 1) / 2 : P.Dl) * (P.tiles_hw / P.nsub) * P.n_tiles;
   if (total >= (1ll << 31)) return false;
   P.total_tiles = (int)total;
   // persistent schedule: `units` CTAs (or pairs) take work items round-robin.  When the last round is at most
@@ -506,7 +566,7 @@ inline int run_gather_halo(const GatherPlan& plan, const GatherLaunch& L, HaloP&
   P.stats = R.stats; P.aux = R.aux; P.aux_nslope = R.aux_nslope; P.err = tc_err_flag();
   { const char* e = getenv("MRA_GATHER_DEBUG"); P.debug = e ? atoi(e) : 0; }
   P.dbg = tc_dbg_counters();
-  P.tmem_cols = pow2_cols(2 * P.n_tile);
+  P.tmem_cols = pow2_cols(2 * P.n_tile * P.nsub);
   halo_fill_skip(P, plan.adims[0]);
   CUtensorMap tmA;
   if (int rc = make_act_map(&tmA, R.a, plan.n, plan.adims[0], plan.adims[1], plan.adims[2], plan.ck, P.Wb, P.Hb, 1, 1)) return rc;

@@ -544,22 +544,23 @@ int mra_debug_schedule(const mra_conv_desc* d, int which, int units, int single,
     int nu = units > 0 ? units : (pair ? num_sms() / 2 : num_sms());
     if (P.total_work < nu) nu = P.total_work;
     put((int)li); put(pair); put(P.mode); put(P.N); put(P.Dl); put(P.Hl); put(P.Wl); put(P.Wb); put(P.Cn); put(P.n_tile);
-    put(P.n_tiles); put(P.total_tiles); put(P.split_from); put(P.total_work); put(nu); put(P.skip); put(P.kd);
+    put(P.n_tiles); put(P.total_tiles); put(P.split_from); put(P.total_work); put(nu); put(P.skip); put(P.kd); put(P.nsub);
     const int at = n;
     put(0);
     int nrec = 0;
     for (int u = 0; u < nu; ++u)
       for (int r = 0; r < (pair ? 2 : 1); ++r)
-        for (int w = u; w < P.total_work; w += nu) {
-          const tc::HaloTile t = tc::halo_decode(P, w, pair, r);
-          int tb, coff;
-          tc::halo_stats_key(P, t, tb, coff);
-          int live = 0;
-          for (int td = 0; td < P.kd && td < 31; ++td) if (tc::halo_plane_live(P, t.d0, td, pair)) live |= 1 << td;
-          put(u); put(r); put(w); put(t.n); put(t.d); put(t.n0); put(t.width); put(t.h0); put(t.w0); put(t.f0); put(tb); put(coff);
-          put(live);
-          ++nrec;
-        }
+        for (int w = u; w < P.total_work; w += nu)
+          for (int sub = 0; sub < P.nsub; ++sub) {
+            const tc::HaloTile t = tc::halo_decode(P, w, pair, r, sub);
+            int tb, coff;
+            tc::halo_stats_key(P, t, tb, coff);
+            int live = 0;
+            for (int td = 0; td < P.kd && td < 31; ++td) if (tc::halo_plane_live(P, t.d0, td, pair)) live |= 1 << td;
+            put(u); put(r); put(w); put(t.n); put(t.d); put(t.n0); put(t.width); put(t.h0); put(t.w0); put(t.f0); put(tb); put(coff);
+            put(live); put(sub); put(t.rot_kc0 * 1000000 + t.rot_td0 * 10000 + t.rot_t);
+            ++nrec;
+          }
     if (at < cap) out[at] = nrec;
     ++nl;
   }

@@ -569,3 +569,54 @@ def test_halo_dead_plane_skipping_is_bit_identical(case, mode, monkeypatch):
     y_ref, _ = ref.conv_fprop(x.double(), w.double(), b.double(), g, want_stats=True)
     dx_ref = ref.conv_dgrad(dy.double(), w.double().transpose(1, 2).contiguous(), g, dims)
     assert rel_l2(y.cpu(), y_ref) < 1e-2 and rel_l2(dx.cpu(), dx_ref) < 1e-2
+
+
+DUAL_CASES = [
+    # (geom, in_dims, n, which)        launches whose tile count per plane is even: eligible for dual items
+    (ConvGeom(256, 256, 3, 1, 0), (18, 18, 18), 1, 0),         # fprop, 2D tiles (2 per plane)
+    (ConvGeom(256, 256, 3, 1, 0), (18, 18, 18), 3, 0),
+    (ConvGeom(256, 256, 3, 1, 0), (12, 12, 12), 2, 1),         # dgrad
+    (ConvGeom(256, 256, 3, 1, 0), (34, 34, 34), 2, 0),         # the bench's G.rb fprop (split tail items) ...
+    (ConvGeom(256, 256, 3, 1, 0), (34, 34, 34), 2, 1),         # ... and dgrad (flat tiles, dead planes)
+    (ConvGeom(256, 256, 3, 1, 0), (34, 34, 34), 3, 1),
+]
+
+
+@pytest.mark.parametrize("case", DUAL_CASES, ids=lambda c: gid(c[:3]) + "_" + "fd"[c[3]])
+def test_halo_dual_items_match_single_items_and_oracle(case, monkeypatch):
+    """MRA_HALO_DUAL=1: a work item of gather_halo_kernel is two position tiles x 128 channels (every weight slab feeds two
+    tiles) instead of one tile x 256.  Same sums in another order: against the default kernel to bf16 rounding, against the
+    fp64 oracle where it finishes in seconds; epilogue statistics (fprop) and norm-backward statistics (dgrad) included."""
+    g, dims, n, which = case
+    I = ops.impl()
+    ref = R.RefImpl(torch.float64)
+    small = dims[0] <= 18
+    x, w, b, dy = _conv_case(g, dims, n, torch.bfloat16, seed=3)
+    xd, wd, bd, dyd = x.cuda(), w.cuda(), b.cuda(), dy.cuda()
+    wT = I.pack_weight_t(wd, torch.bfloat16)
+
+    def run():
+        if which == 0:
+            y, st = I.conv_fprop(xd, wd, bd, g, want_stats=True)
+            return y, st
+        dx = I.conv_dgrad(dyd, wT, g, dims)
+        dx2, sums = I.conv_dgrad_nstats(dyd, wT, g, dims, xd, ops.ACT_RELU, 0.0)
+        assert bool((dx.float() == dx2.float()).all())
+        return dx, sums
+
+    monkeypatch.delenv("MRA_HALO_DUAL", raising=False)
+    a0, s0 = run()
+    monkeypatch.setenv("MRA_HALO_DUAL", "1")
+    words = ops.schedule_describe(g, n, dims, which)
+    assert words[0] == 1 and words[1] == 1 and words[2 + 17] == 2, "case is expected to run as dual items"
+    a1, s1 = run()
+    assert I.tc_error() == 0
+    assert rel_l2(a1.float().cpu(), a0.float().cpu()) < 4e-3
+    assert rel_l2(s1.cpu(), s0.cpu()) < 1e-3
+    if small:
+        if which == 0:
+            y_ref, st_ref = ref.conv_fprop(x.double(), w.double(), b.double(), g, want_stats=True)
+            assert rel_l2(a1.cpu(), y_ref) < 1e-2 and rel_l2(s1.cpu(), st_ref) < 1e-1
+        else:
+            dx_ref = ref.conv_dgrad(dy.double(), w.double().transpose(1, 2).contiguous(), g, dims)
+            assert rel_l2(a1.cpu(), dx_ref) < 1e-2

@@ -20,11 +20,12 @@ def parse_gather(words):
     assert words[0] == 1
     nl, p, out = words[1], 2, []
     for _ in range(nl):
-        keys = ("li pair mode N Dl Hl Wl Wb Cn n_tile n_tiles total_tiles split_from total_work units skip kd nrec").split()
+        keys = ("li pair mode N Dl Hl Wl Wb Cn n_tile n_tiles total_tiles split_from total_work units skip kd nsub "
+                "nrec").split()
         h = dict(zip(keys, words[p:p + len(keys)]))
         p += len(keys)
-        recs = [words[p + 13 * i: p + 13 * (i + 1)] for i in range(h["nrec"])]
-        p += 13 * h["nrec"]
+        recs = [words[p + 15 * i: p + 15 * (i + 1)] for i in range(h["nrec"])]
+        p += 15 * h["nrec"]
         h["recs"] = recs
         out.append(h)
     assert p == len(words)
@@ -55,21 +56,28 @@ def _ids(c):
     return "c%d-%d_k%d_p%d_%s_n%d_%s_u%d" % (g.cin, g.cout, g.k, g.pad, "x".join(map(str, dims)), n, "fdw"[which], units)
 
 
-@pytest.mark.parametrize("single", [False, True], ids=["pair", "single"])
+@pytest.mark.parametrize("form", ["pair", "single", "dual"])
 @pytest.mark.parametrize("case", HALO_CASES, ids=_ids)
-def test_gather_halo_schedule_covers_every_output_once_and_flushes_inside_the_buffer(case, single):
+def test_gather_halo_schedule_covers_every_output_once_and_flushes_inside_the_buffer(case, form, monkeypatch):
     g, dims, n, which, units = case
+    single = form == "single"
+    if form == "dual":
+        monkeypatch.setenv("MRA_HALO_DUAL", "1")      # two position tiles x 128 channels per work item (conv_tc_halo.cuh)
+    else:
+        monkeypatch.delenv("MRA_HALO_DUAL", raising=False)
     launches = parse_gather(ops.schedule_describe(g, n, dims, which, units=units, single=single))
     assert launches, "case is expected to run on gather_halo_kernel"
     for L in launches:
         pair = bool(L["pair"])
         assert pair == (not single)
+        assert L["nsub"] == (2 if form == "dual" and g.cout == 256 and g.cin == 256 and dims == (34, 34, 34) else L["nsub"])
+        assert L["nsub"] == 1 or (form == "dual" and L["n_tile"] == 128)
         Cn, n_tile = L["Cn"], L["n_tile"]
         assert Cn % n_tile == 0 and L["n_tiles"] == Cn // n_tile
         cover = {}
         per_cta = {}
-        for (unit, rank, work, nn, d, n0, width, h0, w0, f0, tb, coff, live) in L["recs"]:
-            assert 0 <= work < L["total_work"] and 0 <= nn < L["N"]
+        for (unit, rank, work, nn, d, n0, width, h0, w0, f0, tb, coff, live, sub, rot) in L["recs"]:
+            assert 0 <= work < L["total_work"] and 0 <= nn < L["N"] and 0 <= sub < L["nsub"]
             assert width in (n_tile, n_tile // 2) and (width == n_tile) == (work < L["split_from"])
             # channel range of the item and of the statistics flush it belongs to
             assert 0 <= n0 and n0 + width <= Cn
@@ -78,7 +86,11 @@ def test_gather_halo_schedule_covers_every_output_once_and_flushes_inside_the_bu
             assert live != 0, "a work item must keep at least one live input plane"
             if not L["skip"]:
                 assert live == (1 << L["kd"]) - 1
-            per_cta.setdefault((unit, rank), []).append((work, nn, tb))
+            if sub == 0:
+                per_cta.setdefault((unit, rank), []).append((work, nn, tb))
+                first = (nn, d, n0, width, tb, coff, live, rot)
+            else:                                   # dual items: same sample, plane, channels, planes and weight order
+                assert first == (nn, d, n0, width, tb, coff, live, rot)
             if d >= L["Dl"]:
                 assert pair and rank == 1 and d == L["Dl"] and L["Dl"] % 2 == 1     # the odd plane's partner: nothing stored
                 continue
@@ -99,16 +111,17 @@ def test_gather_halo_schedule_covers_every_output_once_and_flushes_inside_the_bu
             works = [w for (w, _, _) in items]
             assert works == sorted(works) and all(b - a == L["units"] for a, b in zip(works, works[1:]))
             keys = [(nn, tb) for (_, nn, tb) in items]
-            seen = []
-            for k in keys:
-                if not seen or seen[-1] != k:
-                    assert k not in seen, "a statistics key must not come back after it was flushed"
-                    seen.append(k)
+            if L["units"] % L["n_tiles"] == 0:      # (a grid that is no multiple of n_tiles alternates channel tiles: legal -- a
+                seen = []                           # flush ADDS -- but one flush per item; not the case on 148 SMs)
+                for k in keys:
+                    if not seen or seen[-1] != k:
+                        assert k not in seen, "a statistics key should not come back after it was flushed"
+                        seen.append(k)
         # both CTAs of a pair see the same items (the same weight slabs), planes 2q and 2q + 1
         if pair:
             by_work = {}
-            for (unit, rank, work, nn, d, n0, width, h0, w0, f0, tb, coff, live) in L["recs"]:
-                by_work.setdefault(work, {})[rank] = (unit, nn, d, n0, width, h0, w0, f0, live)
+            for (unit, rank, work, nn, d, n0, width, h0, w0, f0, tb, coff, live, sub, rot) in L["recs"]:
+                by_work.setdefault((work, sub), {})[rank] = (unit, nn, d, n0, width, h0, w0, f0, live, rot)
             for work, rr in by_work.items():
                 a, b = rr[0], rr[1]
                 assert a[0] == b[0] and a[1] == b[1] and b[2] == a[2] + 1 and a[2] % 2 == 0 and a[3:] == b[3:]
