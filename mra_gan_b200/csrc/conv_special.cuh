@@ -125,12 +125,20 @@ __global__ void __launch_bounds__(256) shift_sum_kernel(const bf16* __restrict__
     // Z lines are double-buffered: while line hz is being added up, line hz + 1 streams into the other buffer with
     // cp.async (4-byte pieces: the 33-word pitch that makes the column reads conflict-free is not 16-byte aligned; a
     // warp moves the 128 contiguous bytes of one position per instruction)
+    // (a warp copies whole positions -- 32 words -- and walks them with two pointer increments per copy: the first version
+    // recomputed (i >> 5) * 33 + (i & 31) and the 64-bit global address per element, 13 instructions per 4-byte copy, three
+    // times the cost of the additions the kernel is there for; ncu showed it no faster than its predecessor at 177 us)
     auto stage = [&](int hz, uint32_t* dst) {
       if (hz >= 0 && hz < Hz && hz <= hz_hi) {
-        const uint32_t* gl = reinterpret_cast<const uint32_t*>(Z + ((r * Hz + hz) * (long long)Wz) * 64);
-        for (int i = threadIdx.x; i < Wz * 32; i += blockDim.x) {
-          const uint32_t sa = (uint32_t)__cvta_generic_to_shared(dst + (i >> 5) * 33 + (i & 31));
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gl + i) : "memory");
+        const int nw = (int)(blockDim.x >> 5), wp = (int)(threadIdx.x >> 5), ln = (int)(threadIdx.x & 31);
+        const uint32_t* gp = reinterpret_cast<const uint32_t*>(Z + ((r * Hz + hz) * (long long)Wz) * 64) + wp * 32 + ln;
+        uint32_t sa = (uint32_t)__cvta_generic_to_shared(dst + wp * 33 + ln);
+        const uint32_t sstep = (uint32_t)nw * 33u * 4u;
+        const int gstep = nw * 32;
+#pragma unroll 4
+        for (int pz = wp; pz < Wz; pz += nw) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gp) : "memory");
+          sa += sstep; gp += gstep;
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
