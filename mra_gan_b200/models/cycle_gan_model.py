@@ -92,7 +92,7 @@ class CycleGANModel(BaseModel):
                 for m in net.conv_modules():
                     m.make_shadow(net.compute_dtype)
                 networks3D.set_fused_wgrad(net, True)       # parallel.attach() keeps it unless MRA_DP_FUSED_WGRAD=0
-        self.grad_sync = None        # set by parallel.DataParallelTrainer
+        self.grad_sync = None        # set by parallel.attach()
         self._graphs = None          # CUDA-graph replay of the step (enable_cuda_graphs)
 
     def set_input(self, input):
@@ -204,7 +204,8 @@ class CycleGANModel(BaseModel):
             gc.collect()
             torch.cuda.synchronize()
             # capture only records: each graph is replayed right after its capture to execute this step (the host
-            # side of optimizer.step() -- step counters, pinned hyper-parameters -- already ran during capture)
+            # side of optimizer.step() -- the step counters -- already ran during capture; Adam's own counter is bumped on the
+            # device by the captured mra_adam_advance)
             from .. import ops
             n0 = ops.impl().launch_count() if hasattr(ops.impl(), "launch_count") else 0
             mode = dict(capture_error_mode="thread_local") if self.grad_sync is not None else {}

@@ -227,7 +227,7 @@ def test_cyclegan_step_matches_golden(golden_dir, case, mode, tmp_path):
 
 
 def test_cuda_graph_step_matches_eager(tmp_path):
-    """enable_cuda_graphs(): the two-graph replay of the step (host-advanced Adam state, eager image pools) must
+    """enable_cuda_graphs(): the two-graph replay of the step (Adam's step counter advanced on the device by the captured graph, eager image pools) must
     reproduce the eager step sequence (same kernels in the same order -> same bits up to atomics order)."""
     N3.set_default_compute_dtype(torch.bfloat16)
     runs = []
