@@ -10,7 +10,10 @@
  *     frees device memory that outlives a call), all launches go to the `stream` argument, no host
  *     synchronisation inside, re-entrant across streams.
  *   - return value 0 = success, negative = error; mra_last_error() gives the message for the
- *     calling thread.  Nothing throws across the ABI.
+ *     calling thread.  Nothing throws across the ABI.  Descriptors are validated (sizes, stride,
+ *     dtype, consistent output dims) and the mandatory operands of the conv entry points are
+ *     checked for NULL on the host BEFORE any CUDA call is made: a rejected call has not touched
+ *     the device.  Optional operands (bias, stats, dw / dbias, workspace of size 0) may be NULL.
  *   - activations are channels-last: [N][D][H][W][C] contiguous, element type `dtype`
  *     (MRA_F32 or MRA_BF16); accumulation is always fp32 (statistics fp64).
  *   - conv weights are "packed": [kD*kH*kW][Cout][Cin] (tap-major, Cin contiguous) where Cout/Cin

@@ -28,6 +28,7 @@ static int check_conv(const mra_conv_desc* d) {
   MRA_REQUIRE(d != nullptr, "null conv descriptor");
   MRA_REQUIRE(d->n > 0 && d->cin > 0 && d->cout > 0 && d->k > 0, "bad conv sizes");
   MRA_REQUIRE(d->stride == 1 || d->stride == 2, "stride must be 1 or 2 (got %d)", d->stride);
+  MRA_REQUIRE(d->dtype == MRA_F32 || d->dtype == MRA_BF16, "unknown dtype %d", (int)d->dtype);
   const int in[3] = {d->din, d->hin, d->win}, out[3] = {d->dout, d->hout, d->wout};
   for (int i = 0; i < 3; ++i) {
     MRA_REQUIRE(in[i] > 0 && out[i] > 0, "bad conv spatial dims");
@@ -92,6 +93,7 @@ int mra_conv3d_uses_tensor_cores(const mra_conv_desc* d, int which) {
 int mra_conv3d_fprop(const mra_conv_desc* d, const void* x, const void* w, const float* bias, void* y, double* stats,
                      void* workspace, size_t workspace_bytes, mra_stream_t stream) {
   if (int rc = check_conv(d)) return rc;
+  MRA_REQUIRE(x != nullptr && w != nullptr && y != nullptr, "mra_conv3d_fprop: null operand (x, w and y are mandatory)");
   cudaStream_t st = (cudaStream_t)stream;
   if (stats) MRA_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * d->n * d->cout, st));
   if (special::im2col_eligible(*d)) return special::im2col_fprop(*d, x, w, bias, y, stats, workspace, workspace_bytes, st);
@@ -126,6 +128,7 @@ int mra_conv3d_fprop(const mra_conv_desc* d, const void* x, const void* w, const
 int mra_conv3d_dgrad(const mra_conv_desc* d, const void* dy, const void* wT, void* dx, void* workspace,
                      size_t workspace_bytes, mra_stream_t stream) {
   if (int rc = check_conv(d)) return rc;
+  MRA_REQUIRE(dy != nullptr && wT != nullptr && dx != nullptr, "mra_conv3d_dgrad: null operand (dy, wT and dx are mandatory)");
   cudaStream_t st = (cudaStream_t)stream;
   if (special::im2col_eligible(*d)) return special::im2col_dgrad(*d, dy, wT, dx, workspace, workspace_bytes, st);
   if (special::convT1_eligible(*d))
@@ -153,6 +156,7 @@ int mra_conv3d_dgrad_nstats_supported(const mra_conv_desc* d) { return d && dgra
 int mra_conv3d_dgrad_nstats(const mra_conv_desc* d, const void* dy, const void* wT, void* dx, const void* y_act, int norm_act,
                             float norm_slope, double* sums, void* workspace, size_t workspace_bytes, mra_stream_t stream) {
   if (int rc = check_conv(d)) return rc;
+  MRA_REQUIRE(dy != nullptr && wT != nullptr && dx != nullptr, "mra_conv3d_dgrad_nstats: null operand (dy, wT and dx are mandatory)");
   MRA_REQUIRE(y_act != nullptr && sums != nullptr, "dgrad_nstats needs the norm output and a sums buffer");
   MRA_REQUIRE(dgrad_nstats_ok(*d), "this layer's dgrad does not run on the tensor-core gather kernels");
   float nslope;
@@ -170,6 +174,7 @@ int mra_conv3d_dgrad_nstats(const mra_conv_desc* d, const void* dy, const void* 
 int mra_conv3d_wgrad(const mra_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias,
                      void* workspace, size_t workspace_bytes, mra_stream_t stream) {
   if (int rc = check_conv(d)) return rc;
+  MRA_REQUIRE(dy != nullptr && (x != nullptr || dw == nullptr), "mra_conv3d_wgrad: null operand (dy always, x when dw is asked for)");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t wn = (size_t)d->k * d->k * d->k * d->cout * d->cin;
   if (!(d->flags & MRA_CONV_ACCUMULATE)) {

@@ -48,6 +48,33 @@ def test_host_side_argument_validation():
     assert L.mra_conv_plan_describe(ctypes.byref(d), 0, buf, 16) == -2     # buffer too small
 
 
+def test_null_operands_and_bad_dtype_are_rejected_on_the_host():
+    """The conv entry points return an error code for a NULL mandatory operand or an unknown dtype before any CUDA call
+    (this box has no GPU: a rejected call must not have needed one); nothing is launched."""
+    L = _lib.lib()
+    d = _lib.ConvDesc()
+    d.n, d.cin, d.cout, d.k, d.stride, d.pad = 1, 4, 4, 3, 1, 1
+    d.din = d.hin = d.win = d.dout = d.hout = d.wout = 8
+    n0 = L.mra_debug_launch_count()
+    one = ctypes.c_void_p(0x1000)                # never dereferenced: the calls fail on the NULL next to it
+    assert L.mra_conv3d_fprop(ctypes.byref(d), None, one, None, one, None, None, 0, None) < 0
+    assert b"mra_conv3d_fprop: null operand" in L.mra_last_error()
+    assert L.mra_conv3d_fprop(ctypes.byref(d), one, one, None, None, None, None, 0, None) < 0
+    assert L.mra_conv3d_dgrad(ctypes.byref(d), one, None, one, None, 0, None) < 0
+    assert b"mra_conv3d_dgrad: null operand" in L.mra_last_error()
+    assert L.mra_conv3d_dgrad_nstats(ctypes.byref(d), None, one, one, one, 0, 0.0, one, None, 0, None) < 0
+    assert b"mra_conv3d_dgrad_nstats: null operand" in L.mra_last_error()
+    assert L.mra_conv3d_wgrad(ctypes.byref(d), one, None, one, None, None, 0, None) < 0
+    assert L.mra_conv3d_wgrad(ctypes.byref(d), None, one, one, None, None, 0, None) < 0      # dw asked for without x
+    assert b"mra_conv3d_wgrad: null operand" in L.mra_last_error()
+    d.dtype = 7
+    assert L.mra_conv3d_fprop(ctypes.byref(d), one, one, None, one, None, None, 0, None) < 0
+    assert b"unknown dtype 7" in L.mra_last_error()
+    assert L.mra_conv3d_fprop(None, one, one, None, one, None, None, 0, None) < 0
+    assert b"null conv descriptor" in L.mra_last_error()
+    assert L.mra_debug_launch_count() == n0
+
+
 def test_sass_contains_blackwell_tensor_core_and_tma_instructions():
     import shutil
     import subprocess
